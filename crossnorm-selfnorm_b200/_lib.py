@@ -1,0 +1,278 @@
+"""ctypes binding of libcnsn_b200.so (the C ABI in include/cnsn_b200.h) and the tensor-level backend.
+
+There is NO fallback here: if the shared library is missing this module raises, and every
+operator raises on non-CUDA tensors.  ``set_backend_for_tests`` exists so that the CPU test-suite
+can exercise the host logic (RNG order, ``.active`` protocol, autograd wiring) against a stand-in;
+the package itself never installs one.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_longlong, c_size_t, c_ulonglong, c_void_p
+
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libcnsn_b200.so")
+
+CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
+CNSN_E_BATCH1 = -3
+ABI_VERSION = 2
+
+_DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
+
+
+class GateParams(Structure):       # struct cnsn_gate_params
+    _fields_ = [("w", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
+                ("run_mean", c_void_p), ("run_var", c_void_p), ("nbt", c_void_p)]
+
+
+class GateGrads(Structure):        # struct cnsn_gate_grads
+    _fields_ = [("dw", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p)]
+
+
+_I4 = c_int * 4
+_DIMS = [c_int, c_int, c_int, c_int]
+
+# name -> (restype, argtypes); must list every symbol include/cnsn_b200.h declares
+SIGNATURES = {
+    "cnsn_version": (c_int, []),
+    "cnsn_error_string": (c_char_p, [c_int]),
+    "cnsn_launch_count": (c_ulonglong, []),
+    "cnsn_instance_stats": (c_int, [c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int, c_float,
+                                    c_void_p, c_void_p, c_void_p]),
+    "cnsn_instance_stats_bwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnsn_instance_affine": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p, c_void_p]),
+    "cnsn_instance_dot": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p, c_void_p]),
+    "cnsn_selfnorm_save_floats": (c_size_t, [c_int, c_int, c_int]),
+    "cnsn_selfnorm_workspace_floats": (c_size_t, [c_int, c_int, c_int]),
+    "cnsn_selfnorm_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, POINTER(GateParams), POINTER(GateParams),
+                                  c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_selfnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS,
+                                  POINTER(GateParams), POINTER(GateParams), c_int, c_void_p,
+                                  POINTER(GateGrads), POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_crossnorm_workspace_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_crossnorm_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p,
+                                   POINTER(c_int), POINTER(c_int), c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_crossnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p,
+                                   POINTER(c_int), POINTER(c_int), c_float, c_void_p, c_void_p, c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the ctypes handle.  Raises if the library has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "cnsn_b200: %s is missing. Build it with `python crossnorm-selfnorm_b200/build.py` "
+                "(or __graft_entry__.build()). There is no CPU / PyTorch fallback." % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype, fn.argtypes = res, args
+        if h.cnsn_version() != ABI_VERSION:
+            raise RuntimeError("cnsn_b200: ABI mismatch (library %d, binding %d); rebuild" %
+                               (h.cnsn_version(), ABI_VERSION))
+        _lib = h
+    return _lib
+
+
+def launch_count():
+    return int(lib().cnsn_launch_count())
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = lib().cnsn_error_string(rc).decode()
+    if rc == CNSN_E_BATCH1:          # what nn.BatchNorm1d raises inside the reference SelfNorm
+        raise ValueError(msg)
+    raise RuntimeError("cnsn_b200 error %d: %s" % (rc, msg))
+
+
+def _dtype_code(t):
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError("cnsn_b200 supports float32 / bfloat16 / float16 tensors, got %s" % t.dtype)
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cnsn_b200 operators run only on CUDA tensors (B200, sm_100a); got a %s "
+                               "tensor. There is no CPU fallback." % t.device)
+
+
+def _stream(t):
+    return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _p(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+def _f32(t):
+    """fp32 contiguous view of a parameter / buffer (copy only when needed)."""
+    if t.dtype == torch.float32 and t.is_contiguous():
+        return t
+    return t.detach().to(torch.float32).contiguous()
+
+
+class GateTensors:
+    """One SelfNorm gate branch: Conv1d weight (C,1,2), BatchNorm1d affine and buffers."""
+    __slots__ = ("w", "gamma", "beta", "run_mean", "run_var", "nbt")
+
+    def __init__(self, w, gamma, beta, run_mean, run_var, nbt):
+        self.w, self.gamma, self.beta = w, gamma, beta
+        self.run_mean, self.run_var, self.nbt = run_mean, run_var, nbt
+
+
+class CudaBackend:
+    """Tensor-level calls into the C ABI.  Inputs are dense NCHW CUDA tensors."""
+
+    name = "cuda"
+
+    # -- statistics ---------------------------------------------------------------------
+    def instance_stats(self, x, window, eps):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        std = torch.empty_like(mean)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_instance_stats(_p(x), _dtype_code(x), N, C, H, W, *window, eps,
+                                             _p(mean), _p(std), _stream(x)))
+        return mean, std
+
+    def instance_stats_bwd(self, x, window, mean, std, dmean, dstd):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_instance_stats_bwd(_p(x), _p(dx), _dtype_code(x), N, C, H, W, *window,
+                                                 _p(mean), _p(std), _p(dmean), _p(dstd), _stream(x)))
+        return dx
+
+    def instance_affine(self, x, scale, shift):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_instance_affine(_p(x), _p(out), _dtype_code(x), N, C, H, W,
+                                              _p(scale), _p(shift), _stream(x)))
+        return out
+
+    def instance_dot(self, x, dy):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        sxy = torch.empty((N, C), dtype=torch.float32, device=x.device)
+        st = torch.empty_like(sxy)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_instance_dot(_p(x), _p(dy), _dtype_code(x), N, C, H, W, _p(sxy), _p(st), _stream(x)))
+        return sxy, st
+
+    # -- SelfNorm -------------------------------------------------------------------------
+    @staticmethod
+    def _gate_struct(g, keep):
+        if g is None:
+            return None
+        w, ga, be = _f32(g.w), _f32(g.gamma), _f32(g.beta)
+        rm = _f32(g.run_mean) if g.run_mean is not None else None
+        rv = _f32(g.run_var) if g.run_var is not None else None
+        keep.extend([w, ga, be, rm, rv])
+        return GateParams(_p(w).value, _p(ga).value, _p(be).value, _p(rm).value, _p(rv).value,
+                          _p(g.nbt).value), rm, rv
+
+    def selfnorm_fwd(self, x, g, f, training, momentum, bn_eps, eps):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        two = f is not None
+        keep = []
+        gs, g_rm, g_rv = self._gate_struct(g, keep)
+        fs, f_rm, f_rv = self._gate_struct(f, keep) if two else (None, None, None)
+        save = torch.empty(lib().cnsn_selfnorm_save_floats(N, C, int(two)), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_selfnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W,
+                                           ctypes.byref(gs), ctypes.byref(fs) if two else None,
+                                           int(training), momentum, bn_eps, eps, _p(save), _stream(x)))
+        if training:                     # buffers that were not fp32-contiguous get written back
+            for gate, rm, rv in ((g, g_rm, g_rv), (f, f_rm, f_rv)):
+                if gate is not None:
+                    if rm is not gate.run_mean:
+                        gate.run_mean.copy_(rm)
+                    if rv is not gate.run_var:
+                        gate.run_var.copy_(rv)
+        return y, save
+
+    def selfnorm_bwd(self, x, dy, g, f, training, save):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        two = f is not None
+        keep = []
+        gs, _, _ = self._gate_struct(g, keep)
+        fs = self._gate_struct(f, keep)[0] if two else None
+        dev = x.device
+
+        def grad_block():                # one allocation per gate: dw (C,2) | dgamma (C) | dbeta (C)
+            buf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+            return buf[:2 * C].view(C, 2), buf[2 * C:3 * C], buf[3 * C:]
+
+        out_g = grad_block()
+        out_f = grad_block() if two else None
+        gg = GateGrads(*[_p(t).value for t in out_g])
+        gf = GateGrads(*[_p(t).value for t in out_f]) if two else None
+        ws = torch.empty(lib().cnsn_selfnorm_workspace_floats(N, C, int(two)), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        with torch.cuda.device(dev):
+            _check(lib().cnsn_selfnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,
+                                           ctypes.byref(gs), ctypes.byref(fs) if two else None,
+                                           int(training), _p(save),
+                                           ctypes.byref(gg), ctypes.byref(gf) if two else None,
+                                           _p(ws), _stream(x)))
+        return dx, out_g, out_f
+
+    # -- CrossNorm ------------------------------------------------------------------------
+    def crossnorm_fwd(self, x, perm, chan_perm, cwin, swin, lam, eps):
+        _require_cuda(x, perm, chan_perm)
+        N, C, H, W = x.shape
+        save = torch.empty(lib().cnsn_crossnorm_save_floats(N, C), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_crossnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, _p(perm), _p(chan_perm),
+                                            _I4(*cwin), _I4(*swin), lam, eps, _p(save), _stream(x)))
+        return y, save
+
+    def crossnorm_bwd(self, x, dy, perm, chan_perm, cwin, swin, lam, save):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        ws = torch.empty(lib().cnsn_crossnorm_workspace_floats(N, C), dtype=torch.float32, device=x.device)
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _check(lib().cnsn_crossnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,
+                                            _p(perm), _p(chan_perm), _I4(*cwin), _I4(*swin), lam,
+                                            _p(save), _p(ws), _stream(x)))
+        return dx
+
+
+_backend = None
+
+
+def backend():
+    global _backend
+    if _backend is None:
+        lib()                        # fail loudly if the CUDA library is not built
+        _backend = CudaBackend()
+    return _backend
+
+
+def set_backend_for_tests(b):
+    """TEST HOOK ONLY: swap the tensor-level backend (pass None to restore the CUDA one)."""
+    global _backend
+    old = _backend
+    _backend = b
+    return old

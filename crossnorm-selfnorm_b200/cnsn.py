@@ -1,0 +1,160 @@
+"""Drop-in replacement for the reference's ``models/cnsn.py`` (amazon-science/crossnorm-selfnorm).
+
+Same public names, constructor signatures, ``state_dict`` keys, ``.active`` protocol and host-side
+RNG consumption as the reference, so the reference's unmodified WideResNet / ResNeXt / ResNet-50
+files work with it (``sys.modules['models.cnsn'] = cnsn_b200.cnsn`` or copy it over the file).
+Everything that touches a feature map runs in hand-written sm_100a CUDA kernels behind the C ABI in
+``include/cnsn_b200.h``; there is no PyTorch / CPU fallback.
+
+Reference lines (relative to the reference checkout) are cited per symbol.
+"""
+import functools
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .functional import CrossNormFn, InstanceAffine, InstanceStats, SelfNormFn
+
+__all__ = ["calc_ins_mean_std", "instance_norm_mix", "cn_rand_bbox", "cn_op_2ins_space_chan",
+           "CrossNorm", "SelfNorm", "CNSN"]
+
+_CROPS = ("neither", "style", "content", "both")
+
+
+def _full(x):
+    return (0, x.size(2), 0, x.size(3))
+
+
+def calc_ins_mean_std(x, eps=1e-5):
+    """Per-instance mean and sqrt(unbiased var + eps), each (N,C,1,1).  models/cnsn.py:8-17."""
+    assert x.dim() == 4                                   # :12
+    N, C = x.shape[:2]
+    mean, std = InstanceStats.apply(x, _full(x), float(eps))
+    return mean.to(x.dtype).view(N, C, 1, 1), std.to(x.dtype).view(N, C, 1, 1)
+
+
+def instance_norm_mix(content_feat, style_feat):
+    """Replace content statistics with style statistics.  models/cnsn.py:20-29 (eps 1e-5)."""
+    assert content_feat.size()[:2] == style_feat.size()[:2]                    # :22
+    s_mean, s_std = InstanceStats.apply(style_feat, _full(style_feat), 1e-5)
+    c_mean, c_std = InstanceStats.apply(content_feat, _full(content_feat), 1e-5)
+    scale = s_std / c_std                                  # O(N*C) glue; the planes go through the kernels
+    return InstanceAffine.apply(content_feat, scale, s_mean - c_mean * scale)
+
+
+def cn_rand_bbox(size, beta, bbx_thres):
+    """Sample a crop box; same draws, same order, same return convention as models/cnsn.py:32-55:
+    (bbx1, bby1, bbx2, bby2) with bbx* indexing dim 2 and bby* dim 3.  (The reference's ``np.int``
+    is spelled ``int`` here; NumPy >= 1.24 removed the alias.)"""
+    d2, d3 = size[2], size[3]
+    while True:
+        ratio = np.random.beta(beta, beta)
+        side = np.sqrt(ratio)
+        ext2, ext3 = int(d2 * side), int(d3 * side)
+        c2 = np.random.randint(d2)
+        c3 = np.random.randint(d3)
+        bbx1, bbx2 = np.clip(c2 - ext2 // 2, 0, d2), np.clip(c2 + ext2 // 2, 0, d2)
+        bby1, bby2 = np.clip(c3 - ext3 // 2, 0, d3), np.clip(c3 + ext3 // 2, 0, d3)
+        if float(bbx2 - bbx1) * (bby2 - bby1) / (d2 * d3) > bbx_thres:
+            return bbx1, bby1, bbx2, bby2
+
+
+def _to_device_i32(idx, device):
+    """Upload a host permutation without the reference's blocking pageable copy (:62)."""
+    host = idx.to(torch.int32)
+    if device.type == "cuda":
+        host = host.pin_memory()
+    return host.to(device, non_blocking=True)
+
+
+def cn_op_2ins_space_chan(x, crop='neither', beta=1, bbx_thres=0.1, lam=None, chan=False):
+    """2-instance CrossNorm with optional crops, channel permutation and lam blend.
+
+    models/cnsn.py:58-91.  The host draws exactly what the reference draws, in its order
+    (SURVEY.md A.3): randperm(N) on the CPU generator, style box, randperm(C), content box; the
+    device work (two statistics sets, permuted restyle, copy-through outside the content box) is one
+    fused CUDA forward and one fused backward.
+    """
+    assert crop in _CROPS                                   # :61
+    assert x.dim() == 4
+    N, C, H, W = x.shape
+    perm = torch.randperm(N)                                # :62
+    swin = cwin = (0, H, 0, W)
+    if crop in ('style', 'both'):                           # :64-66
+        a1, b1, a2, b2 = cn_rand_bbox(x.size(), beta=beta, bbx_thres=bbx_thres)
+        swin = (int(a1), int(a2), int(b1), int(b2))
+    chan_perm = torch.randperm(C) if chan else None         # :70-72
+    if crop in ('content', 'both'):                         # :74-77
+        a1, b1, a2, b2 = cn_rand_bbox(x.size(), beta=beta, bbx_thres=bbx_thres)
+        cwin = (int(a1), int(a2), int(b1), int(b2))
+    perm_d = _to_device_i32(perm, x.device)
+    cperm_d = _to_device_i32(chan_perm, x.device) if chan else None
+    return CrossNormFn.apply(x, perm_d, cperm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5)
+
+
+class CrossNorm(nn.Module):
+    """CrossNorm module.  models/cnsn.py:94-110: runs only when training and ``active``; ``active``
+    is a one-shot flag the host model sets and every forward resets.  No parameters or buffers."""
+
+    def __init__(self, crop=None, beta=None):
+        super().__init__()
+        self.active = False
+        self.cn_op = functools.partial(cn_op_2ins_space_chan, crop=crop, beta=beta)
+
+    def forward(self, x):
+        if self.training and self.active:
+            x = self.cn_op(x)
+        self.active = False
+        return x
+
+
+class SelfNorm(nn.Module):
+    """SelfNorm module.  models/cnsn.py:113-150.
+
+    The parameters live in sub-modules named and constructed exactly as in the reference
+    (``g_fc``: depthwise Conv1d k=2 without bias, ``g_bn``: BatchNorm1d; ``f_*`` twins when
+    ``is_two``) so initialisation consumes the same RNG draws and ``state_dict()`` keys / shapes
+    match; those sub-modules are never called -- one fused kernel sequence reads their tensors.
+    """
+
+    def __init__(self, chan_num, is_two=False):
+        super().__init__()
+        self.g_fc = nn.Conv1d(chan_num, chan_num, kernel_size=2, bias=False, groups=chan_num)
+        self.g_bn = nn.BatchNorm1d(chan_num)
+        if is_two is True:
+            self.f_fc = nn.Conv1d(chan_num, chan_num, kernel_size=2, bias=False, groups=chan_num)
+            self.f_bn = nn.BatchNorm1d(chan_num)
+        else:
+            self.f_fc = None
+
+    @staticmethod
+    def _bufs(bn):
+        return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
+
+    def forward(self, x):
+        assert x.dim() == 4
+        bn = self.g_bn
+        args = [x, bn.training, float(bn.momentum), float(bn.eps), 1e-12,          # eps :133
+                self._bufs(bn), self._bufs(self.f_bn) if self.f_fc is not None else None,
+                self.g_fc.weight, bn.weight, bn.bias]
+        if self.f_fc is not None:
+            args += [self.f_fc.weight, self.f_bn.weight, self.f_bn.bias]
+        return SelfNormFn.apply(*args)
+
+
+class CNSN(nn.Module):
+    """CrossNorm then SelfNorm; either may be None.  models/cnsn.py:152-164."""
+
+    def __init__(self, crossnorm, selfnorm):
+        super().__init__()
+        self.crossnorm = crossnorm
+        self.selfnorm = selfnorm
+
+    def forward(self, x):
+        if self.crossnorm and self.crossnorm.active:
+            x = self.crossnorm(x)
+        if self.selfnorm:
+            x = self.selfnorm(x)
+        return x

@@ -1,0 +1,344 @@
+// selfnorm.cu -- SelfNorm forward / backward (models/cnsn.py:113-150 and its autograd), v1:
+// three stream-ordered kernels per direction.
+//
+//   forward : instance stats (1 read of x)  ->  gate (O(N*C))  ->  y = x*g (+ mu*(f-g))   (read x, write y)
+//   backward: per-instance sum(dy*x), sum(dy) (read x, dy) -> gate backward (O(N*C)) -> dx = g*dy + b*x + c
+//
+// Roofline: HBM.  Algorithmic bytes: forward 2*S, backward 3*S (S = N*C*H*W*sizeof(T)); this
+// three-kernel form moves 3*S and 5*S, the fused persistent kernels (selfnorm_fused.cu) remove the
+// re-reads.  The gate couples all N instances of a channel (BatchNorm1d over the batch, :121,:138),
+// which is why a reduction phase must complete for the whole channel before any element of it
+// can be written.
+#include "common.cuh"
+
+namespace cnsn {
+
+constexpr int kGateCh = 32;   // channels per gate CTA (threadIdx.x)
+constexpr int kGateRows = 8;  // batch-strided rows per gate CTA (threadIdx.y)
+
+struct GateFwd {              // one gate branch (g or f) as seen by the forward gate kernel
+    const float* w; const float* gamma; const float* beta;
+    float* run_mean; float* run_var; long long* nbt;
+    float* gate; float* shat; float* r;     // outputs into the save block
+};
+struct GateBwd {
+    const float* w; const float* gamma;
+    const float* gate; const float* shat; const float* r;
+    float* dw; float* dgamma; float* dbeta;
+};
+
+// Sum over threadIdx.y for every threadIdx.x column; result broadcast to all rows.
+template <int K>
+__device__ __forceinline__ void column_sums(float (&v)[K], float (*sm)[kGateRows][kGateCh + 1]) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) sm[k][threadIdx.y][threadIdx.x] = v[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < kGateRows; ++j) s += sm[k][j][threadIdx.x];
+        v[k] = s;
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_acc(float z) { return 1.f / (1.f + expf(-z)); }
+
+// grid = (ceil(C/32), n_gates); block = (32, 8)
+__global__ void __launch_bounds__(kGateCh * kGateRows)
+k_sn_gate_fwd(const float* __restrict__ mu, const float* __restrict__ sd, GateFwd g0, GateFwd g1,
+              int N, int C, int training, float momentum, float bn_eps) {
+    __shared__ float sm[1][kGateRows][kGateCh + 1];
+    const GateFwd g = blockIdx.y == 0 ? g0 : g1;
+    const int c = blockIdx.x * kGateCh + threadIdx.x;
+    const bool live = c < C;
+    const float w0 = live ? g.w[2 * c] : 0.f, w1 = live ? g.w[2 * c + 1] : 0.f;
+    float m, q;
+    if (training) {
+        float acc[1] = {0.f};
+        if (live) for (int n = threadIdx.y; n < N; n += kGateRows)
+            acc[0] += fmaf(w0, mu[(size_t)n * C + c], w1 * sd[(size_t)n * C + c]);
+        column_sums<1>(acc, sm);
+        m = acc[0] / N;
+        acc[0] = 0.f;
+        if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+            const float d = fmaf(w0, mu[(size_t)n * C + c], w1 * sd[(size_t)n * C + c]) - m;
+            acc[0] = fmaf(d, d, acc[0]);
+        }
+        column_sums<1>(acc, sm);
+        q = acc[0] / N;                      // biased variance normalises (BatchNorm semantics)
+        if (live && threadIdx.y == 0) {
+            g.run_mean[c] = (1.f - momentum) * g.run_mean[c] + momentum * m;
+            g.run_var[c] = (1.f - momentum) * g.run_var[c] + momentum * (q * N / (N - 1.f));
+        }
+        if (g.nbt && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *g.nbt += 1;
+    } else {
+        m = live ? g.run_mean[c] : 0.f;
+        q = live ? g.run_var[c] : 1.f;
+    }
+    if (!live) return;
+    const float r = 1.f / sqrtf(q + bn_eps);
+    const float ga = g.gamma[c], be = g.beta[c];
+    if (threadIdx.y == 0) g.r[c] = r;
+    for (int n = threadIdx.y; n < N; n += kGateRows) {
+        const size_t i = (size_t)n * C + c;
+        const float sh = (fmaf(w0, mu[i], w1 * sd[i]) - m) * r;
+        g.shat[i] = sh;
+        g.gate[i] = sigmoidf_acc(fmaf(ga, sh, be));
+    }
+}
+
+// y = x*g                       (one gate)
+// y = x*g + mu*(f-g)            (is_two, models/cnsn.py:148)
+template <typename T, int TPI, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+k_sn_apply_fwd(const T* __restrict__ x, T* __restrict__ y, long long instances, int M,
+               const float* __restrict__ gate, const float* __restrict__ fgate,
+               const float* __restrict__ mu) {
+    const long long inst = Team<TPI>::instance();
+    if (inst >= instances) return;
+    const float a = gate[inst];
+    const float b = fgate ? mu[inst] * (fgate[inst] - a) : 0.f;
+    plane_map<T, TPI, VEC, false>(x + inst * M, nullptr, y + inst * M, M,
+                                  [=](float xv, float, int) { return fmaf(a, xv, b); });
+}
+
+// Per instance: sxy = sum dy*x  (CENTER: sum dy*(x-mu), for the is_two form) and t = sum dy.
+template <typename T, int TPI, bool VEC, bool CENTER>
+__global__ void __launch_bounds__(kBlock)
+k_sn_reduce_bwd(const T* __restrict__ x, const T* __restrict__ dy, long long instances, int M,
+                const float* __restrict__ mu, float* __restrict__ sxy, float* __restrict__ st) {
+    __shared__ float scratch[kWarpsPerBlock];
+    const long long inst = Team<TPI>::instance();
+    if (inst >= instances) return;
+    const T* px = x + inst * M;
+    const T* pd = dy + inst * M;
+    const float mean = CENTER ? mu[inst] : 0.f;
+    const int r = Team<TPI>::rank();
+    float a = 0.f, t = 0.f;
+    if (VEC) {
+        constexpr int V = VecOf<T>::n;
+        constexpr int U = 2;
+        const uint4* vx = reinterpret_cast<const uint4*>(px);
+        const uint4* vd = reinterpret_cast<const uint4*>(pd);
+        const int nv = M / V;
+        for (int i = r; i < nv; i += TPI * U) {
+            uint4 rx[U], rd[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * TPI < nv) { rx[u] = ldg_stream(vx + i + u * TPI); rd[u] = ldg_stream(vd + i + u * TPI); }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (i + u * TPI < nv) {
+                    float fx[V], fd[V];
+                    unpack<T>(rx[u], fx);
+                    unpack<T>(rd[u], fd);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) { a = fmaf(fd[j], fx[j] - mean, a); t += fd[j]; }
+                }
+        }
+    } else {
+#pragma unroll 4
+        for (int i = r; i < M; i += TPI) {
+            const float d = to_f(pd[i]);
+            a = fmaf(d, to_f(px[i]) - mean, a);
+            t += d;
+        }
+    }
+    a = Team<TPI>::all_sum(a, scratch);
+    t = Team<TPI>::all_sum(t, scratch);
+    if (r == 0) { sxy[inst] = a; st[inst] = t; }
+}
+
+// Gate backward for one tile of 32 channels.  Produces the parameter gradients and the two
+// per-instance coefficients of  dx = g*dy + cb*x + cc   (cb = b, cc = a - b*mu).
+// grid = ceil(C/32); block = (32, 8)
+__global__ void __launch_bounds__(kGateCh * kGateRows)
+k_sn_gate_bwd(const float* __restrict__ mu, const float* __restrict__ sd,
+              const float* __restrict__ sxy, const float* __restrict__ st,
+              GateBwd g, GateBwd f, int two, int N, int C, int M, int training,
+              float* __restrict__ cb, float* __restrict__ cc) {
+    __shared__ float sm[4][kGateRows][kGateCh + 1];
+    const int c = blockIdx.x * kGateCh + threadIdx.x;
+    const bool live = c < C;
+    const float invN = 1.f / N;
+    // pass A: dgamma = sum dz*shat, dbeta = sum dz for each gate
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+        const size_t i = (size_t)n * C + c;
+        const float gg = g.gate[i];
+        if (!two) {
+            const float dz = sxy[i] * gg * (1.f - gg);
+            acc[0] = fmaf(dz, g.shat[i], acc[0]); acc[1] += dz;
+        } else {                             // sxy holds sum dy*(x-mu): dgate_g = that, dgate_f = mu*T
+            const float ff = f.gate[i];
+            const float dzg = sxy[i] * gg * (1.f - gg);
+            const float dzf = mu[i] * st[i] * ff * (1.f - ff);
+            acc[0] = fmaf(dzg, g.shat[i], acc[0]); acc[1] += dzg;
+            acc[2] = fmaf(dzf, f.shat[i], acc[2]); acc[3] += dzf;
+        }
+    }
+    column_sums<4>(acc, sm);
+    const float dgam_g = acc[0], dbet_g = acc[1], dgam_f = acc[2], dbet_f = acc[3];
+    float gw0 = 0.f, gw1 = 0.f, gga = 0.f, gr = 0.f, fw0 = 0.f, fw1 = 0.f, fga = 0.f, fr = 0.f;
+    if (live) {
+        gw0 = g.w[2 * c]; gw1 = g.w[2 * c + 1]; gga = g.gamma[c]; gr = g.r[c];
+        if (two) { fw0 = f.w[2 * c]; fw1 = f.w[2 * c + 1]; fga = f.gamma[c]; fr = f.r[c]; }
+        if (threadIdx.y == 0) {
+            g.dgamma[c] = dgam_g; g.dbeta[c] = dbet_g;
+            if (two) { f.dgamma[c] = dgam_f; f.dbeta[c] = dbet_f; }
+        }
+    }
+    // pass B: ds, dw = (sum ds*mu, sum ds*sd), coefficients
+    const float k1g = training ? gga * dbet_g * invN : 0.f, k2g = training ? gga * dgam_g * invN : 0.f;
+    const float k1f = training ? fga * dbet_f * invN : 0.f, k2f = training ? fga * dgam_f * invN : 0.f;
+    const float invM = 1.f / M, invM1 = 1.f / (M - 1.f);
+    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
+    if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+        const size_t i = (size_t)n * C + c;
+        const float mean = mu[i], sdev = sd[i];
+        const float gg = g.gate[i];
+        const float dzg = sxy[i] * gg * (1.f - gg);
+        const float dsg = gr * (dzg * gga - k1g - g.shat[i] * k2g);
+        acc[0] = fmaf(dsg, mean, acc[0]); acc[1] = fmaf(dsg, sdev, acc[1]);
+        float dmu = dsg * gw0, dsd = dsg * gw1;
+        if (two) {
+            const float ff = f.gate[i], T = st[i];
+            const float dzf = mean * T * ff * (1.f - ff);
+            const float dsf = fr * (dzf * fga - k1f - f.shat[i] * k2f);
+            acc[2] = fmaf(dsf, mean, acc[2]); acc[3] = fmaf(dsf, sdev, acc[3]);
+            dmu += dsf * fw0 + (ff - gg) * T;
+            dsd += dsf * fw1;
+        }
+        const float b = dsd * invM1 / sdev;
+        cb[i] = b;
+        cc[i] = dmu * invM - b * mean;
+    }
+    column_sums<4>(acc, sm);
+    if (live && threadIdx.y == 0) {
+        g.dw[2 * c] = acc[0]; g.dw[2 * c + 1] = acc[1];
+        if (two) { f.dw[2 * c] = acc[2]; f.dw[2 * c + 1] = acc[3]; }
+    }
+}
+
+// dx = g*dy + cb*x + cc
+template <typename T, int TPI, bool VEC>
+__global__ void __launch_bounds__(kBlock)
+k_sn_apply_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ dx,
+               long long instances, int M, const float* __restrict__ gate,
+               const float* __restrict__ cb, const float* __restrict__ cc) {
+    const long long inst = Team<TPI>::instance();
+    if (inst >= instances) return;
+    const float g = gate[inst], b = cb[inst], c = cc[inst];
+    plane_map<T, TPI, VEC, true>(x + inst * M, dy + inst * M, dx + inst * M, M,
+                                 [=](float xv, float dv, int) { return fmaf(g, dv, fmaf(b, xv, c)); });
+}
+
+struct SaveLayout {           // offsets (in floats) into the save block
+    size_t mu, sd, g, shat_g, f, shat_f, r_g, r_f, total;
+    SaveLayout(int N, int C, bool two) {
+        const size_t nc = (size_t)N * C;
+        mu = 0; sd = nc; g = 2 * nc; shat_g = 3 * nc;
+        f = 4 * nc; shat_f = 5 * nc;
+        r_g = two ? 6 * nc : 4 * nc;
+        r_f = r_g + C;
+        total = r_g + (two ? 2 : 1) * (size_t)C;
+    }
+};
+
+static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
+
+}  // namespace cnsn
+
+using namespace cnsn;
+
+extern "C" size_t cnsn_selfnorm_save_floats(int N, int C, int is_two) {
+    return SaveLayout(N, C, is_two != 0).total;
+}
+extern "C" size_t cnsn_selfnorm_workspace_floats(int N, int C, int is_two) {
+    (void)is_two;
+    return 4 * (size_t)N * C;               // sxy | st | cb | cc
+}
+
+extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                                 const cnsn_gate_params* g, const cnsn_gate_params* f,
+                                 int training, float momentum, float bn_eps, float eps,
+                                 float* save, void* stream) {
+    if (!x || !y || !save || check_dims(N, C, H, W) || !gate_ok(g) || (f && !gate_ok(f))) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(x) % esize(dtype) || reinterpret_cast<uintptr_t>(y) % esize(dtype)) return CNSN_E_ALIGN;
+    if (training && N < 2) return CNSN_E_BATCH1;    // BatchNorm1d raises ValueError in the reference
+    const bool two = f != nullptr;
+    const SaveLayout L(N, C, two);
+    const int M = H * W;
+    const long long inst = (long long)N * C;
+    cudaStream_t s = (cudaStream_t)stream;
+    const Window full{0, H, 0, W};
+    int rc = launch_instance_stats(x, dtype, inst, H, W, full, eps, save + L.mu, save + L.sd, s);
+    if (rc) return rc;
+    GateFwd a{g->w, g->gamma, g->beta, g->run_mean, g->run_var, g->nbt, save + L.g, save + L.shat_g, save + L.r_g};
+    GateFwd b = a;
+    if (two) b = GateFwd{f->w, f->gamma, f->beta, f->run_mean, f->run_var, f->nbt, save + L.f, save + L.shat_f, save + L.r_f};
+    k_sn_gate_fwd<<<dim3((C + kGateCh - 1) / kGateCh, two ? 2 : 1), dim3(kGateCh, kGateRows), 0, s>>>(
+        save + L.mu, save + L.sd, a, b, N, C, training, momentum, bn_eps);
+    if ((rc = launch_status())) return rc;
+    const bool vec = vec_ok2(x, y, dtype, M);
+    const int tpi = team_for(M);
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC,
+        k_sn_apply_fwd<T, TPI, VEC><<<grid_for(inst, TPI), kBlock, 0, s>>>(
+            (const T*)x, (T*)y, inst, M, save + L.g, two ? save + L.f : nullptr, save + L.mu))));
+    return launch_status();
+}
+
+extern "C" int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
+                                 int N, int C, int H, int W,
+                                 const cnsn_gate_params* g, const cnsn_gate_params* f,
+                                 int training, const float* save,
+                                 const cnsn_gate_grads* dg, const cnsn_gate_grads* df,
+                                 float* workspace, void* stream) {
+    if (!x || !dy || !dx || !save || !workspace || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (!g || !g->w || !g->gamma || !dg || !dg->dw || !dg->dgamma || !dg->dbeta) return CNSN_E_BADARG;
+    const bool two = f != nullptr;
+    if (two && (!f->w || !f->gamma || !df || !df->dw || !df->dgamma || !df->dbeta)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    const SaveLayout L(N, C, two);
+    const int M = H * W;
+    const long long inst = (long long)N * C;
+    const size_t nc = (size_t)inst;
+    float* sxy = workspace; float* st = workspace + nc; float* cb = workspace + 2 * nc; float* cc = workspace + 3 * nc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const bool vec = vec_ok2(x, dy, dtype, M) && aligned16(dx);
+    const int tpi = team_for(M);
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC, CNSN_DISPATCH_BOOL(two, CENTER,
+        k_sn_reduce_bwd<T, TPI, VEC, CENTER><<<grid_for(inst, TPI), kBlock, 0, s>>>(
+            (const T*)x, (const T*)dy, inst, M, save + L.mu, sxy, st)))));
+    int rc = launch_status();
+    if (rc) return rc;
+    GateBwd a{g->w, g->gamma, save + L.g, save + L.shat_g, save + L.r_g, dg->dw, dg->dgamma, dg->dbeta};
+    GateBwd b = a;
+    if (two) b = GateBwd{f->w, f->gamma, save + L.f, save + L.shat_f, save + L.r_f, df->dw, df->dgamma, df->dbeta};
+    k_sn_gate_bwd<<<(C + kGateCh - 1) / kGateCh, dim3(kGateCh, kGateRows), 0, s>>>(
+        save + L.mu, save + L.sd, sxy, st, a, b, two ? 1 : 0, N, C, M, training, cb, cc);
+    if ((rc = launch_status())) return rc;
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC,
+        k_sn_apply_bwd<T, TPI, VEC><<<grid_for(inst, TPI), kBlock, 0, s>>>(
+            (const T*)x, (const T*)dy, (T*)dx, inst, M, save + L.g, cb, cc))));
+    return launch_status();
+}
+
+// Per-instance sums needed by the backward of cnsn_instance_affine: sxy = sum dy*x, st = sum dy.
+extern "C" int cnsn_instance_dot(const void* x, const void* dy, int dtype, int N, int C, int H, int W,
+                                 float* sxy, float* st, void* stream) {
+    if (!x || !dy || !sxy || !st || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    const int M = H * W;
+    const long long inst = (long long)N * C;
+    const bool vec = vec_ok2(x, dy, dtype, M);
+    const int tpi = team_for(M);
+    cudaStream_t s = (cudaStream_t)stream;
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC,
+        k_sn_reduce_bwd<T, TPI, VEC, false><<<grid_for(inst, TPI), kBlock, 0, s>>>(
+            (const T*)x, (const T*)dy, inst, M, nullptr, sxy, st))));
+    return launch_status();
+}

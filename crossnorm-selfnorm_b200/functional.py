@@ -1,0 +1,106 @@
+"""torch.autograd.Function wrappers: one fused forward and one fused backward per operator.
+
+Saved for backward: the input tensor plus O(N*C) fp32 statistics -- not the full-size
+intermediates (normalised features, expanded stds, masks, gathered copies) the reference's eager
+autograd graph keeps alive.
+"""
+import torch
+
+from . import _lib
+
+
+def _dense(x):
+    # the reference forces .contiguous() itself (models/cnsn.py:14,16); kernels take dense NCHW
+    return x if x.is_contiguous() else x.contiguous()
+
+
+class InstanceStats(torch.autograd.Function):
+    """(mean, std) over a window -- calc_ins_mean_std, models/cnsn.py:8-17."""
+
+    @staticmethod
+    def forward(ctx, x, window, eps):
+        x = _dense(x)
+        mean, std = _lib.backend().instance_stats(x, window, eps)
+        ctx.save_for_backward(x, mean, std)
+        ctx.window = window
+        return mean, std
+
+    @staticmethod
+    def backward(ctx, dmean, dstd):
+        x, mean, std = ctx.saved_tensors
+        dx = _lib.backend().instance_stats_bwd(x, ctx.window, mean, std,
+                                               dmean.contiguous().float(), dstd.contiguous().float())
+        return dx, None, None
+
+
+class InstanceAffine(torch.autograd.Function):
+    """out = x*scale[n,c] + shift[n,c] -- the broadcast restyle of models/cnsn.py:27-29."""
+
+    @staticmethod
+    def forward(ctx, x, scale, shift):
+        x = _dense(x)
+        scale = scale.contiguous().float()
+        shift = shift.contiguous().float()
+        ctx.save_for_backward(x, scale)
+        return _lib.backend().instance_affine(x, scale, shift)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, scale = ctx.saved_tensors
+        dy = _dense(dy)
+        b = _lib.backend()
+        dscale, dshift = b.instance_dot(x, dy)
+        dx = b.instance_affine(dy, scale, torch.zeros_like(scale))
+        return dx, dscale, dshift
+
+
+class SelfNormFn(torch.autograd.Function):
+    """SelfNorm.forward (models/cnsn.py:130-150) and its backward."""
+
+    @staticmethod
+    def forward(ctx, x, training, momentum, bn_eps, eps, g_bufs, f_bufs,
+                g_w, g_gamma, g_beta, f_w=None, f_gamma=None, f_beta=None):
+        x = _dense(x)
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
+        f = _lib.GateTensors(f_w, f_gamma, f_beta, *f_bufs) if f_w is not None else None
+        y, save = _lib.backend().selfnorm_fwd(x, g, f, training, momentum, bn_eps, eps)
+        ctx.save_for_backward(x, g_w, g_gamma, g_beta, f_w, f_gamma, f_beta)
+        ctx.sn_save = save          # fp32 statistics block (never a graph input)
+        ctx.training = training
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g_w, g_gamma, g_beta, f_w, f_gamma, f_beta = ctx.saved_tensors
+        save = ctx.sn_save
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
+        f = _lib.GateTensors(f_w, f_gamma, f_beta, None, None, None) if f_w is not None else None
+        dx, gg, gf = _lib.backend().selfnorm_bwd(x, _dense(dy), g, f, ctx.training, save)
+        out = [dx, None, None, None, None, None, None,
+               gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype)]
+        if f is not None:
+            out += [gf[0].view_as(f_w).to(f_w.dtype), gf[1].to(f_gamma.dtype), gf[2].to(f_beta.dtype)]
+        else:
+            out += [None, None, None]
+        return tuple(out)
+
+
+class CrossNormFn(torch.autograd.Function):
+    """Device half of cn_op_2ins_space_chan (models/cnsn.py:58-91) and its backward."""
+
+    @staticmethod
+    def forward(ctx, x, perm, chan_perm, cwin, swin, lam, eps):
+        x = _dense(x)
+        y, save = _lib.backend().crossnorm_fwd(x, perm, chan_perm, cwin, swin, lam, eps)
+        ctx.save_for_backward(x)
+        ctx.cn_save = (perm, chan_perm, save)
+        ctx.meta = (cwin, swin, lam)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        perm, chan_perm, save = ctx.cn_save
+        cwin, swin, lam = ctx.meta
+        dx = _lib.backend().crossnorm_bwd(x, _dense(dy), perm, chan_perm, cwin, swin, lam, save)
+        return dx, None, None, None, None, None, None

@@ -1,0 +1,172 @@
+/*
+ * cnsn_b200.h -- C ABI of libcnsn_b200.so: the CrossNorm / SelfNorm hot path of
+ * amazon-science/crossnorm-selfnorm, rebuilt as hand-written sm_100a CUDA kernels.
+ *
+ * Every entry point replaces a piece of the reference's models/cnsn.py (paths below are
+ * relative to the reference checkout) or of the autograd backward PyTorch derives from it.
+ * The reference has no FFI of its own (it is pure Python over ATen); these are the symbols a
+ * binding for that file would need.  INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *   - all tensor pointers are DEVICE pointers to dense NCHW storage (the reference forces
+ *     .contiguous() itself at models/cnsn.py:14,16); element type given by `dtype`;
+ *   - per-instance statistics, parameters, gradients of parameters and workspaces are fp32;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered;
+ *   - the library never allocates: workspaces / save areas are caller-owned, sizes come from
+ *     the *_floats() helpers; it keeps no mutable state besides the launch counter;
+ *   - return value: 0 on success, a positive cudaError_t, or a negative CNSN_E_* code;
+ *     cnsn_error_string() renders either.
+ *   - windows are half-open [h0,h1) x [w0,w1) in NCHW rows/cols.  NOTE the reference names
+ *     them bbx (dim 2) / bby (dim 3) with W/H swapped (models/cnsn.py:34-35,66,77).
+ */
+#ifndef CNSN_B200_H
+#define CNSN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNSN_ABI_VERSION 2
+
+enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
+
+enum {
+    CNSN_OK = 0,
+    CNSN_E_BADARG = -1,   /* null pointer, non-positive dim, bad dtype, bad window, bad perm ptr */
+    CNSN_E_WORKSPACE = -2,/* workspace too small */
+    CNSN_E_BATCH1 = -3,   /* SelfNorm training with N == 1 (reference: BatchNorm1d ValueError) */
+    CNSN_E_ALIGN = -4     /* tensor base pointer not aligned to its element size */
+};
+
+/* Library / ABI identification. */
+int cnsn_version(void);
+const char* cnsn_error_string(int code);
+/* Number of CUDA kernels this library has launched in this process (monotonic, atomic). */
+unsigned long long cnsn_launch_count(void);
+
+/*
+ * Per-(n,c) mean and std = sqrt(unbiased_var + eps) over the window.
+ * Replaces calc_ins_mean_std, models/cnsn.py:8-17 (and its use on crops at :66,:77).
+ * mean/std: N*C floats.
+ */
+int cnsn_instance_stats(const void* x, int dtype, int N, int C, int H, int W,
+                        int h0, int h1, int w0, int w1, float eps,
+                        float* mean, float* std, void* stream);
+
+/*
+ * Backward of cnsn_instance_stats (autograd of models/cnsn.py:14-16):
+ *   dx = dmean/M + (x - mean)/std * dstd/(M-1) inside the window, 0 outside.
+ */
+int cnsn_instance_stats_bwd(const void* x, void* dx, int dtype, int N, int C, int H, int W,
+                            int h0, int h1, int w0, int w1,
+                            const float* mean, const float* std,
+                            const float* dmean, const float* dstd, void* stream);
+
+/*
+ * out[n,c,:,:] = x[n,c,:,:] * scale[n,c] + shift[n,c]   (scale/shift: N*C floats).
+ * The broadcast normalise-and-restyle of instance_norm_mix, models/cnsn.py:27-29, for callers
+ * that bring their own statistics.
+ */
+int cnsn_instance_affine(const void* x, void* out, int dtype, int N, int C, int H, int W,
+                         const float* scale, const float* shift, void* stream);
+
+/*
+ * Per-instance sums sxy[n,c] = sum_hw dy*x and st[n,c] = sum_hw dy (N*C floats each): the
+ * scale / shift gradients of cnsn_instance_affine, i.e. the reductions autograd performs for the
+ * broadcast multiply-add at models/cnsn.py:27-29.
+ */
+int cnsn_instance_dot(const void* x, const void* dy, int dtype, int N, int C, int H, int W,
+                      float* sxy, float* st, void* stream);
+
+/* ---------------------------------------------------------------- SelfNorm ---------------
+ * Replaces SelfNorm.forward, models/cnsn.py:130-150, and its autograd backward.
+ *
+ *   mu, sd   = instance stats (eps, 1e-12 in the reference :133)
+ *   s        = w[c,0]*mu + w[c,1]*sd                      (depthwise Conv1d k=2, :137)
+ *   train:   m = mean_n s, q = biased var_n s; running_mean/var updated (momentum, unbiased q)
+ *   eval:    m, q = running_mean, running_var
+ *   g        = sigmoid(gamma * (s-m)/sqrt(q+bn_eps) + beta)            (:138-139)
+ *   y        = x*g                         or, is_two (f_* non-NULL): x*g + mu*(f-g)  (:142-150)
+ *
+ * Gate parameter block (all device fp32): w = g_fc.weight viewed (C,2); gamma/beta = g_bn affine;
+ * run_mean/run_var = g_bn buffers (updated in place when training); nbt = num_batches_tracked
+ * (int64, incremented when training; may be NULL).
+ *
+ * `save` (caller-owned, cnsn_selfnorm_save_floats() floats) receives what backward needs:
+ *   [mu | sd | g | shat_g | (f | shat_f)] each N*C, then [r_g (C) | (r_f (C))], r = 1/sqrt(q+bn_eps).
+ */
+typedef struct cnsn_gate_params {
+    const float* w;        /* (C,2) */
+    const float* gamma;    /* (C)   */
+    const float* beta;     /* (C)   */
+    float* run_mean;       /* (C)   */
+    float* run_var;        /* (C)   */
+    long long* nbt;        /* scalar or NULL */
+} cnsn_gate_params;
+
+typedef struct cnsn_gate_grads {
+    float* dw;             /* (C,2) */
+    float* dgamma;         /* (C)   */
+    float* dbeta;          /* (C)   */
+} cnsn_gate_grads;
+
+size_t cnsn_selfnorm_save_floats(int N, int C, int is_two);
+size_t cnsn_selfnorm_workspace_floats(int N, int C, int is_two);
+
+int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                      const cnsn_gate_params* g, const cnsn_gate_params* f /* NULL unless is_two */,
+                      int training, float momentum, float bn_eps, float eps,
+                      float* save, void* stream);
+
+/*
+ * dx = dy*g + a + b*(x - mu); a = dmu/M, b = dsd/((M-1)*sd), through the BatchNorm-over-batch
+ * backward when training.  Parameter gradients are WRITTEN (not accumulated).
+ * workspace: cnsn_selfnorm_workspace_floats() floats.
+ */
+int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
+                      int N, int C, int H, int W,
+                      const cnsn_gate_params* g, const cnsn_gate_params* f,
+                      int training, const float* save,
+                      const cnsn_gate_grads* dg, const cnsn_gate_grads* df,
+                      float* workspace, void* stream);
+
+/* ---------------------------------------------------------------- CrossNorm --------------
+ * Replaces cn_op_2ins_space_chan, models/cnsn.py:58-91 (+ instance_norm_mix :20-29), device
+ * side only; the host draws perm / windows (RNG contract) and passes them in.
+ *
+ *   inside the content window:
+ *     y[i,c] = lam*x + (1-lam) * ((x - mu_c[i,c])/sd_c[i,c] * sd_s[p(i),pi(c)] + mu_s[p(i),pi(c)])
+ *   outside: y = x.          (mu_c, sd_c) over the content window, (mu_s, sd_s) over the style window.
+ *
+ * perm: N int32 (device), a permutation of 0..N-1.  chan_perm: C int32 (device) or NULL.
+ * lam: blend weight, pass 0 for the reference's lam=None.
+ * save: 4*N*C floats, receives [mu_c | sd_c | mu_s | sd_s] for backward.
+ */
+/* content / style: HOST arrays of 4 ints {h0, h1, w0, w1}; pass {0,H,0,W} for "no crop". */
+size_t cnsn_crossnorm_save_floats(int N, int C);
+size_t cnsn_crossnorm_workspace_floats(int N, int C);
+
+int cnsn_crossnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                       const int* perm, const int* chan_perm,
+                       const int* content, const int* style,
+                       float lam, float eps, float* save, void* stream);
+
+/*
+ * Backward: nothing is detached, so dx carries the gradient through the content
+ * statistics and, scattered through the permutation, through the style statistics.
+ * workspace: cnsn_crossnorm_workspace_floats() floats.
+ */
+int cnsn_crossnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
+                       int N, int C, int H, int W,
+                       const int* perm, const int* chan_perm,
+                       const int* content, const int* style,
+                       float lam, const float* save, float* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNSN_B200_H */

@@ -1,0 +1,219 @@
+"""CPU tests of the package's HOST logic with an oracle-backed stand-in for the CUDA backend:
+module surface, state_dict compatibility, .active protocol, RNG consumption order, autograd wiring,
+and the drop-in of the package into the reference's unmodified model files.
+No CUDA compute happens here; numerical parity of the kernels is tests/test_gpu_parity.py (-m gpu).
+"""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers as H
+from _refload import load_reference_cnsn, reference_root
+from fake_backend import OracleBackend
+
+
+@pytest.fixture()
+def mod():
+    import cnsn_b200._lib as L
+    import cnsn_b200.cnsn as m
+    fake = OracleBackend()
+    old = L.set_backend_for_tests(fake)
+    m._fake = fake
+    yield m
+    L.set_backend_for_tests(old)
+
+
+def test_product_path_has_no_cpu_fallback():
+    import cnsn_b200._lib as L
+    import cnsn_b200.cnsn as m
+    L.set_backend_for_tests(None)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.SelfNorm(4)(torch.randn(2, 4, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.cn_op_2ins_space_chan(torch.randn(2, 4, 3, 3))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.calc_ins_mean_std(torch.randn(2, 4, 3, 3))
+
+
+def test_package_never_imports_oracle():
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "crossnorm-selfnorm_b200")
+    for dirpath, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+                assert "fake_backend" not in src, f
+
+
+@pytest.mark.parametrize("name", H.golden_names("selfnorm_"))
+def test_selfnorm_wiring_golden(mod, name):
+    g = H.golden(name)
+    params, bufs = H.sn_params_from_golden(g)
+    two, training = bool(g["is_two"]), bool(g["training"])
+    r = H.run_selfnorm(mod, g["x"], g["dy"], params, bufs, "cpu", two, training, torch.float64)
+    assert H.maxabs(r["y"], g["y_f64"]) < 1e-6 and H.maxabs(r["dx"], g["dx_f64"]) < 1e-6
+    for tag in ("g", "f") if two else ("g",):
+        for k in ("w", "gamma", "beta"):
+            assert H.relmax(r[f"d{tag}_{k}"], g[f"d{tag}_{k}_f64"]) < 1e-5
+        assert H.maxabs(r[f"{tag}_rm_after"], g[f"{tag}_rm_after_f64"]) < 1e-6
+        assert H.maxabs(r[f"{tag}_rv_after"], g[f"{tag}_rv_after_f64"]) < 1e-6
+        assert int(r[f"{tag}_nbt_after"]) == int(g[f"{tag}_nbt_after"])
+
+
+@pytest.mark.parametrize("name", H.golden_names("crossnorm_"))
+def test_crossnorm_wiring_and_rng_golden(mod, name):
+    """Same seeds as the reference run -> same perm / boxes -> same output (pins the RNG contract)."""
+    g = H.golden(name)
+    y, dx = H.run_crossnorm(mod, g["x"], g["dy"], "cpu", str(g["crop"]), bool(g["chan"]), H.lam_of(g),
+                            g["torch_seed"], g["numpy_seed"], torch.float64)
+    assert H.maxabs(y, g["y_f64"]) < 1e-6
+    assert H.maxabs(dx, g["dx_f64"]) < 1e-6
+
+
+def test_cn_rand_bbox_matches_reference_stream():
+    import cnsn_b200.cnsn as m
+    g = H.golden("rng_stream")
+    torch.manual_seed(int(g["seed"]))
+    np.random.seed(int(g["seed"]) + 1)
+    for i in range(int(g["n"])):
+        shape, crop = tuple(int(v) for v in g[f"shape{i}"]), str(g[f"crop{i}"])
+        perm = torch.randperm(shape[0]).numpy()
+        assert np.array_equal(perm, g[f"perm{i}"])
+        for key, on in (("sw", crop in ("style", "both")), ("cw", crop in ("content", "both"))):
+            if on:
+                b = m.cn_rand_bbox(shape, beta=1, bbx_thres=0.1)
+                assert (int(b[0]), int(b[2]), int(b[1]), int(b[3])) == tuple(int(v) for v in g[f"{key}{i}"])
+
+
+def test_stats_and_mix_autograd(mod):
+    torch.manual_seed(0)
+    c = torch.randn(3, 4, 6, 5, dtype=torch.float64, requires_grad=True)
+    s = torch.randn(3, 4, 4, 7, dtype=torch.float64, requires_grad=True)
+    out = mod.instance_norm_mix(c, s)
+    w = torch.randn_like(out)
+    (out * w).sum().backward()
+    # same computation in plain torch (the reference formula, cnsn.py:8-29)
+    c2, s2 = c.detach().clone().requires_grad_(True), s.detach().clone().requires_grad_(True)
+    def st(x):
+        v = x.reshape(3, 4, -1)
+        return v.mean(2).view(3, 4, 1, 1), (v.var(2) + 1e-5).sqrt().view(3, 4, 1, 1)
+    sm, ss = st(s2)
+    cm, cs = st(c2)
+    ref = (c2 - cm) / cs * ss + sm
+    (ref * w).sum().backward()
+    assert torch.allclose(out, ref, atol=1e-10)
+    assert torch.allclose(c.grad, c2.grad, atol=1e-9) and torch.allclose(s.grad, s2.grad, atol=1e-9)
+    m, sd = mod.calc_ins_mean_std(c)
+    assert m.shape == sd.shape == (3, 4, 1, 1)
+    with pytest.raises(AssertionError):
+        mod.calc_ins_mean_std(torch.randn(3, 4, 5))
+
+
+def test_crossnorm_active_protocol(mod):
+    cn = mod.CrossNorm(crop="neither", beta=1)
+    assert list(cn.state_dict().keys()) == [] and bool(cn) and cn.active is False
+    x = torch.randn(4, 3, 5, 5)
+    cn.train()
+    assert cn(x) is x                       # inactive -> identity, same object
+    cn.active = True
+    y = cn(x)
+    assert cn.active is False and y is not x and mod._fake.calls == ["crossnorm_fwd"]
+    cn.eval()
+    cn.active = True
+    assert cn(x) is x and cn.active is False    # reset even in eval (cnsn.py:108)
+    with pytest.raises(AssertionError):
+        mod.cn_op_2ins_space_chan(x, crop="nope")
+
+
+def test_cnsn_composition(mod):
+    x = torch.randn(4, 3, 5, 5)
+    assert mod.CNSN(None, None)(x) is x
+    cn, sn = mod.CrossNorm("neither", 1), mod.SelfNorm(3)
+    blk = mod.CNSN(cn, sn).train()
+    blk(x)
+    assert mod._fake.calls == ["selfnorm_fwd"]          # inactive CrossNorm is not even called (cnsn.py:160)
+    cn.active = True
+    blk(x)
+    assert mod._fake.calls[1:] == ["crossnorm_fwd", "selfnorm_fwd"] and cn.active is False
+
+
+def test_selfnorm_state_dict_matches_reference(mod):
+    ref = load_reference_cnsn()
+    if ref is None:
+        pytest.skip("reference checkout not present")
+    for two in (False, True):
+        torch.manual_seed(3)
+        a = ref.SelfNorm(8, is_two=two)
+        torch.manual_seed(3)
+        b = mod.SelfNorm(8, is_two=two)
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa.keys()) == list(sb.keys())
+        for k in sa:
+            assert sa[k].shape == sb[k].shape and torch.equal(sa[k], sb[k]), k   # same init draws
+        b.load_state_dict(sa)
+
+
+def test_selfnorm_batch1_raises_like_reference(mod):
+    with pytest.raises(ValueError, match="Expected more than 1 value per channel"):
+        mod.SelfNorm(4).train()(torch.randn(1, 4, 3, 3))
+
+
+def _reference_host(modname, cnsn_module):
+    """Import a reference host-model file with `models.cnsn` swapped for ours."""
+    root = reference_root()
+    if root is None:
+        pytest.skip("reference checkout not present")
+    if not hasattr(np, "int"):
+        np.int = int
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, root)
+    try:
+        import models
+        sys.modules["models.cnsn"] = cnsn_module
+        models.cnsn = cnsn_module
+        host = __import__(modname, fromlist=["x"])
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return host
+
+
+def test_dropin_wideresnet_matches_reference(mod):
+    """Unmodified reference WideResNet + our cnsn module == unmodified reference end to end
+    (same seeds -> same active sites, perms, boxes; logits and gradients agree)."""
+    ref = load_reference_cnsn()
+    if ref is None:
+        pytest.skip("reference checkout not present")
+    kw = dict(depth=10, num_classes=10, widen_factor=1, active_num=2, pos="post", beta=1, crop="both",
+              cnsn_type="cnsn")
+    ours = _reference_host("models.cifar.wideresnet_cnsn", mod)
+    theirs = _reference_host("models.cifar.wideresnet_cnsn", ref)
+    torch.manual_seed(0)
+    na = theirs.WideResNet(**kw).double().train()
+    torch.manual_seed(0)
+    nb = ours.WideResNet(**kw).double().train()
+    assert type(nb.cn_modules[0]) is mod.CrossNorm and len(nb.cn_modules) == len(na.cn_modules)
+    assert list(na.state_dict().keys()) == list(nb.state_dict().keys())
+    nb.load_state_dict(na.state_dict())
+    x = torch.randn(6, 3, 32, 32, dtype=torch.float64)
+    outs = []
+    for net in (na, nb):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        out = net(x, aug=True)
+        out.square().sum().backward()
+        outs.append(out)
+    assert "crossnorm_fwd" in mod._fake.calls and "selfnorm_bwd" in mod._fake.calls
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(na.named_parameters(), nb.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+    for (ka, ba), (kb, bb) in zip(na.named_buffers(), nb.named_buffers()):
+        assert torch.allclose(ba.double(), bb.double(), atol=1e-9), ka
