@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- CNSN hot-path benchmark (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Headline workload (config.workload): SelfNorm forward + backward, train mode, on a
+(256,256,56,56) fp32 NCHW tensor -- the shape BASELINE.json's north_star quotes the metric on.
+One "step" = one forward + one backward pass of the hot path over one synthetic batch.
+
+  value      algorithmic GB/s = N_gpus * 5*S / step time, inputs resident in HBM (S = bytes of x;
+             forward reads x writes y = 2S, backward reads x, dy writes dx = 3S)
+  roofline   the dominant call (backward, 3*S) timed with CUDA events inside the timed region,
+             against MEASURED_PEAKS.json's HBM copy bandwidth
+  e2e        the same metric through the nn.Module API with HOST (pinned) buffers: per step
+             H2D of x and dy, forward, backward, D2H of y and dx inside the timed region
+  cpu_baseline / --impl reference
+             the eager-PyTorch op chain of the reference (oracle/eager_chain.py, bit-identical
+             to models/cnsn.py on CPU) timed on this box's host cores on a bounded sample
+  train      secondary: WideResNet-40-2 + CNSN training step images/s (DDP over NCCL when N>1)
+
+Multi-GPU: the CNSN path has no cross-GPU exchange -- every rank runs the same
+per-GPU workload on its own shard ("weak" scaling, no data-path collective); only the secondary
+training step all-reduces gradients.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+NORTH_STAR = (256, 256, 56, 56)
+CPU_SAMPLE_N = 32                     # bounded CPU sample: N=32 of 256 instances per channel
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--shape", default=None, help="N,C,H,W override (parity/debug only)")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
+    ap.add_argument("--no-train", action="store_true", help="skip the secondary WRN-40-2 measurement")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--train-batch", type=int, default=512)
+    ap.add_argument("--train-steps", type=int, default=20)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """Samples SM clock and clock-event reasons through NVML while the timed region runs."""
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index, period=0.005):
+        self.samples, self.reasons, self.period, self.ok = [], set(), period, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:      # pragma: no cover
+            self.err = repr(e)
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for b, name in self.REASONS.items():
+                    if bits & b and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def __enter__(self):
+        if self.ok:
+            self._t = threading.Thread(target=self._run, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def physical_gpu_index(local):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local])
+        except Exception:
+            return local
+    return local
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_selfnorm(shape, steps, warmup):
+    """Eager-PyTorch chain of the reference on this box's host cores (bounded sample)."""
+    import torch
+    from oracle import eager_chain as E
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    N, C, H, W = shape
+    sample = (min(N, CPU_SAMPLE_N), C, H, W)
+    times = E.time_selfnorm_fwd_bwd(sample, steps, warmup, threads=cores)
+    S = sample[0] * C * H * W * 4
+    t = sum(times) / len(times)
+    return {"value": 5 * S / t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
+            "sample": "SelfNorm fwd+bwd fp32 on (%d,%d,%d,%d) = N %d of %d, %d steps after %d warm-up, mean; "
+                      "eager-PyTorch op chain of models/cnsn.py (oracle/eager_chain.py)" % (*sample, sample[0], N, steps, warmup),
+            "ms_per_step": t * 1e3, "best_ms": min(times) * 1e3}
+
+
+def run_reference_arm(args, shape):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 8))
+    warm = max(1, min(args.warmup, 2))
+    cb = cpu_reference_selfnorm(shape, steps, warm)
+    line = {
+        "impl": "reference", "metric": "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)",
+        "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "SelfNorm fwd+bwd train-mode, NCHW fp32 (%d,%d,%d,%d); CPU arm runs a bounded "
+                               "sample of it (see cpu_baseline.sample)" % shape},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else NORTH_STAR
+    if args.impl == "reference":
+        return run_reference_arm(args, shape)
+
+    import torch
+    import torch.distributed as dist
+    import cnsn_b200
+    import cnsn_b200.cnsn as M
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if args.gpus != world and rank == 0 and world > 1:
+        print("warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N, C, H, W = shape
+    tdt = torch.float32 if args.dtype == "f32" else torch.bfloat16
+    esz = 4 if args.dtype == "f32" else 2
+    S = N * C * H * W * esz
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)       # each rank its own shard
+    x = (torch.randn(shape, device=dev, generator=gen) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, device=dev, generator=gen))
+         + torch.randn(N, C, 1, 1, device=dev, generator=gen)).to(tdt).requires_grad_(True)
+    dy = torch.randn(shape, device=dev, generator=gen).to(tdt)
+    sn = M.SelfNorm(C).to(dev).train()
+
+    def step(ev=None):
+        if ev:
+            ev[0].record()
+        y = sn(x)
+        if ev:
+            ev[1].record()
+        (dx,) = torch.autograd.grad(y, x, dy)     # parameter grads are produced by the same fused backward
+        if ev:
+            ev[2].record()
+        return y, dx
+
+    for _ in range(args.warmup):
+        step()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    n0 = cnsn_b200.launch_count()
+    with ClockSampler(physical_gpu_index(local)) as clk:
+        t0.record()
+        for i in range(args.steps):
+            step(evs[i])
+        t1.record()
+        barrier()
+    launches = cnsn_b200.launch_count() - n0
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    ms_step = ms_total / args.steps
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    value = world * 5 * S / (ms_step * 1e-3) / 1e9
+    peak, peak_src = peaks()
+    bwd_gbs = 3 * S / (bwd_ms * 1e-3) / 1e9
+    fwd_gbs = 2 * S / (fwd_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")      # from the committed ncu --set full capture
+    if os.path.isfile(tpath):
+        try:
+            with open(tpath) as f:
+                traffic = json.load(f).get("selfnorm_bwd_%s_bytes_per_launch" % args.dtype)
+        except Exception:
+            traffic = None
+
+    # ---- e2e: module API with HOST pinned buffers, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        e2e_steps = max(2, min(args.steps, 5))
+        hx = torch.empty(shape, dtype=tdt, pin_memory=True).copy_(x.detach())
+        hdy = torch.empty(shape, dtype=tdt, pin_memory=True).copy_(dy)
+        hy = torch.empty(shape, dtype=tdt, pin_memory=True)
+        hdx = torch.empty(shape, dtype=tdt, pin_memory=True)
+
+        def e2e_step():
+            dxi = hx.to(dev, non_blocking=True).requires_grad_(True)
+            ddy = hdy.to(dev, non_blocking=True)
+            y = sn(dxi)
+            hy.copy_(y.detach(), non_blocking=True)
+            (gx,) = torch.autograd.grad(y, dxi, ddy)
+            hdx.copy_(gx, non_blocking=True)
+
+        e2e_step()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        b.record()
+        barrier()
+        e_ms = max_over_ranks(a.elapsed_time(b)) / e2e_steps
+        e2e = {"value": world * 5 * S / (e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 2 * S,
+               "d2h_bytes_per_step": 2 * S, "ms_per_step": e_ms, "steps": e2e_steps,
+               "api": "cnsn_b200.cnsn.SelfNorm forward + autograd backward on pinned host tensors"}
+        del hx, hdy, hy, hdx
+
+    del x, dy
+    torch.cuda.empty_cache()
+
+    # ---- secondary: WRN-40-2 + CNSN training step
+    train = None
+    if not args.no_train:
+        try:
+            from cnsn_b200.train import bench_wrn
+            train = bench_wrn(dev, world, rank, batch=args.train_batch, steps=args.train_steps, warmup=5)
+        except Exception as e:      # the headline must still be printed
+            train = {"error": repr(e)[:300]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_reference_selfnorm(shape, 6, 1)
+        cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    if rank == 0:
+        line = {
+            "metric": "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)",
+            "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "SelfNorm fwd+bwd train-mode, NCHW %s (%d,%d,%d,%d) per GPU, S=%d bytes; "
+                                   "independent per-GPU batches, no data-path collective" % (args.dtype, *shape, S),
+                       "l2": "inputs (x, dy: %.0f MB each) larger than the 126 MB L2; no flush needed" % (S / 1e6),
+                       "parallelism": "replicated shards x%d" % world},
+            "roofline": {"bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
+                         "traffic": traffic, "kernel": "cnsn_selfnorm_bwd (3*S algorithmic bytes per call)",
+                         "peak_source": peak_src,
+                         "fwd": {"achieved": fwd_gbs, "frac": fwd_gbs / peak, "ms": fwd_ms, "bytes": 2 * S},
+                         "bwd": {"achieved": bwd_gbs, "frac": bwd_gbs / peak, "ms": bwd_ms, "bytes": 3 * S},
+                         "step": {"achieved": value / world, "frac": value / world / peak}},
+            "clocks": clk.summary(),
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "cpu_baseline": cpu,
+            "train": train,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,3 +121,22 @@ def run_crossnorm(mod, x, dy, device, crop, chan, lam, torch_seed, numpy_seed, d
     y = mod.cn_op_2ins_space_chan(xt, crop=crop, beta=beta, lam=lam, chan=chan)
     y.backward(torch.from_numpy(dy).to(device=device, dtype=dtype))
     return y.detach().double().cpu().numpy(), xt.grad.detach().double().cpu().numpy()
+
+
+def eager_selfnorm_f32(x, dy, params, bufs, training=True):
+    """The eager-PyTorch fp32 chain (oracle/eager_chain.py, bit-identical to the reference on CPU):
+    used to calibrate what fp32 arithmetic itself can deliver on an ill-conditioned case."""
+    from oracle import eager_chain as E
+    C = x.shape[1]
+    g = E.GateState(C)
+    with torch.no_grad():
+        g.fc_w.copy_(torch.from_numpy(params["g_w"]).view(C, 1, 2))
+        g.bn_w.copy_(torch.from_numpy(params["g_gamma"]))
+        g.bn_b.copy_(torch.from_numpy(params["g_beta"]))
+        g.run_mean.copy_(torch.from_numpy(bufs["g_rm"]))
+        g.run_var.copy_(torch.from_numpy(bufs["g_rv"]))
+    xt = torch.from_numpy(x).requires_grad_(True)
+    y = E.selfnorm(xt, g, training)
+    y.backward(torch.from_numpy(dy))
+    return {"y": y.detach().numpy(), "dx": xt.grad.numpy(), "dg_w": g.fc_w.grad.view(C, 2).numpy(),
+            "dg_gamma": g.bn_w.grad.numpy(), "dg_beta": g.bn_b.grad.numpy()}

@@ -106,8 +106,14 @@ def test_selfnorm_vs_oracle_f32(mod, shape, training):
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     close32(r["y"], o["y"], "y")
     close32(r["dx"], o["dx"], "dx")
+    # Parameter gradients: 1e-5 relative, except where fp32 itself cannot deliver that -- with a tiny
+    # batch the BatchNorm-over-batch backward cancels catastrophically (at N=2 the reference's own fp32
+    # run is 7e-4 off its fp64 run) -- then: no worse than 2x the eager fp32 chain's own error, and
+    # 1e-3 for training batches of 2-3 where that error is itself erratic.
+    e = H.eager_selfnorm_f32(x, dy, params, bufs, training)
     for k in ("dg_w", "dg_gamma", "dg_beta"):
-        close_param(r[k], o[k], k)
+        tol = max(H.PARAM_RTOL, 2 * H.relmax(e[k], o[k]), 1e-3 if (training and shape[0] < 4) else 0.0)
+        assert H.relmax(r[k], o[k]) <= tol, f"{k}: rel err {H.relmax(r[k], o[k]):.3e} > {tol:.3e}"
     close32(r["g_rm_after"], o["g_rm_after"], "running_mean")
     close32(r["g_rv_after"], o["g_rv_after"], "running_var")
 
