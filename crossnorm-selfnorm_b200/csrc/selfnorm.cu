@@ -9,6 +9,8 @@
 // re-reads.  The gate couples all N instances of a channel (BatchNorm1d over the batch, :121,:138),
 // which is why a reduction phase must complete for the whole channel before any element of it
 // can be written.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cnsn {
@@ -236,16 +238,29 @@ k_sn_apply_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict_
 }
 
 struct SaveLayout {           // offsets (in floats) into the save block
-    size_t mu, sd, g, shat_g, f, shat_f, r_g, r_f, total;
+    size_t mu, sd, g, shat_g, f, shat_f, r_g, r_f, scratch, total;
     SaveLayout(int N, int C, bool two) {
         const size_t nc = (size_t)N * C;
         mu = 0; sd = nc; g = 2 * nc; shat_g = 3 * nc;
         f = 4 * nc; shat_f = 5 * nc;
         r_g = two ? 6 * nc : 4 * nc;
         r_f = r_g + C;
-        total = r_g + (two ? 2 : 1) * (size_t)C;
+        scratch = (r_g + (two ? 2 : 1) * (size_t)C + 1) & ~(size_t)1;   // 8-byte aligned
+        total = scratch + 2 * nc;                      // [C][N] (mu, sd) exchange area of the fused kernel
     }
 };
+
+namespace fused {
+int selfnorm_fused_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                       const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
+                       float* mu, float* sd, float* gate, float* shat, float* r, float* scratch_floats,
+                       cudaStream_t stream);
+}
+// CNSN_SELFNORM_IMPL=v1 forces the three-kernel path (A/B measurements); default: fused when it applies.
+static bool force_v1() {
+    const char* e = getenv("CNSN_SELFNORM_IMPL");
+    return e && e[0] == 'v' && e[1] == '1';
+}
 
 static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
 
@@ -274,6 +289,12 @@ extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C
     const int M = H * W;
     const long long inst = (long long)N * C;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!two && !force_v1()) {
+        const int frc = fused::selfnorm_fused_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
+                                                  save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
+                                                  save + L.r_g, save + L.scratch, s);
+        if (frc != -100) return frc;         // -100: shape not eligible, use the three-kernel path
+    }
     const Window full{0, H, 0, W};
     int rc = launch_instance_stats(x, dtype, inst, H, W, full, eps, save + L.mu, save + L.sd, s);
     if (rc) return rc;

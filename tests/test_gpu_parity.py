@@ -255,3 +255,36 @@ def test_selfnorm_north_star_shape_properties(mod):
     y2 = m(x)
     (dx2,) = torch.autograd.grad(y2, x, 2.0 * dy)
     assert torch.allclose(dx2, 2.0 * dx, rtol=1e-4, atol=1e-5)
+
+
+# ------------------------------------------------------------------ fused persistent kernel (tensors >= 8 MB)
+FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.float32), ((256, 64, 14, 14), torch.float32),
+                ((256, 256, 7, 7), torch.float32), ((512, 32, 16, 16), torch.float32), ((96, 24, 28, 28), torch.float32),
+                ((256, 16, 56, 56), torch.bfloat16), ((300, 20, 20, 20), torch.float32), ((40, 6, 224, 224), torch.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", FUSED_SHAPES)
+@pytest.mark.parametrize("training", [True, False])
+def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatch):
+    """Shapes large enough for the persistent fused kernel: against the oracle (all channels) and
+    against the three-kernel path (CNSN_SELFNORM_IMPL=v1) on identical inputs."""
+    x = O.varied_input(shape, seed=sum(shape), dtype=np.float32, relu=True)
+    dy = np.random.RandomState(1).standard_normal(shape).astype(np.float32)
+    if dtype != torch.float32:
+        x = torch.from_numpy(x).to(dtype).float().numpy()
+        dy = torch.from_numpy(dy).to(dtype).float().numpy()
+    params, bufs = H.random_sn_params(shape[1], seed=3)
+    r = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "v1")
+    v1 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.delenv("CNSN_SELFNORM_IMPL")
+    o = H.oracle_selfnorm(x, dy, params, bufs, training)
+    chk = close32 if dtype == torch.float32 else close16
+    for res in (r, v1):
+        chk(res["y"], o["y"], "y")
+        chk(res["dx"], o["dx"], "dx")
+        for k in ("dg_w", "dg_gamma", "dg_beta"):
+            assert H.relmax(res[k], o[k]) <= (H.PARAM_RTOL if dtype == torch.float32 else 1e-4), k
+        close32(res["g_rm_after"], o["g_rm_after"], "running_mean")
+        close32(res["g_rv_after"], o["g_rv_after"], "running_var")
+        assert int(res["g_nbt_after"]) == (1 if training else 0)

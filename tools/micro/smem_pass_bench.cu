@@ -1,0 +1,36 @@
+// Microbenchmark: cycles for one warp to run the two-pass smem statistics over one 56x56 fp32 plane,
+// alone and with 1..15 other warps doing the same on their own planes.
+#include <cstdio>
+#include "../../crossnorm-selfnorm_b200/csrc/fused_common.cuh"
+using namespace cnsn; using namespace cnsn::fused;
+namespace cnsn { void note_launch() {} }
+
+__global__ void k(int nwarps, int M, long long* out, float* sink) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    float* data = reinterpret_cast<float*>(smem);
+    for (int i = threadIdx.x; i < 16 * M; i += blockDim.x) data[i] = (float)(i % 97) * 0.01f;
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nwarps) {
+        long long t0 = clock64();
+        float2 r = smem_mean_m2<float>(data + warp * M, M, lane, 32, true, true);
+        long long t1 = clock64();
+        if (lane == 0) { out[blockIdx.x * 16 + warp] = t1 - t0; sink[blockIdx.x * 16 + warp] = r.x + r.y; }
+    }
+}
+int main() {
+    const int M = 3136;
+    long long* out; float* sink;
+    cudaMalloc(&out, 148 * 16 * 8); cudaMalloc(&sink, 148 * 16 * 4);
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * M * 4);
+    for (int nw : {1, 2, 4, 8, 16}) {
+        for (int rep = 0; rep < 2; ++rep) {
+            k<<<148, 512, 16 * M * 4>>>(nw, M, out, sink);
+            cudaDeviceSynchronize();
+        }
+        long long h[16];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("warps=%2d cycles(warp0)=%lld (warp last)=%lld err=%s\n", nw, h[0], h[nw - 1], cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
