@@ -15,11 +15,15 @@ namespace cnsn {
 namespace fused {
 
 constexpr int kStatsWarps = 8;
-constexpr int kApplyWarps = 8;
+constexpr int kApplyWarps = 12;                  // the apply stream is latency-bound per warp (L2 round trips): more warps,
+constexpr int kApplyTeam = 1;                    //   warps per unit (teams of 3 cut the per-unit latency but measured slower overall)
+constexpr int kApplyTeams = kApplyWarps / kApplyTeam;
 constexpr int kWgThreads = 256;                 // threads in the stats / apply warpgroups
-constexpr int kWarpProducer = 16;               // issues TMA bulk loads
-constexpr int kThreads = 17 * 32;
-constexpr int kPrefetchAhead = 8;               // groups of L2 prefetch distance ahead of the smem loads
+constexpr int kWarpProducer = kStatsWarps + kApplyWarps;      // issues TMA bulk loads
+constexpr int kWarpChan = kWarpProducer + 1;    // first of kChanWarps channel warps (apply slot sl -> warp sl % kChanWarps)
+constexpr int kChanWarps = 3;
+constexpr int kThreads = (kWarpChan + kChanWarps) * 32;
+constexpr int kSlots = 36;                      // max apply-stream slots (runtime: Schedule::R, a multiple of kChanWarps)
 constexpr int kMaxPairs = 1024;                 // N*kk per group handled by one channel warp (32 slots/lane)
 constexpr unsigned kSentinel = 0xffffffffu;     // "not yet published" tag in the second word of a pair
 constexpr int kMaxStages = 12;
@@ -63,6 +67,11 @@ __device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem
                                             uint64_t policy) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
                  :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// Same without a cache hint (default L2 policy: the line stays until the apply stream re-reads it).
+__device__ __forceinline__ void tma_load_1d_plain(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 // L2 prefetch of a future unit: the HBM latency (and its tail) is paid before a ring slot is tied up.
 __device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, unsigned bytes) {
@@ -112,6 +121,7 @@ struct Schedule {
     int S;                  // ring stages
     int rot;                // rotation stride (coprime with B)
     int lpi;                // lanes per instance inside a warp (4..32, power of two)
+    int R;                  // apply-stream slots = how many groups the reduce stream may run ahead of apply
     unsigned unit_elems;    // kk*M
     __device__ __forceinline__ int first(int b, int g) const { return (b + (int)(((long long)g * rot) % B)) % B; }
     __device__ __forceinline__ int count(int first_n) const { return first_n < N ? (N - first_n + B - 1) / B : 0; }
@@ -129,14 +139,16 @@ struct Schedule {
 // the group are advanced incrementally (integer division by runtime values costs ~100 instructions).
 struct GroupIter {
     int g, st, ph, first, cnt;
+    int sl, sp;                                   // apply-stream slot (g % R) and its phase parity
     int q, rem;                                   // N = q*B + rem
     __device__ __forceinline__ void init(const Schedule& s, int b) {
-        g = 0; st = 0; ph = 0; first = b; q = s.N / s.B; rem = s.N - q * s.B;
+        g = 0; st = 0; ph = 0; sl = 0; sp = 0; first = b; q = s.N / s.B; rem = s.N - q * s.B;
         cnt = q + (first < rem ? 1 : 0);
     }
     __device__ __forceinline__ void next(const Schedule& s) {
         ++g;
         if (++st == s.S) { st = 0; ph ^= 1; }
+        if (++sl == s.R) { sl = 0; sp ^= 1; }
         first += s.rot;
         if (first >= s.B) first -= s.B;
         cnt = q + (first < rem ? 1 : 0);

@@ -15,8 +15,7 @@
 
 namespace cnsn {
 
-constexpr int kGateCh = 32;   // channels per gate CTA (threadIdx.x)
-constexpr int kGateRows = 8;  // batch-strided rows per gate CTA (threadIdx.y)
+constexpr int kGateThreads = 256;   // one CTA per (channel, gate branch); thread t owns samples t, t+256, ...
 
 struct GateFwd {              // one gate branch (g or f) as seen by the forward gate kernel
     const float* w; const float* gamma; const float* beta;
@@ -29,61 +28,65 @@ struct GateBwd {
     float* dw; float* dgamma; float* dbeta;
 };
 
-// Sum over threadIdx.y for every threadIdx.x column; result broadcast to all rows.
+// Block-wide sums of K values over kGateThreads threads; every thread gets the totals.
 template <int K>
-__device__ __forceinline__ void column_sums(float (&v)[K], float (*sm)[kGateRows][kGateCh + 1]) {
-    __syncthreads();
+__device__ __forceinline__ void gate_block_sums(float (&v)[K], float (*sm)[kGateThreads / 32]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
-    for (int k = 0; k < K; ++k) sm[k][threadIdx.y][threadIdx.x] = v[k];
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();                         // sm may still be read from the previous call
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sm[k][warp] = v[k];
+    }
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < kGateRows; ++j) s += sm[k][j][threadIdx.x];
+        for (int w = 0; w < kGateThreads / 32; ++w) s += sm[k][w];
         v[k] = s;
     }
 }
 
 __device__ __forceinline__ float sigmoidf_acc(float z) { return 1.f / (1.f + expf(-z)); }
 
-// grid = (ceil(C/32), n_gates); block = (32, 8)
-__global__ void __launch_bounds__(kGateCh * kGateRows)
+// grid = (C, n_gates); block = 256.  The (N,C) statistics are tiny; what matters is latency, so every
+// channel gets its own CTA (the first version used C/32 CTAs and took 15-25 us on its own).
+__global__ void __launch_bounds__(kGateThreads)
 k_sn_gate_fwd(const float* __restrict__ mu, const float* __restrict__ sd, GateFwd g0, GateFwd g1,
               int N, int C, int training, float momentum, float bn_eps) {
-    __shared__ float sm[1][kGateRows][kGateCh + 1];
+    __shared__ float sm[1][kGateThreads / 32];
     const GateFwd g = blockIdx.y == 0 ? g0 : g1;
-    const int c = blockIdx.x * kGateCh + threadIdx.x;
-    const bool live = c < C;
-    const float w0 = live ? g.w[2 * c] : 0.f, w1 = live ? g.w[2 * c + 1] : 0.f;
+    const int c = blockIdx.x;
+    const float w0 = g.w[2 * c], w1 = g.w[2 * c + 1];
     float m, q;
     if (training) {
         float acc[1] = {0.f};
-        if (live) for (int n = threadIdx.y; n < N; n += kGateRows)
+        for (int n = threadIdx.x; n < N; n += kGateThreads)
             acc[0] += fmaf(w0, mu[(size_t)n * C + c], w1 * sd[(size_t)n * C + c]);
-        column_sums<1>(acc, sm);
+        gate_block_sums<1>(acc, sm);
         m = acc[0] / N;
         acc[0] = 0.f;
-        if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+        for (int n = threadIdx.x; n < N; n += kGateThreads) {
             const float d = fmaf(w0, mu[(size_t)n * C + c], w1 * sd[(size_t)n * C + c]) - m;
             acc[0] = fmaf(d, d, acc[0]);
         }
-        column_sums<1>(acc, sm);
+        gate_block_sums<1>(acc, sm);
         q = acc[0] / N;                      // biased variance normalises (BatchNorm semantics)
-        if (live && threadIdx.y == 0) {
+        if (threadIdx.x == 0) {
             g.run_mean[c] = (1.f - momentum) * g.run_mean[c] + momentum * m;
             g.run_var[c] = (1.f - momentum) * g.run_var[c] + momentum * (q * N / (N - 1.f));
+            if (g.nbt && c == 0) *g.nbt += 1;
         }
-        if (g.nbt && blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *g.nbt += 1;
     } else {
-        m = live ? g.run_mean[c] : 0.f;
-        q = live ? g.run_var[c] : 1.f;
+        m = g.run_mean[c];
+        q = g.run_var[c];
     }
-    if (!live) return;
     const float r = 1.f / sqrtf(q + bn_eps);
     const float ga = g.gamma[c], be = g.beta[c];
-    if (threadIdx.y == 0) g.r[c] = r;
-    for (int n = threadIdx.y; n < N; n += kGateRows) {
+    if (threadIdx.x == 0) g.r[c] = r;
+    for (int n = threadIdx.x; n < N; n += kGateThreads) {
         const size_t i = (size_t)n * C + c;
         const float sh = (fmaf(w0, mu[i], w1 * sd[i]) - m) * r;
         g.shat[i] = sh;
@@ -153,21 +156,20 @@ k_sn_reduce_bwd(const T* __restrict__ x, const T* __restrict__ dy, long long ins
     if (r == 0) { sxy[inst] = a; st[inst] = t; }
 }
 
-// Gate backward for one tile of 32 channels.  Produces the parameter gradients and the two
-// per-instance coefficients of  dx = g*dy + cb*x + cc   (cb = b, cc = a - b*mu).
-// grid = ceil(C/32); block = (32, 8)
-__global__ void __launch_bounds__(kGateCh * kGateRows)
+// Gate backward for one channel per CTA.  Produces the parameter gradients and the two per-instance
+// coefficients of  dx = g*dy + cb*x + cc   (cb = b, cc = a - b*mu).
+// grid = C; block = 256
+__global__ void __launch_bounds__(kGateThreads)
 k_sn_gate_bwd(const float* __restrict__ mu, const float* __restrict__ sd,
               const float* __restrict__ sxy, const float* __restrict__ st,
               GateBwd g, GateBwd f, int two, int N, int C, int M, int training,
               float* __restrict__ cb, float* __restrict__ cc) {
-    __shared__ float sm[4][kGateRows][kGateCh + 1];
-    const int c = blockIdx.x * kGateCh + threadIdx.x;
-    const bool live = c < C;
+    __shared__ float sm[4][kGateThreads / 32];
+    const int c = blockIdx.x;
     const float invN = 1.f / N;
     // pass A: dgamma = sum dz*shat, dbeta = sum dz for each gate
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+    for (int n = threadIdx.x; n < N; n += kGateThreads) {
         const size_t i = (size_t)n * C + c;
         const float gg = g.gate[i];
         if (!two) {
@@ -181,23 +183,21 @@ k_sn_gate_bwd(const float* __restrict__ mu, const float* __restrict__ sd,
             acc[2] = fmaf(dzf, f.shat[i], acc[2]); acc[3] += dzf;
         }
     }
-    column_sums<4>(acc, sm);
+    gate_block_sums<4>(acc, sm);
     const float dgam_g = acc[0], dbet_g = acc[1], dgam_f = acc[2], dbet_f = acc[3];
-    float gw0 = 0.f, gw1 = 0.f, gga = 0.f, gr = 0.f, fw0 = 0.f, fw1 = 0.f, fga = 0.f, fr = 0.f;
-    if (live) {
-        gw0 = g.w[2 * c]; gw1 = g.w[2 * c + 1]; gga = g.gamma[c]; gr = g.r[c];
-        if (two) { fw0 = f.w[2 * c]; fw1 = f.w[2 * c + 1]; fga = f.gamma[c]; fr = f.r[c]; }
-        if (threadIdx.y == 0) {
-            g.dgamma[c] = dgam_g; g.dbeta[c] = dbet_g;
-            if (two) { f.dgamma[c] = dgam_f; f.dbeta[c] = dbet_f; }
-        }
+    const float gw0 = g.w[2 * c], gw1 = g.w[2 * c + 1], gga = g.gamma[c], gr = g.r[c];
+    float fw0 = 0.f, fw1 = 0.f, fga = 0.f, fr = 0.f;
+    if (two) { fw0 = f.w[2 * c]; fw1 = f.w[2 * c + 1]; fga = f.gamma[c]; fr = f.r[c]; }
+    if (threadIdx.x == 0) {
+        g.dgamma[c] = dgam_g; g.dbeta[c] = dbet_g;
+        if (two) { f.dgamma[c] = dgam_f; f.dbeta[c] = dbet_f; }
     }
     // pass B: ds, dw = (sum ds*mu, sum ds*sd), coefficients
     const float k1g = training ? gga * dbet_g * invN : 0.f, k2g = training ? gga * dgam_g * invN : 0.f;
     const float k1f = training ? fga * dbet_f * invN : 0.f, k2f = training ? fga * dgam_f * invN : 0.f;
     const float invM = 1.f / M, invM1 = 1.f / (M - 1.f);
     acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    if (live) for (int n = threadIdx.y; n < N; n += kGateRows) {
+    for (int n = threadIdx.x; n < N; n += kGateThreads) {
         const size_t i = (size_t)n * C + c;
         const float mean = mu[i], sdev = sd[i];
         const float gg = g.gate[i];
@@ -217,8 +217,8 @@ k_sn_gate_bwd(const float* __restrict__ mu, const float* __restrict__ sd,
         cb[i] = b;
         cc[i] = dmu * invM - b * mean;
     }
-    column_sums<4>(acc, sm);
-    if (live && threadIdx.y == 0) {
+    gate_block_sums<4>(acc, sm);
+    if (threadIdx.x == 0) {
         g.dw[2 * c] = acc[0]; g.dw[2 * c + 1] = acc[1];
         if (two) { f.dw[2 * c] = acc[2]; f.dw[2 * c + 1] = acc[3]; }
     }
@@ -246,7 +246,7 @@ struct SaveLayout {           // offsets (in floats) into the save block
         r_g = two ? 6 * nc : 4 * nc;
         r_f = r_g + C;
         scratch = (r_g + (two ? 2 : 1) * (size_t)C + 1) & ~(size_t)1;   // 8-byte aligned
-        total = scratch + 2 * nc;                      // [C][N] (mu, sd) exchange area of the fused kernel
+        total = scratch + 2 * nc;                      // [C][N] published (mu, sd) words of the fused kernel
     }
 };
 
@@ -255,11 +255,16 @@ int selfnorm_fused_fwd(const void* x, void* y, int dtype, int N, int C, int H, i
                        const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
                        float* mu, float* sd, float* gate, float* shat, float* r, float* scratch_floats,
                        cudaStream_t stream);
+int selfnorm_fused_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                       const cnsn_gate_params* g, int training,
+                       float* mu, float* sd, float* gate, float* shat, float* r,
+                       const cnsn_gate_grads* dg, float* scratch_floats, cudaStream_t stream);
 }
-// CNSN_SELFNORM_IMPL=v1 forces the three-kernel path (A/B measurements); default: fused when it applies.
-static bool force_v1() {
+// CNSN_SELFNORM_IMPL=v1 forces the three-kernel path (A/B measurements); unset = the two-stream
+// fused kernels (selfnorm_fused.cu) where they apply.
+static int impl_choice() {
     const char* e = getenv("CNSN_SELFNORM_IMPL");
-    return e && e[0] == 'v' && e[1] == '1';
+    return (e && e[0] == 'v') ? 1 : 0;
 }
 
 static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
@@ -273,7 +278,7 @@ extern "C" size_t cnsn_selfnorm_save_floats(int N, int C, int is_two) {
 }
 extern "C" size_t cnsn_selfnorm_workspace_floats(int N, int C, int is_two) {
     (void)is_two;
-    return 4 * (size_t)N * C;               // sxy | st | cb | cc
+    return 4 * (size_t)N * C;               // sxy | st | cb | cc   (fused path: [C][N] published words)
 }
 
 extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
@@ -289,7 +294,7 @@ extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C
     const int M = H * W;
     const long long inst = (long long)N * C;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!two && !force_v1()) {
+    if (!two && impl_choice() != 1) {
         const int frc = fused::selfnorm_fused_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
                                                   save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
                                                   save + L.r_g, save + L.scratch, s);
@@ -301,7 +306,7 @@ extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C
     GateFwd a{g->w, g->gamma, g->beta, g->run_mean, g->run_var, g->nbt, save + L.g, save + L.shat_g, save + L.r_g};
     GateFwd b = a;
     if (two) b = GateFwd{f->w, f->gamma, f->beta, f->run_mean, f->run_var, f->nbt, save + L.f, save + L.shat_f, save + L.r_f};
-    k_sn_gate_fwd<<<dim3((C + kGateCh - 1) / kGateCh, two ? 2 : 1), dim3(kGateCh, kGateRows), 0, s>>>(
+    k_sn_gate_fwd<<<dim3(C, two ? 2 : 1), kGateThreads, 0, s>>>(
         save + L.mu, save + L.sd, a, b, N, C, training, momentum, bn_eps);
     if ((rc = launch_status())) return rc;
     const bool vec = vec_ok2(x, y, dtype, M);
@@ -329,6 +334,15 @@ extern "C" int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dt
     const size_t nc = (size_t)inst;
     float* sxy = workspace; float* st = workspace + nc; float* cb = workspace + 2 * nc; float* cc = workspace + 3 * nc;
     cudaStream_t s = (cudaStream_t)stream;
+    // Backward: the fused kernels move the ideal 3*S but are not faster than the three-kernel path yet
+    // (profiles/README.md), so they are opt-in: CNSN_SELFNORM_BWD=fused.
+    const char* bsel = getenv("CNSN_SELFNORM_BWD");
+    if (!two && impl_choice() == 0 && bsel && bsel[0] == 'f') {
+        float* sv = const_cast<float*>(save);
+        const int frc = fused::selfnorm_fused_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
+                                                  sv + L.g, sv + L.shat_g, sv + L.r_g, dg, workspace, s);
+        if (frc != -100) return frc;
+    }
     const bool vec = vec_ok2(x, dy, dtype, M) && aligned16(dx);
     const int tpi = team_for(M);
     CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC, CNSN_DISPATCH_BOOL(two, CENTER,
@@ -339,7 +353,7 @@ extern "C" int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dt
     GateBwd a{g->w, g->gamma, save + L.g, save + L.shat_g, save + L.r_g, dg->dw, dg->dgamma, dg->dbeta};
     GateBwd b = a;
     if (two) b = GateBwd{f->w, f->gamma, save + L.f, save + L.shat_f, save + L.r_f, df->dw, df->dgamma, df->dbeta};
-    k_sn_gate_bwd<<<(C + kGateCh - 1) / kGateCh, dim3(kGateCh, kGateRows), 0, s>>>(
+    k_sn_gate_bwd<<<C, kGateThreads, 0, s>>>(
         save + L.mu, save + L.sd, sxy, st, a, b, two ? 1 : 0, N, C, M, training, cb, cc);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_TEAM(tpi, TPI, CNSN_DISPATCH_BOOL(vec, VEC,

@@ -266,21 +266,26 @@ FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.floa
 @pytest.mark.parametrize("shape,dtype", FUSED_SHAPES)
 @pytest.mark.parametrize("training", [True, False])
 def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatch):
-    """Shapes large enough for the persistent fused kernel: against the oracle (all channels) and
-    against the three-kernel path (CNSN_SELFNORM_IMPL=v1) on identical inputs."""
+    """Shapes large enough for the persistent kernels: the default dispatch, the three-kernel path, the
+    two-stream fused kernels (forward and backward, forced), all against the oracle on identical inputs."""
     x = O.varied_input(shape, seed=sum(shape), dtype=np.float32, relu=True)
     dy = np.random.RandomState(1).standard_normal(shape).astype(np.float32)
     if dtype != torch.float32:
         x = torch.from_numpy(x).to(dtype).float().numpy()
         dy = torch.from_numpy(dy).to(dtype).float().numpy()
     params, bufs = H.random_sn_params(shape[1], seed=3)
-    r = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "v1")
+    r = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)          # default dispatch
+    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "v1")                                     # three-kernel path
     v1 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
     monkeypatch.delenv("CNSN_SELFNORM_IMPL")
+    monkeypatch.setenv("CNSN_FUSED_FORCE", "1")                                        # two-stream fused fwd + bwd
+    monkeypatch.setenv("CNSN_SELFNORM_BWD", "fused")
+    fz = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.delenv("CNSN_FUSED_FORCE")
+    monkeypatch.delenv("CNSN_SELFNORM_BWD")
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     chk = close32 if dtype == torch.float32 else close16
-    for res in (r, v1):
+    for res in (r, v1, fz):
         chk(res["y"], o["y"], "y")
         chk(res["dx"], o["dx"], "dx")
         for k in ("dg_w", "dg_gamma", "dg_beta"):
