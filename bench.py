@@ -148,6 +148,16 @@ def run_reference_arm(args, shape):
     steps = max(1, min(args.steps, 8))
     warm = max(1, min(args.warmup, 2))
     cb = cpu_reference_selfnorm(shape, steps, warm)
+    train = None
+    if not args.no_train:
+        try:                                     # secondary: the same training step with the eager-PyTorch CNSN on CPU
+            import torch
+            from cnsn_b200.train import bench_wrn
+            from oracle import eager_modules
+            train = bench_wrn(torch.device("cpu"), 1, 0, batch=64, steps=2, warmup=1, ops=eager_modules)
+            train["sample"] = "batch 64 (of 512), 2 steps after 1 warm-up, CPU, eager-PyTorch CNSN (oracle/eager_modules.py)"
+        except Exception as e:
+            train = {"error": repr(e)[:300]}
     line = {
         "impl": "reference", "metric": "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)",
         "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
@@ -158,6 +168,7 @@ def run_reference_arm(args, shape):
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "train": train,
     }
     print(json.dumps(line), flush=True)
 

@@ -1,0 +1,2 @@
+"""Host models that call the CNSN operators (the callers either side of the hot path)."""
+from .wideresnet import WideResNet  # noqa: F401

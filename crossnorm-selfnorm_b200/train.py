@@ -1,0 +1,112 @@
+"""Synthetic-data training harness for the CNSN host models (stands in for the reference's cifar.py).
+
+One process per GPU; gradients are all-reduced by DistributedDataParallel over NCCL.  The CNSN path
+itself never crosses GPUs: CrossNorm permutes inside the per-GPU batch and SelfNorm's BatchNorm1d uses
+per-GPU batch statistics -- the per-replica behaviour of the reference's DataParallel.
+
+The step mirrors ``train_cn`` of the reference's cifar.py:117-145: a coin ``np.random.rand(1) < cn_prob``
+decides whether this step's forward activates CrossNorm sites (``net(x, aug=True)``), then cross-entropy,
+``zero_grad``, ``backward``, SGD-Nesterov step, per-step cosine LR, and a ``float(loss)`` read (host sync)
+every step, as there.
+"""
+import math
+import os
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+def wrn40_2(ops=None, num_classes=10, active_num=2, pos="post", beta=1, crop="both", cnsn_type="cnsn"):
+    """WideResNet-40-2 + CNSN with the hyper-parameters of cifar10-scripts/wideresnet/run-cnsn.sh."""
+    from .hosts.wideresnet import WideResNet
+    return WideResNet(40, num_classes, widen_factor=2, drop_rate=0.0, active_num=active_num, pos=pos, beta=beta,
+                      crop=crop, cnsn_type=cnsn_type, ops=ops)
+
+
+def cosine_lr(step, total_steps, lr_max, lr_min):
+    return lr_min + (lr_max - lr_min) * 0.5 * (1 + math.cos(step / total_steps * math.pi))
+
+
+def make_optimizer(net, total_steps, lr=0.1, momentum=0.9, wd=5e-4):
+    opt = torch.optim.SGD(net.parameters(), lr, momentum=momentum, weight_decay=wd, nesterov=True)
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, lr_lambda=lambda s: cosine_lr(s, total_steps, 1, 1e-6 / lr))
+    return opt, sched
+
+
+def train_step(net, images, targets, opt, sched, cn_prob):
+    """One ``train_cn`` step; returns the loss as a Python float (host sync, as in the reference)."""
+    aug = bool(np.random.rand(1) < cn_prob)
+    logits = net(images, aug=aug)
+    loss = F.cross_entropy(logits, targets)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    sched.step()
+    return float(loss.detach())
+
+
+def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None):
+    """images/s of WideResNet-40-2 + CNSN training on synthetic CIFAR-shaped data (fp32, batch per GPU)."""
+    import torch.distributed as dist
+    torch.manual_seed(1 + rank)
+    np.random.seed(1 + rank)                  # each rank draws its own perms / boxes / coins
+    net = wrn40_2(ops=ops).to(dev).train()
+    model = net
+    if world > 1:
+        # broadcast_buffers=False: SelfNorm / BatchNorm running statistics stay per replica, as under the
+        # reference's DataParallel; only gradients are exchanged
+        model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index] if dev.type == "cuda" else None,
+                                                    broadcast_buffers=False)
+    opt, sched = make_optimizer(model, total_steps=steps + warmup)
+    x = torch.randn(batch, 3, 32, 32, device=dev)
+    y = torch.randint(0, 10, (batch,), device=dev)
+    is_cuda = dev.type == "cuda"
+    launches0 = None
+    if is_cuda:
+        from . import _lib
+        launches0 = _lib.launch_count()
+    for _ in range(warmup):
+        train_step(model, x, y, opt, sched, cn_prob)
+    if is_cuda:
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+    else:
+        import time
+        if world > 1:
+            dist.barrier()
+        w0 = time.perf_counter()
+    loss = 0.0
+    for _ in range(steps):
+        loss = train_step(model, x, y, opt, sched, cn_prob)
+    if is_cuda:
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+    else:
+        ms = (time.perf_counter() - w0) * 1e3
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+    out = {"metric": "WideResNet-40-2 + CNSN training images/s", "value": world * batch * steps / (ms * 1e-3),
+           "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+           "batch_per_gpu": batch, "n_gpus": world, "dtype": "f32 (TF32 convolutions: %s)" % torch.backends.cudnn.allow_tf32,
+           "config": "depth 40, widen 2, cnsn_type=cnsn, pos=post, crop=both, beta=1, active_num=2, cn_prob=%g, "
+                     "SGD nesterov lr 0.1 wd 5e-4, cosine LR, synthetic 32x32" % cn_prob,
+           "final_loss": loss, "params": sum(p.numel() for p in net.parameters())}
+    if launches0 is not None:
+        from . import _lib
+        out["cnsn_kernel_launches"] = _lib.launch_count() - launches0
+    out["param_checksum"] = float(sum(p.detach().double().sum() for p in net.parameters()))
+    return out

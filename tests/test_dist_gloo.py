@@ -1,0 +1,54 @@
+"""world_size-2 gloo run of the training harness on CPU (host logic of the multi-GPU path): gradients
+are all-reduced (replicas stay identical), each rank draws its own augmentation stream, timing is the
+max over ranks.  The CNSN operators here are the eager-PyTorch set (no GPU in this test)."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import numpy as np
+    import torch.distributed as dist
+    torch.set_num_threads(2)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cnsn_b200.train import bench_wrn
+    from oracle import eager_modules
+    r = bench_wrn(torch.device("cpu"), world, rank, batch=4, steps=2, warmup=1, cn_prob=1.0, ops=eager_modules)
+    q.put((rank, r["param_checksum"], r["value"], r["n_gpus"], float(np.random.rand())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_two_rank_gloo_training_keeps_replicas_in_sync():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=500) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    (_, c0, v0, n0, u0), (_, c1, v1, n1, u1) = res
+    assert n0 == n1 == 2
+    assert c0 == pytest.approx(c1, rel=1e-12)          # same initial weights + all-reduced grads -> identical replicas
+    assert v0 == pytest.approx(v1, rel=1e-9)           # throughput is computed from the max-over-ranks time
+    assert u0 != u1                                    # per-rank host RNG streams (seed + rank)

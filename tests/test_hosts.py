@@ -1,0 +1,91 @@
+"""Host model (WideResNet + CNSN) against the live reference model file (build container only) and
+its own invariants everywhere."""
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _refload import load_reference_cnsn, reference_root
+from fake_backend import OracleBackend
+
+
+@pytest.fixture()
+def fake():
+    import cnsn_b200._lib as L
+    f = OracleBackend()
+    old = L.set_backend_for_tests(f)
+    yield f
+    L.set_backend_for_tests(old)
+
+
+def _reference_wrn():
+    root = reference_root()
+    if root is None:
+        pytest.skip("reference checkout not present")
+    ref = load_reference_cnsn()
+    saved = {k: v for k, v in sys.modules.items() if k == "models" or k.startswith("models.")}
+    for k in saved:
+        del sys.modules[k]
+    sys.path.insert(0, root)
+    try:
+        import models
+        sys.modules["models.cnsn"] = ref
+        models.cnsn = ref
+        host = __import__("models.cifar.wideresnet_cnsn", fromlist=["x"])
+    finally:
+        sys.path.remove(root)
+        for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
+            del sys.modules[k]
+        sys.modules.update(saved)
+    return host.WideResNet
+
+
+@pytest.mark.parametrize("pos", ["post", "pre", "residual", "identity"])
+def test_wideresnet_matches_reference_model(fake, pos, capsys):
+    """Same seed -> identical parameters; same inputs and host RNG -> same logits and gradients."""
+    from cnsn_b200.hosts import WideResNet
+    RefWRN = _reference_wrn()
+    kw = dict(depth=10, num_classes=10, widen_factor=2, active_num=2, pos=pos, beta=1, crop="both", cnsn_type="cnsn")
+    torch.manual_seed(0)
+    a = RefWRN(**kw).double().train()
+    torch.manual_seed(0)
+    b = WideResNet(**kw).double().train()
+    capsys.readouterr()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    assert len(a.cn_modules) == len(b.cn_modules) == 3
+    x = torch.randn(6, 3, 32, 32, dtype=torch.float64)
+    outs = []
+    for net in (a, b):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        o = net(x, aug=True)
+        o.square().sum().backward()
+        outs.append(o)
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+    a.eval(), b.eval()
+    assert torch.allclose(a(x), b(x), atol=1e-8)
+
+
+def test_wrn40_2_census():
+    """WRN-40-2 cnsn/post: 2,248,922 parameters, 18 CrossNorm + 18 SelfNorm sites."""
+    from cnsn_b200.train import wrn40_2
+    import cnsn_b200.cnsn as m
+    net = wrn40_2()
+    assert sum(p.numel() for p in net.parameters()) == 2248922
+    assert len(net.cn_modules) == 18
+    assert sum(isinstance(k, m.SelfNorm) for k in net.modules()) == 18
+    assert "block1.layer.0.cnsn.selfnorm.g_fc.weight" in net.state_dict()
+
+
+def test_train_step_on_cpu_with_eager_ops():
+    """The harness runs end to end on CPU when given the eager-PyTorch operator set (the CPU baseline arm)."""
+    from cnsn_b200.train import bench_wrn
+    from oracle import eager_modules
+    r = bench_wrn(torch.device("cpu"), 1, 0, batch=8, steps=2, warmup=1, cn_prob=1.0, ops=eager_modules)
+    assert r["value"] > 0 and np.isfinite(r["final_loss"]) and r["params"] == 2248922
