@@ -108,6 +108,24 @@ def _require_cuda(*ts):
                                "tensor. There is no CPU fallback." % t.device)
 
 
+class _NoCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+_NOCTX = _NoCtx()
+
+
+def _on(device):
+    """Device guard that costs nothing in the common case (tensor already on the current device)."""
+    if torch.cuda.current_device() == device.index:
+        return _NOCTX
+    return torch.cuda.device(device)
+
+
 def _stream(t):
     return c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
@@ -143,7 +161,7 @@ class CudaBackend:
         N, C, H, W = x.shape
         mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
         std = torch.empty_like(mean)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_instance_stats(_p(x), _dtype_code(x), N, C, H, W, *window, eps,
                                              _p(mean), _p(std), _stream(x)))
         return mean, std
@@ -152,7 +170,7 @@ class CudaBackend:
         _require_cuda(x)
         N, C, H, W = x.shape
         dx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_instance_stats_bwd(_p(x), _p(dx), _dtype_code(x), N, C, H, W, *window,
                                                  _p(mean), _p(std), _p(dmean), _p(dstd), _stream(x)))
         return dx
@@ -161,7 +179,7 @@ class CudaBackend:
         _require_cuda(x)
         N, C, H, W = x.shape
         out = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_instance_affine(_p(x), _p(out), _dtype_code(x), N, C, H, W,
                                               _p(scale), _p(shift), _stream(x)))
         return out
@@ -171,7 +189,7 @@ class CudaBackend:
         N, C, H, W = x.shape
         sxy = torch.empty((N, C), dtype=torch.float32, device=x.device)
         st = torch.empty_like(sxy)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_instance_dot(_p(x), _p(dy), _dtype_code(x), N, C, H, W, _p(sxy), _p(st), _stream(x)))
         return sxy, st
 
@@ -196,7 +214,7 @@ class CudaBackend:
         fs, f_rm, f_rv = self._gate_struct(f, keep) if two else (None, None, None)
         save = torch.empty(lib().cnsn_selfnorm_save_floats(N, C, int(two)), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_selfnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W,
                                            ctypes.byref(gs), ctypes.byref(fs) if two else None,
                                            int(training), momentum, bn_eps, eps, _p(save), _stream(x)))
@@ -228,7 +246,7 @@ class CudaBackend:
         gf = GateGrads(*[_p(t).value for t in out_f]) if two else None
         ws = torch.empty(lib().cnsn_selfnorm_workspace_floats(N, C, int(two)), dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
-        with torch.cuda.device(dev):
+        with _on(dev):
             _check(lib().cnsn_selfnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,
                                            ctypes.byref(gs), ctypes.byref(fs) if two else None,
                                            int(training), _p(save),
@@ -242,7 +260,7 @@ class CudaBackend:
         N, C, H, W = x.shape
         save = torch.empty(lib().cnsn_crossnorm_save_floats(N, C), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_crossnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, _p(perm), _p(chan_perm),
                                             _I4(*cwin), _I4(*swin), lam, eps, _p(save), _stream(x)))
         return y, save
@@ -252,7 +270,7 @@ class CudaBackend:
         N, C, H, W = x.shape
         ws = torch.empty(lib().cnsn_crossnorm_workspace_floats(N, C), dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
-        with torch.cuda.device(x.device):
+        with _on(x.device):
             _check(lib().cnsn_crossnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,
                                             _p(perm), _p(chan_perm), _I4(*cwin), _I4(*swin), lam,
                                             _p(save), _p(ws), _stream(x)))

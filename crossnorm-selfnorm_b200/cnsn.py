@@ -63,9 +63,10 @@ def cn_rand_bbox(size, beta, bbx_thres):
 
 def _to_device_i32(idx, device):
     """Upload a host permutation without the reference's blocking pageable copy (:62)."""
-    host = idx.to(torch.int32)
-    if device.type == "cuda":
-        host = host.pin_memory()
+    if device.type != "cuda":
+        return idx.to(torch.int32)
+    host = torch.empty(idx.numel(), dtype=torch.int32, pin_memory=True)   # cached pinned block, no cudaHostAlloc
+    host.copy_(idx)
     return host.to(device, non_blocking=True)
 
 

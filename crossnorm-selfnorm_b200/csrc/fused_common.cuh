@@ -166,23 +166,23 @@ struct GroupIter {
 // the E[x^2]-mean^2 formula); cross-lane reductions are plain adds.
 constexpr int kBatch = 8;
 
+// Batched loops are written as "full batches without any bounds check, then a scalar tail": a bounds
+// check per load compiles to a branch region (BSSY/BSYNC) per load and made this loop 3x slower.
 template <typename T>
 __device__ __forceinline__ float2 smem_mean_m2(const T* inst, int M, int r, int lpi, bool vec, bool live) {
     constexpr int V = VecOf<T>::n;
     const int nv = M / V;
-    // 1. shift estimate
+    // 1. shift estimate: one element (vector) per lane, spread over the plane
     float ks = 0.f, kn = 0.f;
     if (live) {
         if (vec) {
-            const int i = (int)(((long long)r * nv) / lpi);          // spread over the plane
             float v[V];
-            unpack<T>(reinterpret_cast<const uint4*>(inst)[i], v);
+            unpack<T>(reinterpret_cast<const uint4*>(inst)[r * (nv / lpi)], v);
 #pragma unroll
             for (int j = 0; j < V; ++j) ks += v[j];
             kn = (float)V;
         } else {
-            const int i = (int)(((long long)r * M) / lpi);
-            ks = to_f(inst[i]);
+            ks = to_f(inst[r * (M / lpi)]);
             kn = 1.f;
         }
     }
@@ -190,30 +190,41 @@ __device__ __forceinline__ float2 smem_mean_m2(const T* inst, int M, int r, int 
         ks += __shfl_xor_sync(0xffffffffu, ks, o);
         kn += __shfl_xor_sync(0xffffffffu, kn, o);
     }
-    const float K = kn > 0.f ? ks / kn : 0.f;
+    const float K = kn > 0.f ? __fdividef(ks, kn) : 0.f;
     // 2. shifted sums
     float s1 = 0.f, s2 = 0.f;
     if (live) {
         if (vec) {
             const uint4* p = reinterpret_cast<const uint4*>(inst);
             float a1[4] = {0.f, 0.f, 0.f, 0.f}, a2[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int i = r; i < nv; i += lpi * kBatch) {
+            const int step = lpi * kBatch;
+            const int nfull = (nv / step) * step;
+            int i = r;
+            for (; i < nfull; i += step) {
                 uint4 raw[kBatch];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u)
-                    if (i + u * lpi < nv) raw[u] = p[i + u * lpi];
+                for (int u = 0; u < kBatch; ++u) raw[u] = p[i + u * lpi];
 #pragma unroll
-                for (int u = 0; u < kBatch; ++u)
-                    if (i + u * lpi < nv) {
-                        float v[V];
-                        unpack<T>(raw[u], v);
+                for (int u = 0; u < kBatch; ++u) {
+                    float v[V];
+                    unpack<T>(raw[u], v);
 #pragma unroll
-                        for (int j = 0; j < V; ++j) {
-                            const float d = v[j] - K;
-                            a1[j & 3] += d;
-                            a2[j & 3] = fmaf(d, d, a2[j & 3]);
-                        }
+                    for (int j = 0; j < V; ++j) {
+                        const float d = v[j] - K;
+                        a1[j & 3] += d;
+                        a2[j & 3] = fmaf(d, d, a2[j & 3]);
                     }
+                }
+            }
+            for (; i < nv; i += lpi) {
+                float v[V];
+                unpack<T>(p[i], v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const float d = v[j] - K;
+                    a1[j & 3] += d;
+                    a2[j & 3] = fmaf(d, d, a2[j & 3]);
+                }
             }
             s1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
             s2 = (a2[0] + a2[1]) + (a2[2] + a2[3]);

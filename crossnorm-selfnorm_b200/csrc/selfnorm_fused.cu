@@ -51,6 +51,7 @@ struct Args {
     unsigned stage_bytes;   // ring slot size (multiple of 128)
     unsigned off_chan, off_pair, off_data;   // smem offsets
     int keep_l2;            // experiment: evict-last policy on the ring loads
+    int dbg;                // experiment bits: 1 = apply warps skip the data loop, 2 = channel warps skip polling
     unsigned long long* trace;   // debug only (CNSN_FUSED_TRACE): [B][G][8] globaltimer stamps, else NULL
 };
 
@@ -90,20 +91,28 @@ __device__ __forceinline__ float2 smem_dot(const T* ix, const T* id, int M, int 
             const uint4* pd = reinterpret_cast<const uint4*>(id);
             const int nv = M / V;
             float a0[2] = {0.f, 0.f}, a1[2] = {0.f, 0.f};
-            for (int i = r; i < nv; i += lpi * 4) {
+            const int step = lpi * 4;
+            const int nfull = (nv / step) * step;
+            int i = r;
+            for (; i < nfull; i += step) {                   // full batches: no bounds checks (see fused_common.cuh)
                 uint4 rx[4], rd[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i + u * lpi < nv) { rx[u] = px[i + u * lpi]; rd[u] = pd[i + u * lpi]; }
+                for (int u = 0; u < 4; ++u) { rx[u] = px[i + u * lpi]; rd[u] = pd[i + u * lpi]; }
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (i + u * lpi < nv) {
-                        float vx[V], vd[V];
-                        unpack<T>(rx[u], vx);
-                        unpack<T>(rd[u], vd);
+                for (int u = 0; u < 4; ++u) {
+                    float vx[V], vd[V];
+                    unpack<T>(rx[u], vx);
+                    unpack<T>(rd[u], vd);
 #pragma unroll
-                        for (int e = 0; e < V; ++e) { a0[e & 1] = fmaf(vd[e], vx[e], a0[e & 1]); a1[e & 1] += vd[e]; }
-                    }
+                    for (int e = 0; e < V; ++e) { a0[e & 1] = fmaf(vd[e], vx[e], a0[e & 1]); a1[e & 1] += vd[e]; }
+                }
+            }
+            for (; i < nv; i += lpi) {
+                float vx[V], vd[V];
+                unpack<T>(px[i], vx);
+                unpack<T>(pd[i], vd);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { a0[e & 1] = fmaf(vd[e], vx[e], a0[e & 1]); a1[e & 1] += vd[e]; }
             }
             s0 = a0[0] + a0[1]; s1 = a1[0] + a1[1];
         } else {
@@ -263,30 +272,41 @@ __global__ void __launch_bounds__(kThreads, 1) k_sn_fused(const Args a) {
                         const T* sx = x + nc * M;
                         const T* sd_ = BWD ? dy + nc * M : nullptr;
                         T* dst = out + nc * M;
+                        if (a.dbg & 1) continue;
                         if (vec) {
                             const uint4* px = reinterpret_cast<const uint4*>(sx);
                             const uint4* pd = reinterpret_cast<const uint4*>(sd_);
                             uint4* po = reinterpret_cast<uint4*>(dst);
                             constexpr int U = BWD ? 4 : 8;   // independent 128-bit loads in flight per lane and tensor
-                            for (int v0 = vlo + r; v0 < vhi; v0 += lpi * U) {
+                            const int step = lpi * U;
+                            const int vfull = vlo + ((vhi - vlo) / step) * step;
+                            int v0 = vlo + r;
+                            for (; v0 < vfull; v0 += step) {         // full batches: no bounds checks
                                 uint4 rx[U], rd[U];
 #pragma unroll
-                                for (int u = 0; u < U; ++u)
-                                    if (v0 + u * lpi < vhi) {
-                                        rx[u] = ldg_hint(px + v0 + u * lpi, pol);          // L2 hit, last use
-                                        if (BWD) rd[u] = ldg_hint(pd + v0 + u * lpi, pol);
-                                    }
+                                for (int u = 0; u < U; ++u) {
+                                    rx[u] = ldg_hint(px + v0 + u * lpi, pol);              // L2 hit, last use
+                                    if (BWD) rd[u] = ldg_hint(pd + v0 + u * lpi, pol);
+                                }
 #pragma unroll
-                                for (int u = 0; u < U; ++u)
-                                    if (v0 + u * lpi < vhi) {
-                                        float vx[V], vd[V], vo[V];
-                                        unpack<T>(rx[u], vx);
-                                        if (BWD) unpack<T>(rd[u], vd);
+                                for (int u = 0; u < U; ++u) {
+                                    float vx[V], vd[V], vo[V];
+                                    unpack<T>(rx[u], vx);
+                                    if (BWD) unpack<T>(rd[u], vd);
 #pragma unroll
-                                        for (int e = 0; e < V; ++e)
-                                            vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : vx[e] * cb;
-                                        stg_stream(po + v0 + u * lpi, pack<T>(vo));
-                                    }
+                                    for (int e = 0; e < V; ++e)
+                                        vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : vx[e] * cb;
+                                    stg_stream(po + v0 + u * lpi, pack<T>(vo));
+                                }
+                            }
+                            for (; v0 < vhi; v0 += lpi) {
+                                float vx[V], vd[V], vo[V];
+                                unpack<T>(ldg_hint(px + v0, pol), vx);
+                                if (BWD) unpack<T>(ldg_hint(pd + v0, pol), vd);
+#pragma unroll
+                                for (int e = 0; e < V; ++e)
+                                    vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : vx[e] * cb;
+                                stg_stream(po + v0, pack<T>(vo));
                             }
                         } else {
                             for (int e = r; e < M; e += lpi)
@@ -326,7 +346,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sn_fused(const Args a) {
                 while (*issued < g) { __nanosleep(200); if (++spins > kWaitLimit) __trap(); }
             }
             float ra = 0.f, rb = 0.f, rq = 0.f, rw0 = 0.f, rw1 = 0.f;   // lane cl: per-channel results
-            if (BWD || a.training) {
+            if ((BWD || a.training) && !(a.dbg & 2)) {
                 const float2* pbase = a.pairs + (size_t)g * kk * N;   // [kk][N], contiguous
                 unsigned pend = 0;                           // bit j: word lane+32j not yet seen
                 for (int j = 0; j < nslots; ++j) if (lane + 32 * j < total) pend |= 1u << j;
@@ -502,6 +522,7 @@ static int launch(Args& a, int dtype, unsigned smem_total, cudaStream_t stream) 
     if (e != cudaSuccess) return (int)e;
     a.trace = nullptr;
     a.keep_l2 = getenv("CNSN_FUSED_KEEP") ? 1 : 0;
+    a.dbg = getenv("CNSN_FUSED_DBG") ? atoi(getenv("CNSN_FUSED_DBG")) : 0;
     const char* trace_path = BWD ? getenv("CNSN_FUSED_TRACE_BWD") : getenv("CNSN_FUSED_TRACE");   // debug: per-group timestamps
     const size_t trace_bytes = (size_t)a.sch.B * a.sch.G * 8 * sizeof(unsigned long long);
     if (trace_path) {

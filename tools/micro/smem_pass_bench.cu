@@ -1,5 +1,5 @@
-// Microbenchmark: cycles for one warp to run the two-pass smem statistics over one 56x56 fp32 plane,
-// alone and with 1..15 other warps doing the same on their own planes.
+// Microbenchmark: cycles for one warp to run the fused kernel's smem statistics (smem_mean_m2) over one
+// 56x56 fp32 plane, alone and with other warps doing the same on their own planes.
 #include <cstdio>
 #include "../../crossnorm-selfnorm_b200/csrc/fused_common.cuh"
 using namespace cnsn; using namespace cnsn::fused;
@@ -15,22 +15,24 @@ __global__ void k(int nwarps, int M, long long* out, float* sink) {
         long long t0 = clock64();
         float2 r = smem_mean_m2<float>(data + warp * M, M, lane, 32, true, true);
         long long t1 = clock64();
-        if (lane == 0) { out[blockIdx.x * 16 + warp] = t1 - t0; sink[blockIdx.x * 16 + warp] = r.x + r.y; }
+        float sdv = sqrtf(r.y / (float)(M - 1) + 1e-12f);
+        long long t2 = clock64();
+        if (lane == 0) { out[blockIdx.x * 48 + warp * 3] = t1 - t0; out[blockIdx.x * 48 + warp * 3 + 1] = t2 - t1; sink[blockIdx.x * 16 + warp] = r.x + sdv; }
     }
 }
 int main() {
     const int M = 3136;
     long long* out; float* sink;
-    cudaMalloc(&out, 148 * 16 * 8); cudaMalloc(&sink, 148 * 16 * 4);
+    cudaMalloc(&out, 148 * 48 * 8); cudaMalloc(&sink, 148 * 16 * 4);
     cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * M * 4);
     for (int nw : {1, 2, 4, 8, 16}) {
         for (int rep = 0; rep < 2; ++rep) {
             k<<<148, 512, 16 * M * 4>>>(nw, M, out, sink);
             cudaDeviceSynchronize();
         }
-        long long h[16];
+        long long h[48];
         cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
-        printf("warps=%2d cycles(warp0)=%lld (warp last)=%lld err=%s\n", nw, h[0], h[nw - 1], cudaGetErrorString(cudaGetLastError()));
+        printf("warps=%2d smem_mean_m2 cycles(warp0)=%lld (last)=%lld  sqrt/div tail=%lld  err=%s\n", nw, h[0], h[(nw - 1) * 3], h[1], cudaGetErrorString(cudaGetLastError()));
     }
     return 0;
 }
