@@ -15,7 +15,7 @@ namespace cnsn {
 namespace fused {
 
 constexpr int kStatsWarps = 8;
-constexpr int kApplyWarps = 12;                  // the apply stream is latency-bound per warp (L2 round trips): more warps,
+constexpr int kApplyWarps = 16;                  // the apply stream is latency-bound per warp (L2 round trips): more warps,
 constexpr int kApplyTeam = 1;                    //   warps per unit (teams of 3 cut the per-unit latency but measured slower overall)
 constexpr int kApplyTeams = kApplyWarps / kApplyTeam;
 constexpr int kWgThreads = 256;                 // threads in the stats / apply warpgroups

@@ -260,11 +260,21 @@ int selfnorm_fused_bwd(const void* x, const void* dy, void* dx, int dtype, int N
                        float* mu, float* sd, float* gate, float* shat, float* r,
                        const cnsn_gate_grads* dg, float* scratch_floats, cudaStream_t stream);
 }
-// CNSN_SELFNORM_IMPL=v1 forces the three-kernel path (A/B measurements); unset = the two-stream
-// fused kernels (selfnorm_fused.cu) where they apply.
+namespace cluster {
+int selfnorm_cluster_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                         const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
+                         float* mu, float* sd, float* gate, float* shat, float* r, cudaStream_t stream);
+int selfnorm_cluster_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                         const cnsn_gate_params* g, int training,
+                         float* mu, float* sd, float* gate, float* shat, float* r,
+                         const cnsn_gate_grads* dg, cudaStream_t stream);
+}
+// CNSN_SELFNORM_IMPL selects the path for A/B measurements: "v1" = three kernels, "cluster" = one 16-CTA
+// cluster per channel (selfnorm_cluster.cu), unset = the default dispatch.
 static int impl_choice() {
     const char* e = getenv("CNSN_SELFNORM_IMPL");
-    return (e && e[0] == 'v') ? 1 : 0;
+    if (!e) return 0;
+    return e[0] == 'v' ? 1 : e[0] == 'c' ? 2 : 0;
 }
 
 static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
@@ -294,6 +304,12 @@ extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C
     const int M = H * W;
     const long long inst = (long long)N * C;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!two && impl_choice() == 2) {
+        const int frc = cluster::selfnorm_cluster_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
+                                                      save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
+                                                      save + L.r_g, s);
+        if (frc != -100) return frc;
+    }
     if (!two && impl_choice() != 1) {
         const int frc = fused::selfnorm_fused_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
                                                   save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
@@ -337,6 +353,12 @@ extern "C" int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dt
     // Backward: the fused kernels move the ideal 3*S but are not faster than the three-kernel path yet
     // (profiles/README.md), so they are opt-in: CNSN_SELFNORM_BWD=fused.
     const char* bsel = getenv("CNSN_SELFNORM_BWD");
+    if (!two && impl_choice() == 2) {
+        float* sv = const_cast<float*>(save);
+        const int frc = cluster::selfnorm_cluster_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
+                                                      sv + L.g, sv + L.shat_g, sv + L.r_g, dg, s);
+        if (frc != -100) return frc;
+    }
     if (!two && impl_choice() == 0 && bsel && bsel[0] == 'f') {
         float* sv = const_cast<float*>(save);
         const int frc = fused::selfnorm_fused_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,

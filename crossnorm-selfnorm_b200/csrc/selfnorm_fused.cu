@@ -278,35 +278,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_sn_fused(const Args a) {
                             const uint4* pd = reinterpret_cast<const uint4*>(sd_);
                             uint4* po = reinterpret_cast<uint4*>(dst);
                             constexpr int U = BWD ? 4 : 8;   // independent 128-bit loads in flight per lane and tensor
-                            const int step = lpi * U;
-                            const int vfull = vlo + ((vhi - vlo) / step) * step;
-                            int v0 = vlo + r;
-                            for (; v0 < vfull; v0 += step) {         // full batches: no bounds checks
-                                uint4 rx[U], rd[U];
+                            // Full-duty register ring: U loads per tensor stay in flight per lane; a slot's register is
+                            // refilled with slot s+U as soon as it has been consumed.  Out-of-range slots are clamped
+                            // for the load and predicated for the store (no branch regions in the loop).
+                            const int span = vhi - vlo;
+                            const int nsl = (span + lpi - 1) / lpi;                   // slots per lane
+                            uint4 rx[U], rd[U];
+#pragma unroll
+                            for (int u = 0; u < U; ++u) {
+                                const int v = vlo + min(r + lpi * u, span - 1);
+                                rx[u] = ldg_hint(px + v, pol);                        // L2 hit, last use
+                                if (BWD) rd[u] = ldg_hint(pd + v, pol);
+                            }
+                            for (int s0 = 0; s0 < nsl; s0 += U) {
 #pragma unroll
                                 for (int u = 0; u < U; ++u) {
-                                    rx[u] = ldg_hint(px + v0 + u * lpi, pol);              // L2 hit, last use
-                                    if (BWD) rd[u] = ldg_hint(pd + v0 + u * lpi, pol);
-                                }
-#pragma unroll
-                                for (int u = 0; u < U; ++u) {
+                                    const int o = r + lpi * (s0 + u);
                                     float vx[V], vd[V], vo[V];
                                     unpack<T>(rx[u], vx);
                                     if (BWD) unpack<T>(rd[u], vd);
 #pragma unroll
                                     for (int e = 0; e < V; ++e)
                                         vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : vx[e] * cb;
-                                    stg_stream(po + v0 + u * lpi, pack<T>(vo));
+                                    if (o < span) stg_stream(po + vlo + o, pack<T>(vo));
+                                    if (s0 + u + U < nsl) {                           // warp-uniform
+                                        const int vn = vlo + min(o + lpi * U, span - 1);
+                                        rx[u] = ldg_hint(px + vn, pol);
+                                        if (BWD) rd[u] = ldg_hint(pd + vn, pol);
+                                    }
                                 }
-                            }
-                            for (; v0 < vhi; v0 += lpi) {
-                                float vx[V], vd[V], vo[V];
-                                unpack<T>(ldg_hint(px + v0, pol), vx);
-                                if (BWD) unpack<T>(ldg_hint(pd + v0, pol), vd);
-#pragma unroll
-                                for (int e = 0; e < V; ++e)
-                                    vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : vx[e] * cb;
-                                stg_stream(po + v0, pack<T>(vo));
                             }
                         } else {
                             for (int e = r; e < M; e += lpi)

@@ -283,9 +283,12 @@ def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatc
     fz = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
     monkeypatch.delenv("CNSN_FUSED_FORCE")
     monkeypatch.delenv("CNSN_SELFNORM_BWD")
+    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "cluster")                                # 16-CTA cluster per channel (falls
+    cl = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)         # back where it does not apply)
+    monkeypatch.delenv("CNSN_SELFNORM_IMPL")
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     chk = close32 if dtype == torch.float32 else close16
-    for res in (r, v1, fz):
+    for res in (r, v1, fz, cl):
         chk(res["y"], o["y"], "y")
         chk(res["dx"], o["dx"], "dx")
         for k in ("dg_w", "dg_gamma", "dg_beta"):

@@ -20,7 +20,7 @@ g = torch.Generator(device=dev).manual_seed(0)
 x = (torch.randn(shape, device=dev, generator=g) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, device=dev, generator=g))
      + torch.randn(N, C, 1, 1, device=dev, generator=g)).to(dt).requires_grad_(True)
 dy = torch.randn(shape, device=dev, generator=g).to(dt)
-sn = M.SelfNorm(C).to(dev).train()
+sn = M.SelfNorm(C).to(dev).train(os.environ.get("PERF_EVAL") is None)
 S = x.numel() * x.element_size()
 ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
 for i in range(5):
@@ -37,6 +37,6 @@ torch.cuda.synchronize()
 f = sorted(e[0].elapsed_time(e[1]) for e in ev)
 b = sorted(e[1].elapsed_time(e[2]) for e in ev)
 fm, bm = f[len(f) // 2], b[len(b) // 2]
-tag = "impl=%s ctas=%s" % (os.environ.get("CNSN_SELFNORM_IMPL", "auto"), os.environ.get("CNSN_FUSED_CTAS", "all"))
+tag = "%simpl=%s ctas=%s" % ("EVAL " if os.environ.get("PERF_EVAL") else "", os.environ.get("CNSN_SELFNORM_IMPL", "auto"), os.environ.get("CNSN_FUSED_CTAS", "all"))
 print("%s %s %s | fwd %.3f ms (min %.3f) %.0f GB/s | bwd %.3f ms (min %.3f) %.0f GB/s | fwd+bwd %.0f GB/s" % (
     shape, str(dt).split(".")[-1], tag, fm, f[0], 2 * S / fm / 1e6, bm, b[0], 3 * S / bm / 1e6, 5 * S / (fm + bm) / 1e6))

@@ -18,10 +18,24 @@ sn = M.SelfNorm(shape[1]).cuda().train()
 for _ in range(3):
     sn(x)
 torch.cuda.synchronize()
-os.environ["CNSN_FUSED_TRACE"] = out
-sn(x)
-torch.cuda.synchronize()
-del os.environ["CNSN_FUSED_TRACE"]
+bwd = os.environ.get("TRACE_BWD") is not None
+if bwd:
+    os.environ["CNSN_SELFNORM_BWD"] = "fused"
+    xr = x.clone().requires_grad_(True)
+    dy = torch.randn_like(x)
+    for _ in range(2):
+        torch.autograd.grad(sn(xr), xr, dy)
+    torch.cuda.synchronize()
+    y = sn(xr)
+    os.environ["CNSN_FUSED_TRACE_BWD"] = out
+    torch.autograd.grad(y, xr, dy)
+    torch.cuda.synchronize()
+    del os.environ["CNSN_FUSED_TRACE_BWD"]
+else:
+    os.environ["CNSN_FUSED_TRACE"] = out
+    sn(x)
+    torch.cuda.synchronize()
+    del os.environ["CNSN_FUSED_TRACE"]
 raw = open(out, "rb").read()
 G, S, B, kk = struct.unpack("4i", raw[:16])
 t = np.frombuffer(raw[16:], dtype=np.uint64).reshape(B, G, 8).astype(np.int64)
