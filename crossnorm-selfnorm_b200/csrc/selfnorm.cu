@@ -246,7 +246,8 @@ struct SaveLayout {           // offsets (in floats) into the save block
         r_g = two ? 6 * nc : 4 * nc;
         r_f = r_g + C;
         scratch = (r_g + (two ? 2 : 1) * (size_t)C + 1) & ~(size_t)1;   // 8-byte aligned
-        total = scratch + 2 * nc;                      // [C][N] published (mu, sd) words of the fused kernel
+        total = scratch + 2 * nc + 4 * (size_t)C + 8;  // [C][N] published (mu, sd) words of the fused / flow kernels,
+                                                       // then the flow kernel's [C] constants, counters, ticket
     }
 };
 
@@ -269,12 +270,25 @@ int selfnorm_cluster_bwd(const void* x, const void* dy, void* dx, int dtype, int
                          float* mu, float* sd, float* gate, float* shat, float* r,
                          const cnsn_gate_grads* dg, cudaStream_t stream);
 }
+namespace flow {
+size_t scratch_floats(int N, int C);
+int selfnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                      const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
+                      float* mu, float* sd, float* gate, float* shat, float* r, float* scratch,
+                      cudaStream_t stream);
+int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                      const cnsn_gate_params* g, int training,
+                      float* mu, float* sd, float* gate, float* shat, float* r,
+                      const cnsn_gate_grads* dg, float* scratch, cudaStream_t stream);
+}
 // CNSN_SELFNORM_IMPL selects the path for A/B measurements: "v1" = three kernels, "cluster" = one 16-CTA
-// cluster per channel (selfnorm_cluster.cu), unset = the default dispatch.
+// cluster per channel (selfnorm_cluster.cu), "flow" = ticket-ordered dataflow kernel (selfnorm_flow.cu),
+// "persistent" = the persistent fused kernels (selfnorm_fused.cu), unset = the default dispatch.
+enum { kImplAuto = 0, kImplV1 = 1, kImplCluster = 2, kImplFlow = 3, kImplPersistent = 4 };
 static int impl_choice() {
     const char* e = getenv("CNSN_SELFNORM_IMPL");
-    if (!e) return 0;
-    return e[0] == 'v' ? 1 : e[0] == 'c' ? 2 : 0;
+    if (!e) return kImplAuto;
+    return e[0] == 'v' ? kImplV1 : e[0] == 'c' ? kImplCluster : e[0] == 'f' ? kImplFlow : e[0] == 'p' ? kImplPersistent : kImplAuto;
 }
 
 static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
@@ -288,7 +302,7 @@ extern "C" size_t cnsn_selfnorm_save_floats(int N, int C, int is_two) {
 }
 extern "C" size_t cnsn_selfnorm_workspace_floats(int N, int C, int is_two) {
     (void)is_two;
-    return 4 * (size_t)N * C;               // sxy | st | cb | cc   (fused path: [C][N] published words)
+    return 4 * (size_t)N * C + 4 * (size_t)C + 8;   // sxy | st | cb | cc   (fused / flow paths: [C][N] published words, ...)
 }
 
 extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
@@ -304,13 +318,21 @@ extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C
     const int M = H * W;
     const long long inst = (long long)N * C;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!two && impl_choice() == 2) {
+    // Default: the ticket-ordered dataflow kernel (measured faster than the three-kernel path and at least as
+    // fast as the persistent kernels on every shape of the r01 sweep, profiles/README.md).
+    if (!two && (impl_choice() == kImplFlow || impl_choice() == kImplAuto)) {
+        const int frc = flow::selfnorm_flow_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
+                                                save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
+                                                save + L.r_g, save + L.scratch, s);
+        if (frc != -100) return frc;
+    }
+    if (!two && impl_choice() == kImplCluster) {
         const int frc = cluster::selfnorm_cluster_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
                                                       save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
                                                       save + L.r_g, s);
         if (frc != -100) return frc;
     }
-    if (!two && impl_choice() != 1) {
+    if (!two && impl_choice() == kImplPersistent) {
         const int frc = fused::selfnorm_fused_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
                                                   save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
                                                   save + L.r_g, save + L.scratch, s);
@@ -350,16 +372,21 @@ extern "C" int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dt
     const size_t nc = (size_t)inst;
     float* sxy = workspace; float* st = workspace + nc; float* cb = workspace + 2 * nc; float* cc = workspace + 3 * nc;
     cudaStream_t s = (cudaStream_t)stream;
-    // Backward: the fused kernels move the ideal 3*S but are not faster than the three-kernel path yet
-    // (profiles/README.md), so they are opt-in: CNSN_SELFNORM_BWD=fused.
-    const char* bsel = getenv("CNSN_SELFNORM_BWD");
-    if (!two && impl_choice() == 2) {
+    // Default: the dataflow kernel (3*S of HBM traffic).  The persistent and cluster kernels stay selectable for
+    // A/B measurements (CNSN_SELFNORM_IMPL=persistent|cluster|v1).
+    if (!two && (impl_choice() == kImplFlow || impl_choice() == kImplAuto)) {
+        float* sv = const_cast<float*>(save);
+        const int frc = flow::selfnorm_flow_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
+                                                sv + L.g, sv + L.shat_g, sv + L.r_g, dg, workspace, s);
+        if (frc != -100) return frc;
+    }
+    if (!two && impl_choice() == kImplCluster) {
         float* sv = const_cast<float*>(save);
         const int frc = cluster::selfnorm_cluster_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
                                                       sv + L.g, sv + L.shat_g, sv + L.r_g, dg, s);
         if (frc != -100) return frc;
     }
-    if (!two && impl_choice() == 0 && bsel && bsel[0] == 'f') {
+    if (!two && impl_choice() == kImplPersistent) {
         float* sv = const_cast<float*>(save);
         const int frc = fused::selfnorm_fused_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
                                                   sv + L.g, sv + L.shat_g, sv + L.r_g, dg, workspace, s);

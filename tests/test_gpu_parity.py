@@ -228,10 +228,13 @@ def test_selfnorm_permutation_equivariance(mod):
     assert torch.allclose(m1(x)[p], m2(x[p]), atol=1e-6)
 
 
-def test_selfnorm_north_star_shape_properties(mod):
+@pytest.mark.parametrize("impl", ["auto", "persistent"])
+def test_selfnorm_north_star_shape_properties(mod, impl, monkeypatch):
     """Full-size (256,256,56,56) fp32: too big for the numpy oracle in seconds, so check
     size-independent properties: y/x is constant per instance and equals the saved gate; linearity
     of backward in dy; and a strided subset of instances against the oracle restricted to 2 channels."""
+    if impl != "auto":
+        monkeypatch.setenv("CNSN_SELFNORM_IMPL", impl)
     N, C, Hh, Ww = 256, 256, 56, 56
     g = torch.Generator(device=DEV).manual_seed(0)
     x = torch.randn(N, C, Hh, Ww, device=DEV, generator=g) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, device=DEV, generator=g)) \
@@ -266,8 +269,9 @@ FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.floa
 @pytest.mark.parametrize("shape,dtype", FUSED_SHAPES)
 @pytest.mark.parametrize("training", [True, False])
 def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatch):
-    """Shapes large enough for the persistent kernels: the default dispatch, the three-kernel path, the
-    two-stream fused kernels (forward and backward, forced), all against the oracle on identical inputs."""
+    """Every SelfNorm code path -- the default dispatch (dataflow kernel), the three-kernel path, the persistent
+    two-stream kernels (forced), the cluster kernels, the dataflow kernel in ticket and blockIdx order -- against
+    the oracle on identical inputs."""
     x = O.varied_input(shape, seed=sum(shape), dtype=np.float32, relu=True)
     dy = np.random.RandomState(1).standard_normal(shape).astype(np.float32)
     if dtype != torch.float32:
@@ -278,17 +282,23 @@ def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatc
     monkeypatch.setenv("CNSN_SELFNORM_IMPL", "v1")                                     # three-kernel path
     v1 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
     monkeypatch.delenv("CNSN_SELFNORM_IMPL")
-    monkeypatch.setenv("CNSN_FUSED_FORCE", "1")                                        # two-stream fused fwd + bwd
-    monkeypatch.setenv("CNSN_SELFNORM_BWD", "fused")
+    monkeypatch.setenv("CNSN_FUSED_FORCE", "1")                                        # persistent two-stream fwd + bwd
+    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "persistent")
     fz = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
     monkeypatch.delenv("CNSN_FUSED_FORCE")
-    monkeypatch.delenv("CNSN_SELFNORM_BWD")
     monkeypatch.setenv("CNSN_SELFNORM_IMPL", "cluster")                                # 16-CTA cluster per channel (falls
     cl = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)         # back where it does not apply)
+    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "flow")                                   # ticket-ordered dataflow kernel
+    fl = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.setenv("CNSN_FLOW_ORDER", "1")                                         # blockIdx order, look-ahead 1
+    monkeypatch.setenv("CNSN_FLOW_D", "1")
+    fl2 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.delenv("CNSN_FLOW_ORDER")
+    monkeypatch.delenv("CNSN_FLOW_D")
     monkeypatch.delenv("CNSN_SELFNORM_IMPL")
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     chk = close32 if dtype == torch.float32 else close16
-    for res in (r, v1, fz, cl):
+    for res in (r, v1, fz, cl, fl, fl2):
         chk(res["y"], o["y"], "y")
         chk(res["dx"], o["dx"], "dx")
         for k in ("dg_w", "dg_gamma", "dg_beta"):

@@ -1,7 +1,7 @@
 """Quick A/B timing of SelfNorm forward / backward (CUDA events, inputs larger than L2 by default).
 
     python tools/perf_selfnorm.py [N,C,H,W] [f32|bf16] [steps]
-Environment knobs are read by the library per call: CNSN_SELFNORM_IMPL=v1, CNSN_SELFNORM_BWD=fused, CNSN_FUSED_FORCE=1, CNSN_FUSED_CTAS=<n>.
+Environment knobs are read by the library per call: CNSN_SELFNORM_IMPL=v1|persistent|cluster|flow, CNSN_FUSED_FORCE=1, CNSN_FUSED_CTAS=<n>.
 """
 import os
 import sys

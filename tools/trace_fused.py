@@ -15,12 +15,12 @@ out = sys.argv[2] if len(sys.argv) > 2 else "gpurun_out/trace.bin"
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
 x = torch.randn(shape, device="cuda:0")
 sn = M.SelfNorm(shape[1]).cuda().train()
+os.environ["CNSN_SELFNORM_IMPL"] = "persistent"      # the traced kernels are the persistent ones (selfnorm_fused.cu)
 for _ in range(3):
     sn(x)
 torch.cuda.synchronize()
 bwd = os.environ.get("TRACE_BWD") is not None
 if bwd:
-    os.environ["CNSN_SELFNORM_BWD"] = "fused"
     xr = x.clone().requires_grad_(True)
     dy = torch.randn_like(x)
     for _ in range(2):
