@@ -246,7 +246,7 @@ struct SaveLayout {           // offsets (in floats) into the save block
         r_g = two ? 6 * nc : 4 * nc;
         r_f = r_g + C;
         scratch = (r_g + (two ? 2 : 1) * (size_t)C + 1) & ~(size_t)1;   // 8-byte aligned
-        total = scratch + 2 * nc + 4 * (size_t)C + 8;  // [C][N] published (mu, sd) words of the fused / flow kernels,
+        total = scratch + 2 * nc + 36 * (size_t)C + 8;  // [C][N] published (mu, sd) words of the fused / flow kernels,
                                                        // then the flow kernel's [C] constants, counters, ticket
     }
 };
@@ -302,7 +302,7 @@ extern "C" size_t cnsn_selfnorm_save_floats(int N, int C, int is_two) {
 }
 extern "C" size_t cnsn_selfnorm_workspace_floats(int N, int C, int is_two) {
     (void)is_two;
-    return 4 * (size_t)N * C + 4 * (size_t)C + 8;   // sxy | st | cb | cc   (fused / flow paths: [C][N] published words, ...)
+    return 4 * (size_t)N * C + 36 * (size_t)C + 8;   // sxy | st | cb | cc   (fused / flow paths: [C][N] published words, ...)
 }
 
 extern "C" int cnsn_selfnorm_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,

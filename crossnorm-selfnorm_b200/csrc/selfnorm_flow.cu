@@ -28,13 +28,16 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "fused_common.cuh"
 
 namespace cnsn {
 namespace flow {
 
+using fused::smem_u32;
+
 constexpr int kT = 256;                 // threads per CTA
-constexpr int kU = 4;                   // 128-bit loads in flight per thread and tensor
+constexpr int kUReg = 4;                // 128-bit loads in flight per thread and tensor (register path)
+constexpr int kUTma = 2;                // shared-memory reads batched per thread and tensor (TMA path)
 constexpr unsigned kSpin = 1u << 22;    // bounded polls (>= 64 ns each): trap instead of hanging the GPU
 
 struct FArgs {
@@ -55,6 +58,8 @@ struct FArgs {
     unsigned* done;         // [C]    R items of the channel that have published
     unsigned* ready;        // [C]    channel constants are in chan[c]
     unsigned* ticket;       // [1]
+    int poll_ns;            // sleep between polls of ready[c]
+    unsigned long long* trace;   // debug only (CNSN_FLOW_TRACE): [items][8] globaltimer stamps, else NULL
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -106,9 +111,9 @@ __device__ __forceinline__ Moments team_merge(Moments a, Moments* sm) {
     for (int i = 1; i < WPT; ++i) r = merge(r, sm[w0 + i]);
     return r;
 }
-// Sums over the whole CTA (channel fold by the last R item).
-template <int K>
-__device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[kT / 32]) {
+// Sums over the whole CTA of TH threads (channel fold by the last R item).
+template <int K, int TH>
+__device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[TH / 32]) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
@@ -122,25 +127,112 @@ __device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[kT / 32]) {
     for (int k = 0; k < K; ++k) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kT / 32; ++w) s += sm[k][w];
+        for (int w = 0; w < TH / 32; ++w) s += sm[k][w];
         v[k] = s;
     }
 }
 
-template <typename T, bool BWD, int TPI>
-__global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
+// Fold the N published words of channel c into the channel constants (whole CTA of TH threads; the caller has
+// made the words visible: fence + atomic counter).  Forward: BatchNorm batch mean / rstd of s = w0*mu + w1*sd,
+// running statistics (models/cnsn.py:121,138); backward: dgamma, dbeta, dw and the two batch-norm backward scalars.
+template <bool BWD, int TH>
+__device__ __forceinline__ void channel_fold(const FArgs& a, unsigned c, float (*s_f)[TH / 32]) {
+    const int N = a.N, C = a.C;
+    const float2* pb = a.pub + (size_t)c * N;
+    const float invN = 1.f / N;
+    if (!BWD) {
+        const float w0 = a.w[2 * c], w1 = a.w[2 * c + 1];
+        float m, q;
+        if (a.training) {
+            float v[1] = {0.f};
+            for (int k = threadIdx.x; k < N; k += TH) { const float2 p = __ldcg(pb + k); v[0] += fmaf(w0, p.x, w1 * p.y); }
+            cta_sums<1, TH>(v, s_f);
+            m = v[0] / N;
+            v[0] = 0.f;
+            for (int k = threadIdx.x; k < N; k += TH) {
+                const float2 p = __ldcg(pb + k);
+                const float d = fmaf(w0, p.x, w1 * p.y) - m;
+                v[0] = fmaf(d, d, v[0]);
+            }
+            cta_sums<1, TH>(v, s_f);
+            q = v[0] / N;                // biased variance normalises (BatchNorm semantics)
+            if (threadIdx.x == 0) {
+                a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * m;
+                a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * (q * N / (N - 1.f));
+                if (a.nbt && c == 0) *a.nbt += 1;
+            }
+        } else {
+            m = a.run_mean[c]; q = a.run_var[c];
+        }
+        if (threadIdx.x == 0) {
+            const float rstd = 1.f / sqrtf(q + a.bn_eps);
+            a.r[c] = rstd;
+            a.chan[c] = make_float2(m, rstd);
+        }
+    } else {
+        const float ga = a.gamma[c], rstd = a.r[c];
+        float v[2] = {0.f, 0.f};
+        for (int k = threadIdx.x; k < N; k += TH) { const float2 p = __ldcg(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
+        cta_sums<2, TH>(v, s_f);
+        const float dgam = v[0], dbet = v[1];
+        const float k1 = a.training ? ga * dbet * invN : 0.f, k2 = a.training ? ga * dgam * invN : 0.f;
+        v[0] = v[1] = 0.f;
+        for (int k = threadIdx.x; k < N; k += TH) {
+            const float2 p = __ldcg(pb + k);
+            const size_t i = (size_t)k * C + c;
+            const float ds = rstd * (p.x * ga - k1 - p.y * k2);
+            v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
+        }
+        cta_sums<2, TH>(v, s_f);
+        if (threadIdx.x == 0) {
+            a.dgamma[c] = dgam; a.dbeta[c] = dbet;
+            a.dw[2 * c] = v[0]; a.dw[2 * c + 1] = v[1];
+            a.chan[c] = make_float2(k1, k2);
+        }
+    }
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define CNSN_FTRACE(slot)                                                                      \
+    do {                                                                                       \
+        if (a.trace && threadIdx.x == 0) a.trace[(size_t)t * 8 + (slot)] = gtime();             \
+    } while (0)
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+// TMA = true: the item's planes are fetched by cp.async.bulk into shared memory (one thread issues, the
+// whole item is in flight at once, no registers are tied up); TMA = false: 128-bit loads into registers.
+template <typename T, bool BWD, int TPI, bool TMA, int KU>
+__global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_sn_flow(const FArgs a) {
     constexpr int I = kT / TPI;          // instances per item
     constexpr int V = VecOf<T>::n;
+    constexpr int kU = TMA ? kUTma : KU;
+    extern __shared__ __align__(128) unsigned char dsm[];    // TMA: [mbarrier | I planes of x | I planes of dy]
     __shared__ unsigned s_word;
     __shared__ float s_f[2][kT / 32];
     __shared__ Moments s_m[kT / 32];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
 
     // ---- which item am I --------------------------------------------------------------------
     unsigned t = blockIdx.x;
+    if (TMA && threadIdx.x == 0) {
+        fused::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     if (a.order == 0) {
         if (threadIdx.x == 0) s_word = atomicAdd(a.ticket, 1u);
         __syncthreads();
         t = s_word;
+    } else if (TMA) {
+        __syncthreads();
     }
     const unsigned nI = (unsigned)a.nI, D = (unsigned)a.D, C = (unsigned)a.C;
     bool isA;
@@ -166,6 +258,23 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
     const uint4* px = reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + nc * M);
     const uint4* pd = BWD ? reinterpret_cast<const uint4*>(static_cast<const T*>(a.dy) + nc * M) : nullptr;
     constexpr int kStep = TPI * kU;
+    // TMA: shared-memory addresses of this team's planes; warp 0 issues the bulk copies (lane i: instance i).
+    const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
+    const uint32_t sx = smem_u32(dsm) + 128u + (threadIdx.x / TPI) * pbytes;
+    const uint32_t sdy = sx + (unsigned)I * pbytes;
+    if (TMA && threadIdx.x < 32) {
+        const int first = (int)j * I;
+        const int nlive = min(I, N - first);
+        const uint64_t pol = isA ? l2_policy_evict_first() : (a.keep ? l2_policy_evict_last() : l2_policy_evict_normal());
+        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        __syncwarp();
+        for (int q = threadIdx.x; q < nlive; q += 32) {
+            const size_t off = ((size_t)(first + q) * C + c) * M;
+            unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
+            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+        }
+    }
 
     if (!isA) {
         // =============================================================== R item
@@ -173,14 +282,20 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
         float sxy = 0.f, pre_g = 0.f, pre_s = 0.f;
         if (BWD && live && r == 0) { pre_g = a.gate[nc]; pre_s = a.shat[nc]; }   // issued ahead of the plane loads
         Moments acc = moments_zero();
+        if (TMA) fused::mbar_wait(bar, 0);
         for (int i0 = r; i0 < nv; i0 += kStep) {
             uint4 rx[kU], rd[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int i = i0 + u * TPI;
                 if (live && i < nv) {
-                    rx[u] = a.keep ? ldg_hint(px + i, pol) : ldg_stream(px + i);
-                    if (BWD) rd[u] = a.keep ? ldg_hint(pd + i, pol) : ldg_stream(pd + i);
+                    if (TMA) {
+                        rx[u] = lds128(sx + 16u * i);
+                        if (BWD) rd[u] = lds128(sdy + 16u * i);
+                    } else {
+                        rx[u] = a.keep ? ldg_hint(px + i, pol) : ldg_stream(px + i);
+                        if (BWD) rd[u] = a.keep ? ldg_hint(pd + i, pol) : ldg_stream(pd + i);
+                    }
                 }
             }
 #pragma unroll
@@ -220,58 +335,7 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
         __syncthreads();
         if (s_word != nI - 1) return;
         __threadfence();
-        const float2* pb = a.pub + (size_t)c * N;
-        const float invN = 1.f / N;
-        if (!BWD) {
-            const float w0 = a.w[2 * c], w1 = a.w[2 * c + 1];
-            float m, q;
-            if (a.training) {
-                float v[1] = {0.f};
-                for (int k = threadIdx.x; k < N; k += kT) { const float2 p = __ldcg(pb + k); v[0] += fmaf(w0, p.x, w1 * p.y); }
-                cta_sums<1>(v, s_f);
-                m = v[0] / N;
-                v[0] = 0.f;
-                for (int k = threadIdx.x; k < N; k += kT) {
-                    const float2 p = __ldcg(pb + k);
-                    const float d = fmaf(w0, p.x, w1 * p.y) - m;
-                    v[0] = fmaf(d, d, v[0]);
-                }
-                cta_sums<1>(v, s_f);
-                q = v[0] / N;                // biased variance normalises (BatchNorm semantics)
-                if (threadIdx.x == 0) {
-                    a.run_mean[c] = (1.f - a.momentum) * a.run_mean[c] + a.momentum * m;
-                    a.run_var[c] = (1.f - a.momentum) * a.run_var[c] + a.momentum * (q * N / (N - 1.f));
-                    if (a.nbt && c == 0) *a.nbt += 1;
-                }
-            } else {
-                m = a.run_mean[c]; q = a.run_var[c];
-            }
-            if (threadIdx.x == 0) {
-                const float rstd = 1.f / sqrtf(q + a.bn_eps);
-                a.r[c] = rstd;
-                a.chan[c] = make_float2(m, rstd);
-            }
-        } else {
-            const float ga = a.gamma[c], rstd = a.r[c];
-            float v[2] = {0.f, 0.f};
-            for (int k = threadIdx.x; k < N; k += kT) { const float2 p = __ldcg(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
-            cta_sums<2>(v, s_f);
-            const float dgam = v[0], dbet = v[1];
-            const float k1 = a.training ? ga * dbet * invN : 0.f, k2 = a.training ? ga * dgam * invN : 0.f;
-            v[0] = v[1] = 0.f;
-            for (int k = threadIdx.x; k < N; k += kT) {
-                const float2 p = __ldcg(pb + k);
-                const size_t i = (size_t)k * C + c;
-                const float ds = rstd * (p.x * ga - k1 - p.y * k2);
-                v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
-            }
-            cta_sums<2>(v, s_f);
-            if (threadIdx.x == 0) {
-                a.dgamma[c] = dgam; a.dbeta[c] = dbet;
-                a.dw[2 * c] = v[0]; a.dw[2 * c + 1] = v[1];
-                a.chan[c] = make_float2(k1, k2);
-            }
-        }
+        channel_fold<BWD, kT>(a, c, s_f);
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence();
@@ -289,12 +353,17 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
         for (int u = 0; u < kU; ++u) {
             const int i = i0 + u * TPI;
             if (live && i < nv) {
-                rx[u] = ldg_hint(px + i, pol);           // L2 hit (read D channels ago), last use
-                if (BWD) rd[u] = ldg_hint(pd + i, pol);
+                if (TMA) {
+                    rx[u] = lds128(sx + 16u * i);
+                    if (BWD) rd[u] = lds128(sdy + 16u * i);
+                } else {
+                    rx[u] = ldg_hint(px + i, pol);       // L2 hit (read D channels ago), last use
+                    if (BWD) rd[u] = ldg_hint(pd + i, pol);
+                }
             }
         }
     };
-    issue(r);                                            // the plane loads do not depend on the channel
+    if (!TMA) issue(r);                                  // the plane loads do not depend on the channel
     // ... nor do the saved per-instance statistics and the parameters: fetch them under the flag wait too
     float p_w0 = 0.f, p_w1 = 0.f, p_ga = 0.f, p_b = 0.f, p_gt = 0.f, p_mu = 0.f, p_sd = 1.f;
     if (live) {
@@ -328,6 +397,7 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
             cb = gt;
         }
     }
+    if (TMA) { fused::mbar_wait(bar, 0); issue(r); }
     for (int i0 = r;;) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -347,6 +417,253 @@ __global__ void __launch_bounds__(kT) k_sn_flow(const FArgs a) {
     }
 }
 
+// =============================================================================================
+// Shared-memory-resident variant: ONE item = reduce AND apply of I instances, the planes stay in shared
+// memory in between, so every byte crosses L2 exactly once in each direction (forward 2*S, backward 3*S of
+// HBM traffic AND of L2 traffic; the L2-resident variant above pays a second L2 read, and the L2 slices --
+// not HBM -- are what saturates first on B200: profiles/README.md).
+//
+//   CTA(ticket t): channel c = t / nI (channel-major), instances j*I .. j*I+I-1
+//     1. cp.async.bulk the planes (x [, dy]) into shared memory          (TMA, whole item in flight at once)
+//     2. per-instance reduction out of shared memory (forward: exact two-pass mean / variance), published as
+//        ONE aligned 8-byte word per instance into a sentinel-filled [C][N] area ("data is the flag": no
+//        fence, no counter)
+//     3. the CTA holding the channel's LAST ticket polls the channel's N words, folds them and publishes the
+//        channel constants as one 8-byte word; every other CTA of the channel polls that word
+//     4. rebuild the gate / backward coefficients, apply out of shared memory, stream the result out
+//
+// Deadlock freedom: tickets are handed out in increasing order, so the co-resident CTAs always include the
+// lowest unfinished tickets; a channel's nI items are consecutive tickets, so as long as the GPU can hold nI
+// CTAs at once (checked on the host with the occupancy API) the lowest unfinished channel is always completely
+// resident, none of its CTAs waits before it has published, and it completes.  All N planes of a channel (and
+// the next few) live in shared memory across the GPU: N*M*sizeof(T)*tensors must fit a fraction of 148 x 227 KB.
+__device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns) {
+    float2 v = fused::ll_peek(p);
+    unsigned spins = 0;
+    while (!fused::ll_valid(v)) {
+        __nanosleep(sleep_ns);
+        v = fused::ll_peek(p);
+        if (++spins > kSpin) __trap();
+    }
+    return v;
+}
+
+template <typename T, bool BWD, int TPI, int TH>
+__global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
+    constexpr int I = TH / TPI;
+    constexpr int V = VecOf<T>::n;
+    constexpr int kHold = 4;                                 // published words a folding thread keeps in registers
+    extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
+    __shared__ unsigned s_word;
+    __shared__ float2 s_chan;
+    __shared__ float s_f[2][TH / 32];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
+    if (threadIdx.x == 0) {
+        fused::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;   // the counter starts at 0xffffffff
+    }
+    __syncthreads();
+    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned c = t / nI, j = t - c * nI;
+    const int N = a.N, C = a.C, M = a.M;
+    CNSN_FTRACE(0);                                          // 0 ticket taken
+    const int n = (int)j * I + (int)(threadIdx.x / TPI);
+    const int r = threadIdx.x % TPI;
+    const bool live = n < N;
+    const size_t nc = (size_t)(live ? n : 0) * C + c;
+    const int nv = M / V;
+    const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
+    const uint32_t sx = smem_u32(dsm) + 128u + (threadIdx.x / TPI) * pbytes;
+    const uint32_t sdy = sx + (unsigned)I * pbytes;
+    if (threadIdx.x < 32) {                                  // lane q fetches instance q of the item
+        const int first = (int)j * I;
+        const int nlive = min(I, N - first);
+        const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
+        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        __syncwarp();
+        for (int q = threadIdx.x; q < nlive; q += 32) {
+            const size_t off = ((size_t)(first + q) * C + c) * M;
+            unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
+            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+        }
+    }
+    // everything that does not depend on the channel is fetched under the TMA latency
+    const bool folder = j == nI - 1;                         // holds the channel's last ticket
+    float pre_g = 0.f, pre_s = 0.f, p_w0, p_w1, p_ga, p_b, p_mu = 0.f, p_sd = 1.f, p_rm = 0.f, p_rv = 1.f;
+    p_w0 = a.w[2 * c]; p_w1 = a.w[2 * c + 1]; p_ga = a.gamma[c];
+    if (BWD) {
+        p_b = a.r[c];
+        if (live) { pre_g = a.gate[nc]; pre_s = a.shat[nc]; p_mu = a.mu[nc]; p_sd = a.sd[nc]; }
+    } else {
+        p_b = a.beta[c];
+        if (folder && threadIdx.x == 0) { p_rm = a.run_mean[c]; p_rv = a.run_var[c]; }
+    }
+    fused::mbar_wait(bar, 0);
+    CNSN_FTRACE(1);                                          // 1 planes landed
+
+    // ---- reduce out of shared memory -----------------------------------------------------------
+    float own_x = 0.f, own_y = 0.f;                          // this instance's published word
+    if (BWD) {
+        float s0 = 0.f, s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V], vd[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+                unpack<T>(lds128(sdy + 16u * i), vd);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { if (e & 1) s1 = fmaf(vd[e], vx[e], s1); else s0 = fmaf(vd[e], vx[e], s0); }
+            }
+        }
+        const float sxy = team_sum<TPI>(s0 + s1, s_f[0]);
+        own_x = sxy * pre_g * (1.f - pre_g); own_y = pre_s;
+    } else {                                                 // exact two-pass: the plane is on chip
+        float s0 = 0.f, s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { if (e & 1) s1 += vx[e]; else s0 += vx[e]; }
+            }
+        }
+        const float mean = team_sum<TPI>(s0 + s1, s_f[0]) * (1.f / M);
+        s0 = s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { const float d = vx[e] - mean; if (e & 1) s1 = fmaf(d, d, s1); else s0 = fmaf(d, d, s0); }
+            }
+        }
+        const float m2 = team_sum<TPI>(s0 + s1, s_f[1]);
+        own_x = mean; own_y = sqrtf(m2 / (M - 1.f) + a.eps);
+        if (live && r == 0) { a.mu[nc] = own_x; a.sd[nc] = own_y; }
+    }
+    if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    CNSN_FTRACE(2);                                          // 2 reduced + published
+
+    // ---- channel constants ------------------------------------------------------------------------
+    float2* flag = a.chan + 4u * c;                          // one 32-byte sector per channel
+    if (folder) {
+        const float2* pb = a.pub + (size_t)c * N;
+        const float invN = 1.f / N;
+        float2 hold[kHold];
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            const int k = threadIdx.x + u * TH;
+            hold[u] = make_float2(0.f, 0.f);
+            if (k < N) hold[u] = poll_word(pb + k, 100);
+        }
+        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100);   // N > kHold*TH: re-read below
+        CNSN_FTRACE(3);                                      // 3 (folder) all words of the channel seen
+        float v[2] = {0.f, 0.f};
+        float2 cst;
+        if (!BWD) {
+            float m = p_rm, q = p_rv;
+            if (a.training) {
+#pragma unroll
+                for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) v[0] += fmaf(p_w0, hold[u].x, p_w1 * hold[u].y);
+                for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] += fmaf(p_w0, p.x, p_w1 * p.y); }
+                cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[0]), reinterpret_cast<float(*)[TH / 32]>(s_f[0]));
+                m = v[0] / N;
+                v[1] = 0.f;
+#pragma unroll
+                for (int u = 0; u < kHold; ++u)
+                    if (threadIdx.x + u * TH < N) { const float d = fmaf(p_w0, hold[u].x, p_w1 * hold[u].y) - m; v[1] = fmaf(d, d, v[1]); }
+                for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
+                    const float2 p = fused::ll_peek(pb + k);
+                    const float d = fmaf(p_w0, p.x, p_w1 * p.y) - m;
+                    v[1] = fmaf(d, d, v[1]);
+                }
+                cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[1]), reinterpret_cast<float(*)[TH / 32]>(s_f[1]));
+                q = v[1] / N;                                // biased variance normalises (BatchNorm semantics)
+            }
+            // eval: thread 0 holds the running statistics; the other threads' m, q are unused
+            const float rstd = 1.f / sqrtf(q + a.bn_eps);
+            cst = make_float2(m, rstd);
+            if (threadIdx.x == 0) {
+                fused::ll_publish(flag, cst.x, cst.y);       // the channel is ready: 8 bytes, no fence
+                s_chan = cst;
+                a.r[c] = rstd;
+                if (a.training) {
+                    a.run_mean[c] = (1.f - a.momentum) * p_rm + a.momentum * m;
+                    a.run_var[c] = (1.f - a.momentum) * p_rv + a.momentum * (q * N / (N - 1.f));
+                    if (a.nbt && c == 0) *a.nbt += 1;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) { v[0] = fmaf(hold[u].x, hold[u].y, v[0]); v[1] += hold[u].x; }
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
+            cta_sums<2, TH>(v, s_f);
+            const float dgam = v[0], dbet = v[1];
+            const float k1 = a.training ? p_ga * dbet * invN : 0.f, k2 = a.training ? p_ga * dgam * invN : 0.f;
+            cst = make_float2(k1, k2);
+            if (threadIdx.x == 0) {
+                fused::ll_publish(flag, cst.x, cst.y);
+                s_chan = cst;
+                a.dgamma[c] = dgam; a.dbeta[c] = dbet;
+            }
+            // off the critical path: dw = (sum ds*mu, sum ds*sd)
+            v[0] = v[1] = 0.f;
+#pragma unroll
+            for (int u = 0; u < kHold; ++u) {
+                const int k = threadIdx.x + u * TH;
+                if (k < N) {
+                    const size_t i = (size_t)k * C + c;
+                    const float ds = p_b * (hold[u].x * p_ga - k1 - hold[u].y * k2);
+                    v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
+                }
+            }
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
+                const float2 p = fused::ll_peek(pb + k);
+                const size_t i = (size_t)k * C + c;
+                const float ds = p_b * (p.x * p_ga - k1 - p.y * k2);
+                v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
+            }
+            cta_sums<2, TH>(v, s_f);
+            if (threadIdx.x == 0) { a.dw[2 * c] = v[0]; a.dw[2 * c + 1] = v[1]; }
+        }
+    } else if (threadIdx.x == 0) {
+        s_chan = poll_word(flag, a.poll_ns);
+    }
+    __syncthreads();
+    CNSN_FTRACE(4);                                          // 4 channel constants known
+
+    // ---- apply out of shared memory -------------------------------------------------------------
+    if (!live) return;
+    const float2 cm = s_chan;
+    float ca = 0.f, cb = 0.f, cc = 0.f;                       // out = ca*dy + cb*x + cc
+    if (BWD) {
+        const float ds = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
+        ca = pre_g;
+        cb = ds * p_w1 * (1.f / (M - 1.f)) / p_sd;
+        cc = ds * p_w0 * (1.f / M) - cb * p_mu;
+    } else {
+        const float sh = (fmaf(p_w0, own_x, p_w1 * own_y) - cm.x) * cm.y;
+        const float gt = 1.f / (1.f + expf(-fmaf(p_ga, sh, p_b)));
+        if (live && r == 0) { a.gate[nc] = gt; a.shat[nc] = sh; }
+        cb = gt;
+    }
+    uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + nc * M);
+#pragma unroll 4
+    for (int i = r; i < nv; i += TPI) {
+        float vx[V], vd[V], vo[V];
+        unpack<T>(lds128(sx + 16u * i), vx);
+        if (BWD) unpack<T>(lds128(sdy + 16u * i), vd);
+#pragma unroll
+        for (int e = 0; e < V; ++e) vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : fmaf(cb, vx[e], 0.f);
+        stg_stream(po + i, pack<T>(vo));
+    }
+    CNSN_FTRACE(5);                                          // 5 applied
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -363,7 +680,7 @@ static int env_int(const char* name, int dflt) {
 static int pick_tpi(int nv) {
     const int batches = env_int("CNSN_FLOW_BATCHES", 6);
     int tpi = 8;
-    while (tpi < kT && tpi * kU * batches < nv) tpi <<= 1;
+    while (tpi < kT && tpi * kUReg * batches < nv) tpi <<= 1;
     return tpi;
 }
 
@@ -374,9 +691,20 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     if (((size_t)a.M * esz) % 16) return -100;
     if (N < 1 || C < 1) return -100;
     const int nv = a.M * esz / 16;
+    // TMA mode: the item is I whole instances staged in shared memory, about CNSN_FLOW_ITEM_KB per CTA.
+    bool tma = env_int("CNSN_FLOW_TMA", 0) != 0;
     int tpi = pick_tpi(nv);
+    if (tma) {
+        const size_t inst_bytes = (size_t)a.M * esz * (BWD ? 2 : 1);
+        const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 24) << 10;
+        int inst = 1;
+        while (inst < 32 && (size_t)(2 * inst) * inst_bytes <= target) inst <<= 1;
+        tpi = kT / inst;
+        if (inst_bytes > (size_t)100 << 10) tma = false;     // one plane (pair) does not fit: register path
+    }
     if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kT && (v & (v - 1)) == 0) tpi = v; }
     const int I = kT / tpi;
+    if (tma && 128 + (size_t)I * a.M * esz * (BWD ? 2 : 1) > (size_t)200 << 10) tma = false;
     a.nI = (N + I - 1) / I;
     // Look-ahead: enough channels to cover the R items in flight plus the fold latency, bounded by L2.
     const size_t chan_bytes = (size_t)N * a.M * esz * (BWD ? 2 : 1);
@@ -399,20 +727,125 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(a.done, 0, (2 * (size_t)C + 1) * sizeof(unsigned), stream);
     if (e != cudaSuccess) return (int)e;
     const dim3 grid((unsigned)items), block(kT);
+    const int ku = env_int("CNSN_FLOW_KU", kUReg);
+    const size_t dsmem = tma ? 128 + (size_t)I * a.M * esz * (BWD ? 2 : 1) : 0;
 #define CNSN_FLOW_CASE(TPI_)                                                                 \
-    case TPI_: k_sn_flow<T, BWD, TPI_><<<grid, block, 0, stream>>>(a); break;
+    case TPI_:                                                                               \
+        if (tma) {                                                                           \
+            if (dsmem > 48 * 1024) {                                                         \
+                e = cudaFuncSetAttribute(k_sn_flow<T, BWD, TPI_, true, kUReg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
+                if (e != cudaSuccess) return (int)e;                                         \
+            }                                                                                \
+            k_sn_flow<T, BWD, TPI_, true, kUReg><<<grid, block, dsmem, stream>>>(a);          \
+        } else if (ku == 8) {                                                                \
+            k_sn_flow<T, BWD, TPI_, false, 8><<<grid, block, 0, stream>>>(a);                 \
+        } else {                                                                             \
+            k_sn_flow<T, BWD, TPI_, false, kUReg><<<grid, block, 0, stream>>>(a);             \
+        }                                                                                    \
+        break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_FLOW_CASE(8) CNSN_FLOW_CASE(16) CNSN_FLOW_CASE(32) CNSN_FLOW_CASE(64) CNSN_FLOW_CASE(128) CNSN_FLOW_CASE(256)
         default: return -100;
     });
 #undef CNSN_FLOW_CASE
     if (getenv("CNSN_FLOW_DEBUG"))
-        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu order=%d\n", BWD ? "bwd" : "fwd", tpi, I, a.nI, D,
-                items, a.order);
+        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu order=%d tma=%d smem=%zu\n", BWD ? "bwd" : "fwd", tpi, I,
+                a.nI, D, items, a.order, (int)tma, dsmem);
     return launch_status();
 }
 
-size_t scratch_floats(int N, int C) { return 2 * (size_t)N * C + 4 * (size_t)C + 8; }
+
+constexpr int kResT = 128;              // threads per CTA of the shared-memory-resident kernel
+
+// Shared-memory-resident path.  Returns -100 when the shape does not fit (the caller uses the L2 path).
+template <bool BWD>
+static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
+    const int N = a.N, C = a.C;
+    const int esz = (int)esize(dtype);
+    if (((size_t)a.M * esz) % 16 || N < 1 || C < 1) return -100;
+    const size_t inst_bytes = (size_t)a.M * esz * (BWD ? 2 : 1);
+    const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
+    int inst = 1;
+    while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
+    if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kResT && (v & (v - 1)) == 0) inst = kResT / v; }
+    const int tpi = kResT / inst;
+    const size_t dsmem = 128 + (size_t)inst * inst_bytes;
+    int dev = 0, sms = 0, smem_optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (dsmem > (size_t)smem_optin / 2) return -100;         // at least two CTAs per SM
+    a.nI = (N + inst - 1) / inst;
+    a.D = 0;
+    a.order = env_int("CNSN_FLOW_ORDER", 0);
+    const unsigned long long items = (unsigned long long)C * a.nI;
+    if (items > 0x7fffffffull) return -100;
+    // scratch: pub [C][N] float2 | channel words [C] x 4 float2 (one 32-byte sector each) | ticket.  Everything is
+    // pre-filled with 0xff: the sentinel of the 8-byte words, and a ticket counter that wraps to 0 on first use.
+    a.pub = reinterpret_cast<float2*>(scratch);
+    a.chan = a.pub + (size_t)N * C;
+    a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
+    a.done = nullptr;
+    a.ready = nullptr;
+    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
+    const dim3 grid((unsigned)items), block(kResT);
+    cudaError_t e = cudaSuccess;
+    int per_sm = 0;
+    const char* trace_path = getenv("CNSN_FLOW_TRACE");      // debug: per-item timestamps (synchronous)
+    const size_t trace_bytes = (size_t)items * 8 * sizeof(unsigned long long);
+    a.trace = nullptr;
+    if (trace_path && cudaMalloc(&a.trace, trace_bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, trace_bytes, stream);
+#define CNSN_RES_CASE(TPI_)                                                                              \
+    case TPI_: {                                                                                         \
+        auto fn = k_sn_res<T, BWD, TPI_, kResT>;                                                         \
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);           \
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kResT, dsmem); \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
+        if ((long long)per_sm * sms < 2ll * a.nI) return -100;                                           \
+        e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        fn<<<grid, block, dsmem, stream>>>(a);                                                           \
+    } break;
+    CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
+        CNSN_RES_CASE(8) CNSN_RES_CASE(16) CNSN_RES_CASE(32) CNSN_RES_CASE(64) CNSN_RES_CASE(128)
+        default: return -100;
+    });
+#undef CNSN_RES_CASE
+    if (a.trace) {
+        cudaStreamSynchronize(stream);
+        unsigned long long* h = (unsigned long long*)malloc(trace_bytes);
+        cudaMemcpy(h, a.trace, trace_bytes, cudaMemcpyDeviceToHost);
+        if (FILE* f = fopen(trace_path, "wb")) {
+            const int hdr[4] = {(int)items, a.nI, per_sm, BWD ? 1 : 0};
+            fwrite(hdr, sizeof(int), 4, f);
+            fwrite(h, 1, trace_bytes, f);
+            fclose(f);
+        }
+        free(h);
+        cudaFree(a.trace);
+    }
+    if (getenv("CNSN_FLOW_DEBUG"))
+        fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu order=%d smem=%zu ctas/sm=%d\n", BWD ? "bwd" : "fwd", tpi,
+                inst, a.nI, items, a.order, dsmem, per_sm);
+    return launch_status();
+}
+
+// Which kernel: the shared-memory-resident one when a channel (all N planes, x [and dy]) is a small enough part
+// of the GPU's shared memory -- measured cross-over on B200 (profiles/README.md): 1/8 of 148 x 200 KB forward,
+// 1/16 backward (the L2-resident backward is the stronger alternative).  CNSN_FLOW_MODE=res|l2 forces one.
+static bool use_resident(size_t chan_bytes, bool bwd) {
+    if (const char* e = getenv("CNSN_FLOW_MODE")) return e[0] == 'r';
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const size_t on_chip = (size_t)sms * 200 * 1024;
+    return chan_bytes * (bwd ? 16 : 8) <= on_chip;
+}
+
+size_t scratch_floats(int N, int C) { return 2 * (size_t)N * C + 36 * (size_t)C + 8; }
 
 // Both return 0 when launched, >0 cuda error, -100 when the path does not apply.
 int selfnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
@@ -425,6 +858,10 @@ int selfnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, in
     a.training = training; a.momentum = momentum; a.bn_eps = bn_eps; a.eps = eps;
     a.w = g->w; a.gamma = g->gamma; a.beta = g->beta; a.run_mean = g->run_mean; a.run_var = g->run_var; a.nbt = g->nbt;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
+    if (use_resident((size_t)N * H * W * esize(dtype), false)) {
+        const int rc = launch_res<false>(a, dtype, scratch, stream);
+        if (rc != -100) return rc;
+    }
     return launch<false>(a, dtype, scratch, stream);
 }
 
@@ -439,6 +876,10 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N,
     a.w = g->w; a.gamma = g->gamma;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
     a.dw = dg->dw; a.dgamma = dg->dgamma; a.dbeta = dg->dbeta;
+    if (use_resident((size_t)N * H * W * esize(dtype) * 2, true)) {
+        const int rc = launch_res<true>(a, dtype, scratch, stream);
+        if (rc != -100) return rc;
+    }
     return launch<true>(a, dtype, scratch, stream);
 }
 
