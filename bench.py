@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--no-train", action="store_true", help="skip the secondary WRN-40-2 measurement")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-crossnorm", action="store_true", help="skip the secondary CrossNorm measurements")
     ap.add_argument("--train-batch", type=int, default=512)
     ap.add_argument("--train-steps", type=int, default=20)
     return ap.parse_args()
@@ -173,6 +174,38 @@ def run_reference_arm(args, shape):
     print(json.dumps(line), flush=True)
 
 
+def bench_crossnorm(torch, M, dev, steps=30):
+    """CrossNorm forward + backward through cn_op_2ins_space_chan (host RNG, perm upload, autograd included):
+    BASELINE config 2 (128,64,32,32) bf16 crop='neither' -- a 16 MiB tensor, launch-latency regime, reported in
+    microseconds -- and (256,256,56,56) fp32, reported as algorithmic GB/s (5*S per step)."""
+    import numpy as np
+    out = {}
+    for name, shape, dt, crop in (("cfg2_128x64x32x32_bf16_neither", (128, 64, 32, 32), torch.bfloat16, "neither"),
+                                  ("wrn_512x32x32x32_f32_both", (512, 32, 32, 32), torch.float32, "both"),
+                                  ("large_256x256x56x56_f32_neither", (256, 256, 56, 56), torch.float32, "neither")):
+        x = torch.randn(shape, device=dev).to(dt).requires_grad_(True)
+        dy = torch.randn(shape, device=dev).to(dt)
+        S = x.numel() * x.element_size()
+        torch.manual_seed(0)
+        np.random.seed(0)
+        for _ in range(5):
+            torch.autograd.grad(M.cn_op_2ins_space_chan(x, crop=crop, beta=1), x, dy)
+        ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        torch.cuda.synchronize()
+        for e in ev:
+            e[0].record()
+            y = M.cn_op_2ins_space_chan(x, crop=crop, beta=1)
+            e[1].record()
+            torch.autograd.grad(y, x, dy)
+            e[2].record()
+        torch.cuda.synchronize()
+        f = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2]
+        b = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2]
+        out[name] = {"fwd_us": f * 1e3, "bwd_us": b * 1e3, "bytes_5S": 5 * S, "gbs": 5 * S / ((f + b) * 1e-3) / 1e9}
+        del x, dy
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -293,6 +326,15 @@ def main():
     del x, dy
     torch.cuda.empty_cache()
 
+    # ---- secondary: CrossNorm (BASELINE config 2 and a north-star-sized tensor), module API, CUDA events
+    crossnorm = None
+    if not args.no_crossnorm:
+        try:
+            crossnorm = bench_crossnorm(torch, M, dev)
+        except Exception as e:
+            crossnorm = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- secondary: WRN-40-2 + CNSN training step
     train = None
     if not args.no_train:
@@ -327,6 +369,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "cpu_baseline": cpu,
+            "crossnorm": crossnorm,
             "train": train,
         }
         print(json.dumps(line), flush=True)

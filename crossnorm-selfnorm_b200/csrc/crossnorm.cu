@@ -1,5 +1,7 @@
 // crossnorm.cu -- 2-instance CrossNorm (cn_op_2ins_space_chan, models/cnsn.py:58-91, with
-// instance_norm_mix :20-29) forward / backward, v1: two stream-ordered kernels per direction.
+// instance_norm_mix :20-29) forward / backward: the C entry points, and the general path (two stream-ordered
+// kernels per direction) used for channel permutation, odd plane sizes and channels too large for the
+// shared-memory-resident dataflow kernel of crossnorm_flow.cu (the default).
 //
 //   forward : per-instance (content window, style window) statistics        (1 read of x)
 //             y = ca*x + cb inside the content window, x outside             (read x, write y)
@@ -12,6 +14,8 @@
 // that fit the 126 MB L2, e.g. BASELINE config 2 at 16 MiB, the second read is an L2 hit).
 // Instance i needs the statistics of instance p(i), so a statistics phase over ALL instances
 // precedes the apply phase: that is the kernel boundary here.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cnsn {
@@ -169,12 +173,29 @@ k_cn_apply_bwd(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict_
     }
 }
 
+namespace flow {
+size_t crossnorm_scratch_floats(int N, int C);
+int crossnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, const int* perm,
+                       const Window& cw, const Window& sw, float lam, float eps,
+                       float* mu_c, float* sd_c, float* mu_s, float* sd_s, float* scratch, cudaStream_t stream);
+int crossnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W, const int* perm,
+                       const Window& cw, const Window& sw, float lam,
+                       const float* mu_c, const float* sd_c, const float* mu_s, const float* sd_s,
+                       float* scratch, cudaStream_t stream);
+}
+// CNSN_CROSSNORM_IMPL=v1 forces the two-kernel path (A/B measurements).
+static bool cn_use_flow() {
+    const char* e = getenv("CNSN_CROSSNORM_IMPL");
+    return !(e && e[0] == 'v');
+}
+
 }  // namespace cnsn
 
 using namespace cnsn;
 
-extern "C" size_t cnsn_crossnorm_save_floats(int N, int C) { return 4 * (size_t)N * C; }
-extern "C" size_t cnsn_crossnorm_workspace_floats(int N, int C) { return 4 * (size_t)N * C; }
+// save: [mu_c | sd_c | mu_s | sd_s] (N*C each), then the dataflow kernel's polled words
+extern "C" size_t cnsn_crossnorm_save_floats(int N, int C) { return 4 * (size_t)N * C + flow::crossnorm_scratch_floats(N, C); }
+extern "C" size_t cnsn_crossnorm_workspace_floats(int N, int C) { return 4 * (size_t)N * C + 8; }
 
 static int cn_check(const void* x, const void* y, int dtype, int N, int C, int H, int W, const int* perm,
                     const int* content, const int* style, Window& cw, Window& sw) {
@@ -200,6 +221,11 @@ extern "C" int cnsn_crossnorm_fwd(const void* x, void* y, int dtype, int N, int 
     const size_t nc = (size_t)inst;
     float* mu_c = save; float* sd_c = save + nc; float* mu_s = save + 2 * nc; float* sd_s = save + 3 * nc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!chan_perm && cn_use_flow()) {
+        const int frc = flow::crossnorm_flow_fwd(x, y, dtype, N, C, H, W, perm, cw, sw, lam, eps, mu_c, sd_c, mu_s, sd_s,
+                                                 save + 4 * nc, s);
+        if (frc != -100) return frc;         // -100: shape not eligible, use the two-kernel path
+    }
     {
         const bool vec = cw.full(H, W) && vec_ok(x, dtype, M);
         const int tpi = team_for(M);
@@ -231,6 +257,11 @@ extern "C" int cnsn_crossnorm_bwd(const void* x, const void* dy, void* dx, int d
     const float* mu_c = save; const float* sd_c = save + nc; const float* mu_s = save + 2 * nc; const float* sd_s = save + 3 * nc;
     float* s1 = workspace; float* s2 = workspace + nc; float* dmu = workspace + 2 * nc; float* dsd = workspace + 3 * nc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!chan_perm && cn_use_flow()) {
+        const int frc = flow::crossnorm_flow_bwd(x, dy, dx, dtype, N, C, H, W, perm, cw, sw, lam, mu_c, sd_c, mu_s, sd_s,
+                                                 workspace, s);
+        if (frc != -100) return frc;
+    }
     {
         const bool vec = cw.full(H, W) && vec_ok2(x, dy, dtype, M);
         const int tpi = team_for(cw.area());

@@ -1,0 +1,155 @@
+// flow_common.cuh -- building blocks shared by the ticket-ordered dataflow kernels (selfnorm_flow.cu,
+// crossnorm_flow.cu): gpu-scope flags, polled 8-byte words, team / CTA reductions, shared-memory vector loads.
+#pragma once
+
+#include <stdlib.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "fused_common.cuh"
+
+namespace cnsn {
+namespace flow {
+
+using fused::smem_u32;
+
+constexpr unsigned kSpin = 1u << 22;    // bounded polls (>= 64 ns each): trap instead of hanging the GPU
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+
+// Sum over the TPI threads of a team (TPI <= 32: lanes of a warp; else TPI/32 consecutive warps).
+// Every thread of the CTA must call it (it may contain __syncthreads).
+template <int TPI>
+__device__ __forceinline__ float team_sum(float v, float* sm) {
+#pragma unroll
+    for (int o = (TPI < 32 ? TPI : 32) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (TPI <= 32) return v;
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[w] = v;
+    __syncthreads();
+    constexpr int WPT = TPI > 32 ? TPI / 32 : 1;
+    const int w0 = (w / WPT) * WPT;
+    float r = 0.f;
+#pragma unroll
+    for (int i = 0; i < WPT; ++i) r += sm[w0 + i];
+    return r;
+}
+template <int TPI>
+__device__ __forceinline__ Moments team_merge(Moments a, Moments* sm) {
+#pragma unroll
+    for (int o = (TPI < 32 ? TPI : 32) >> 1; o > 0; o >>= 1) {
+        Moments b;
+        b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
+        b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
+        b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
+        a = merge(a, b);
+    }
+    if (TPI <= 32) return a;
+    const int w = threadIdx.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[w] = a;
+    __syncthreads();
+    constexpr int WPT = TPI > 32 ? TPI / 32 : 1;
+    const int w0 = (w / WPT) * WPT;
+    Moments r = sm[w0];
+#pragma unroll
+    for (int i = 1; i < WPT; ++i) r = merge(r, sm[w0 + i]);
+    return r;
+}
+// Sums over the whole CTA of TH threads (channel fold by the last R item).
+template <int K, int TH>
+__device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[TH / 32]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < K; ++k) sm[k][warp] = v[k];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < TH / 32; ++w) s += sm[k][w];
+        v[k] = s;
+    }
+}
+
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+    return r;
+}
+
+__device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns) {
+    float2 v = fused::ll_peek(p);
+    unsigned spins = 0;
+    while (!fused::ll_valid(v)) {
+        __nanosleep(sleep_ns);
+        v = fused::ll_peek(p);
+        if (++spins > kSpin) __trap();
+    }
+    return v;
+}
+
+// host: per-(device, kernel, dynamic shared memory) launch preparation, done once: opt in to the shared-memory
+// size, prefer the maximum carve-out, ask the occupancy API how many CTAs fit an SM.  (Three driver calls that
+// would otherwise be paid on every launch; they dominate the host time of small tensors.)
+struct DeviceShape { int sms = 0, smem_optin = 0; };
+static inline DeviceShape device_shape() {
+    static std::mutex mu;
+    static std::unordered_map<int, DeviceShape> cache;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(dev);
+    if (it != cache.end()) return it->second;
+    DeviceShape d;
+    cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cache[dev] = d;
+    return d;
+}
+template <typename K>
+static inline cudaError_t prepare_kernel(K fn, int threads, size_t dsmem, int* ctas_per_sm) {
+    static std::mutex mu;
+    static std::unordered_map<unsigned long long, int> cache;     // per kernel instantiation (K is its type)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long key = ((unsigned long long)dev << 56) ^ ((unsigned long long)(uintptr_t)fn * 0x9e3779b97f4a7c15ull) ^ dsmem;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *ctas_per_sm = it->second; return cudaSuccess; }
+    cudaError_t e = cudaSuccess;
+    if (dsmem > 48 * 1024) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+    if (e == cudaSuccess && dsmem) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fn, threads, dsmem);
+    if (e == cudaSuccess) cache[key] = *ctas_per_sm;
+    return e;
+}
+
+// host: integer environment knob (A/B measurements only)
+static inline int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+
+}  // namespace flow
+}  // namespace cnsn

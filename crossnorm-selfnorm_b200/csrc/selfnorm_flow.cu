@@ -28,17 +28,14 @@
 #include <stdio.h>
 #include <stdlib.h>
 
-#include "fused_common.cuh"
+#include "flow_common.cuh"
 
 namespace cnsn {
 namespace flow {
 
-using fused::smem_u32;
-
 constexpr int kT = 256;                 // threads per CTA
 constexpr int kUReg = 4;                // 128-bit loads in flight per thread and tensor (register path)
 constexpr int kUTma = 2;                // shared-memory reads batched per thread and tensor (TMA path)
-constexpr unsigned kSpin = 1u << 22;    // bounded polls (>= 64 ns each): trap instead of hanging the GPU
 
 struct FArgs {
     const void* x; const void* dy; void* out;      // forward: dy == nullptr, out = y; backward: out = dx
@@ -61,76 +58,6 @@ struct FArgs {
     int poll_ns;            // sleep between polls of ready[c]
     unsigned long long* trace;   // debug only (CNSN_FLOW_TRACE): [items][8] globaltimer stamps, else NULL
 };
-
-__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
-}
-
-// Sum over the TPI threads of a team (TPI <= 32: lanes of a warp; else TPI/32 consecutive warps).
-// Every thread of the CTA must call it (it may contain __syncthreads).
-template <int TPI>
-__device__ __forceinline__ float team_sum(float v, float* sm) {
-#pragma unroll
-    for (int o = (TPI < 32 ? TPI : 32) >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (TPI <= 32) return v;
-    const int w = threadIdx.x >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[w] = v;
-    __syncthreads();
-    constexpr int WPT = TPI > 32 ? TPI / 32 : 1;
-    const int w0 = (w / WPT) * WPT;
-    float r = 0.f;
-#pragma unroll
-    for (int i = 0; i < WPT; ++i) r += sm[w0 + i];
-    return r;
-}
-template <int TPI>
-__device__ __forceinline__ Moments team_merge(Moments a, Moments* sm) {
-#pragma unroll
-    for (int o = (TPI < 32 ? TPI : 32) >> 1; o > 0; o >>= 1) {
-        Moments b;
-        b.n = __shfl_xor_sync(0xffffffffu, a.n, o);
-        b.mean = __shfl_xor_sync(0xffffffffu, a.mean, o);
-        b.m2 = __shfl_xor_sync(0xffffffffu, a.m2, o);
-        a = merge(a, b);
-    }
-    if (TPI <= 32) return a;
-    const int w = threadIdx.x >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) sm[w] = a;
-    __syncthreads();
-    constexpr int WPT = TPI > 32 ? TPI / 32 : 1;
-    const int w0 = (w / WPT) * WPT;
-    Moments r = sm[w0];
-#pragma unroll
-    for (int i = 1; i < WPT; ++i) r = merge(r, sm[w0 + i]);
-    return r;
-}
-// Sums over the whole CTA of TH threads (channel fold by the last R item).
-template <int K, int TH>
-__device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[TH / 32]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < K; ++k) sm[k][warp] = v[k];
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < K; ++k) {
-        float s = 0.f;
-#pragma unroll
-        for (int w = 0; w < TH / 32; ++w) s += sm[k][w];
-        v[k] = s;
-    }
-}
 
 // Fold the N published words of channel c into the channel constants (whole CTA of TH threads; the caller has
 // made the words visible: fence + atomic counter).  Forward: BatchNorm batch mean / rstd of s = w0*mu + w1*sd,
@@ -192,21 +119,10 @@ __device__ __forceinline__ void channel_fold(const FArgs& a, unsigned c, float (
     }
 }
 
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 #define CNSN_FTRACE(slot)                                                                      \
     do {                                                                                       \
         if (a.trace && threadIdx.x == 0) a.trace[(size_t)t * 8 + (slot)] = gtime();             \
     } while (0)
-
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
-    uint4 r;
-    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
-    return r;
-}
 
 // TMA = true: the item's planes are fetched by cp.async.bulk into shared memory (one thread issues, the
 // whole item is in flight at once, no registers are tied up); TMA = false: 128-bit loads into registers.
@@ -437,17 +353,6 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
 // CTAs at once (checked on the host with the occupancy API) the lowest unfinished channel is always completely
 // resident, none of its CTAs waits before it has published, and it completes.  All N planes of a channel (and
 // the next few) live in shared memory across the GPU: N*M*sizeof(T)*tensors must fit a fraction of 148 x 227 KB.
-__device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns) {
-    float2 v = fused::ll_peek(p);
-    unsigned spins = 0;
-    while (!fused::ll_valid(v)) {
-        __nanosleep(sleep_ns);
-        v = fused::ll_peek(p);
-        if (++spins > kSpin) __trap();
-    }
-    return v;
-}
-
 template <typename T, bool BWD, int TPI, int TH>
 __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     constexpr int I = TH / TPI;
@@ -545,12 +450,25 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         own_x = mean; own_y = sqrtf(m2 / (M - 1.f) + a.eps);
         if (live && r == 0) { a.mu[nc] = own_x; a.sd[nc] = own_y; }
     }
-    if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    // eval mode: the channel constants are the running statistics (forward) / vanish (backward, k1 = k2 = 0):
+    // nothing to wait for -- a single pass per instance.  Backward still publishes (parameter gradients).
+    const bool batch_coupled = a.training != 0;
+    if (live && r == 0 && (BWD || batch_coupled)) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
     CNSN_FTRACE(2);                                          // 2 reduced + published
 
     // ---- channel constants ------------------------------------------------------------------------
     float2* flag = a.chan + 4u * c;                          // one 32-byte sector per channel
-    if (folder) {
+    if (!batch_coupled && !(BWD && folder)) {
+        if (threadIdx.x == 0) {
+            if (BWD) {
+                s_chan = make_float2(0.f, 0.f);
+            } else {
+                const float rstd = 1.f / sqrtf(a.run_var[c] + a.bn_eps);
+                s_chan = make_float2(a.run_mean[c], rstd);
+                if (folder) a.r[c] = rstd;
+            }
+        }
+    } else if (folder) {
         const float2* pb = a.pub + (size_t)c * N;
         const float invN = 1.f / N;
         float2 hold[kHold];
@@ -667,11 +585,6 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 // Threads per instance: a power of two that covers the plane in about kBatches batches of kU loads.  Fewer
 // threads per instance amortise the per-item latencies (ticket, flag, fence) over more bytes; more threads
 // keep the resident window (and with it the L2 footprint between the two reads) narrow.  Measured on
@@ -770,11 +683,9 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kResT && (v & (v - 1)) == 0) inst = kResT / v; }
     const int tpi = kResT / inst;
     const size_t dsmem = 128 + (size_t)inst * inst_bytes;
-    int dev = 0, sms = 0, smem_optin = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    if (dsmem > (size_t)smem_optin / 2) return -100;         // at least two CTAs per SM
+    const DeviceShape ds = device_shape();
+    const int sms = ds.sms;
+    if (dsmem > (size_t)ds.smem_optin / 2) return -100;      // at least two CTAs per SM
     a.nI = (N + inst - 1) / inst;
     a.D = 0;
     a.order = env_int("CNSN_FLOW_ORDER", 0);
@@ -799,9 +710,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
 #define CNSN_RES_CASE(TPI_)                                                                              \
     case TPI_: {                                                                                         \
         auto fn = k_sn_res<T, BWD, TPI_, kResT>;                                                         \
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);           \
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100); \
-        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kResT, dsmem); \
+        e = prepare_kernel(fn, kResT, dsmem, &per_sm);                                                   \
         if (e != cudaSuccess) return (int)e;                                                             \
         /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
         if ((long long)per_sm * sms < 2ll * a.nI) return -100;                                           \
@@ -838,10 +747,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
 // 1/16 backward (the L2-resident backward is the stronger alternative).  CNSN_FLOW_MODE=res|l2 forces one.
 static bool use_resident(size_t chan_bytes, bool bwd) {
     if (const char* e = getenv("CNSN_FLOW_MODE")) return e[0] == 'r';
-    int dev = 0, sms = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const size_t on_chip = (size_t)sms * 200 * 1024;
+    const size_t on_chip = (size_t)device_shape().sms * 200 * 1024;
     return chan_bytes * (bwd ? 16 : 8) <= on_chip;
 }
 

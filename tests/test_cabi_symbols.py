@@ -45,4 +45,4 @@ def test_argument_validation_without_gpu():
     assert h.cnsn_instance_stats(None, 0, 1, 1, 1, 1, 0, 1, 0, 1, 1e-5, None, None, None) == -1
     assert h.cnsn_selfnorm_save_floats(4, 16, 0) == 4 * 64 + 16 + 2 * 64 + 36 * 16 + 8
     assert h.cnsn_selfnorm_save_floats(4, 16, 1) == 6 * 64 + 32 + 2 * 64 + 36 * 16 + 8
-    assert h.cnsn_crossnorm_save_floats(4, 16) == 256
+    assert h.cnsn_crossnorm_save_floats(4, 16) == 256 + 2 * 64 + 8

@@ -153,13 +153,18 @@ def test_selfnorm_batch1_raises(mod):
     assert m(torch.randn(1, 4, 8, 8, device=DEV)).shape == (1, 4, 8, 8)
 
 
-CN_SHAPES = [(8, 6, 12, 10), (4, 16, 8, 8), (6, 5, 7, 7), (16, 8, 32, 32), (3, 2, 72, 72), (5, 3, 9, 14)]
+CN_SHAPES = [(8, 6, 12, 10), (4, 16, 8, 8), (6, 5, 7, 7), (16, 8, 32, 32), (3, 2, 72, 72), (5, 3, 9, 14), (37, 3, 20, 20)]
 
 
 @pytest.mark.parametrize("shape", CN_SHAPES)
 @pytest.mark.parametrize("crop", ["neither", "style", "content", "both"])
-@pytest.mark.parametrize("chan,lam", [(False, None), (True, 0.3)])
-def test_crossnorm_vs_oracle_f32(mod, shape, crop, chan, lam):
+@pytest.mark.parametrize("chan,lam,impl", [(False, None, "auto"), (True, 0.3, "auto"), (False, 0.3, "auto"), (False, None, "v1")])
+def test_crossnorm_vs_oracle_f32(mod, shape, crop, chan, lam, impl, monkeypatch):
+    """All crop modes, with and without channel permutation / lam, through the default dispatch (the
+    shared-memory-resident dataflow kernel where it applies: no channel permutation, 16-byte planes) and through
+    the two-kernel path (forced)."""
+    if impl != "auto":
+        monkeypatch.setenv("CNSN_CROSSNORM_IMPL", impl)
     x = O.varied_input(shape, seed=11, dtype=np.float32)
     dy = np.random.RandomState(12).standard_normal(shape).astype(np.float32)
     y, dx = H.run_crossnorm(mod, x, dy, DEV, crop, chan, lam, 21, 22)
@@ -170,8 +175,11 @@ def test_crossnorm_vs_oracle_f32(mod, shape, crop, chan, lam):
     close32(dx, O.crossnorm_bwd(x, dy, plan, lam), "dx")
 
 
-def test_crossnorm_cfg2_bf16(mod):
+@pytest.mark.parametrize("impl", ["auto", "v1"])
+def test_crossnorm_cfg2_bf16(mod, impl, monkeypatch):
     """BASELINE config 2: CrossNorm (2-instance swap, no crop) on (128,64,32,32) bf16."""
+    if impl != "auto":
+        monkeypatch.setenv("CNSN_CROSSNORM_IMPL", impl)
     shape = (128, 64, 32, 32)
     x = torch.randn(shape, generator=torch.Generator().manual_seed(0)).to(torch.bfloat16).float().numpy()
     dy = torch.randn(shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).float().numpy()
@@ -181,6 +189,27 @@ def test_crossnorm_cfg2_bf16(mod):
     plan = O.draw_plan(shape, crop="neither")
     close16(y, O.crossnorm_fwd(x, plan), "y")
     close16(dx, O.crossnorm_bwd(x, dy, plan), "dx")
+
+
+@pytest.mark.parametrize("shape,dtype,crop", [((512, 32, 32, 32), torch.float32, "both"), ((64, 64, 56, 56), torch.float32, "neither"),
+                                              ((256, 128, 8, 8), torch.float32, "content"), ((128, 64, 32, 32), torch.float16, "style"),
+                                              ((48, 3, 224, 224), torch.float32, "both")])
+def test_crossnorm_large_flow_vs_two_kernel(mod, shape, dtype, crop, monkeypatch):
+    """Training-size tensors (the WideResNet sites, image-space CrossNorm): the dataflow kernel against the
+    two-kernel path on identical inputs and identical RNG draws (both are oracle-checked at small sizes above)."""
+    g = torch.Generator().manual_seed(5)
+    x = (torch.randn(shape, generator=g) * (0.5 + torch.rand(shape[0], shape[1], 1, 1, generator=g)) + torch.randn(shape[0], shape[1], 1, 1, generator=g))
+    x = x.to(dtype).float().numpy()
+    dy = torch.randn(shape, generator=g).to(dtype).float().numpy()
+    y0, dx0 = H.run_crossnorm(mod, x, dy, DEV, crop, False, None, 7, 8, dtype)
+    monkeypatch.setenv("CNSN_CROSSNORM_IMPL", "v1")
+    y1, dx1 = H.run_crossnorm(mod, x, dy, DEV, crop, False, None, 7, 8, dtype)
+    if dtype == torch.float32:
+        close32(y0, y1, "y")
+        close32(dx0, dx1, "dx")
+    else:
+        close16(y0, y1, "y")
+        close16(dx0, dx1, "dx")
 
 
 # ------------------------------------------------------------------ properties (size independent)
