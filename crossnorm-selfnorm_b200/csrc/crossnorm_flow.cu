@@ -36,6 +36,8 @@ struct CNArgs {
     int nI;                 // items per channel = ceil(N / I)
     int order;              // 0: atomic ticket per CTA; 1: blockIdx.x
     int poll_ns;
+    int pf_dist;            // L2-prefetch the item pf_dist tickets ahead (0 = off)
+    unsigned items;         // total tickets
     Window cw, sw;          // content / style window
     float lam, eps;
     const int* perm;        // [N] style source of every sample
@@ -145,6 +147,17 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
             fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
             if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+        }
+        // L2 prefetch for the CTA that will take this one's place (see selfnorm_flow.cu)
+        const unsigned tf = t + (unsigned)a.pf_dist;
+        if (a.pf_dist && tf < a.items) {
+            const unsigned cf = tf / nI, jf = tf - cf * nI;
+            const int ff = (int)jf * I, nf = min(I, N - ff);
+            for (int q = threadIdx.x; q < nf; q += 32) {
+                const size_t off = ((size_t)(ff + q) * C + cf) * M;
+                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+            }
         }
     }
     const Window cw = a.cw, sw = a.sw;
@@ -261,6 +274,7 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return -100;
+    a.items = (unsigned)items;
     a.pub = reinterpret_cast<float2*>(scratch);              // [C][N] float2 | ticket
     a.ticket = reinterpret_cast<unsigned*>(a.pub + (size_t)N * C);
     const size_t fill_bytes = ((size_t)N * C + 1) * sizeof(float2);
@@ -273,6 +287,7 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = prepare_kernel(fn, kCnT, dsmem, &per_sm);                                                    \
         if (e != cudaSuccess) return (int)e;                                                             \
         if ((long long)per_sm * sms < 2ll * a.nI) return -100;    /* a whole channel must be co-resident */ \
+        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
         fn<<<grid, block, dsmem, stream>>>(a);                                                           \

@@ -56,6 +56,8 @@ struct FArgs {
     unsigned* ready;        // [C]    channel constants are in chan[c]
     unsigned* ticket;       // [1]
     int poll_ns;            // sleep between polls of ready[c]
+    int pf_dist;            // resident kernel: L2-prefetch the item pf_dist tickets ahead (0 = off)
+    unsigned items;         // resident kernel: total tickets
     unsigned long long* trace;   // debug only (CNSN_FLOW_TRACE): [items][8] globaltimer stamps, else NULL
 };
 
@@ -393,6 +395,18 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
             if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
         }
+        // L2 prefetch for the CTA that will take this one's place: its TMA loads then hit L2 instead of paying
+        // the HBM latency (and its tail) while its shared memory is already tied up.  Same L2 traffic.
+        const unsigned tf = t + (unsigned)a.pf_dist;
+        if (a.pf_dist && tf < a.items) {
+            const unsigned cf = tf / nI, jf = tf - cf * nI;
+            const int ff = (int)jf * I, nf = min(I, N - ff);
+            for (int q = threadIdx.x; q < nf; q += 32) {
+                const size_t off = ((size_t)(ff + q) * C + cf) * M;
+                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+            }
+        }
     }
     // everything that does not depend on the channel is fetched under the TMA latency
     const bool folder = j == nI - 1;                         // holds the channel's last ticket
@@ -699,6 +713,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     a.done = nullptr;
     a.ready = nullptr;
     a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.items = (unsigned)items;
     const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
     const dim3 grid((unsigned)items), block(kResT);
     cudaError_t e = cudaSuccess;
@@ -714,6 +729,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         if (e != cudaSuccess) return (int)e;                                                             \
         /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
         if ((long long)per_sm * sms < 2ll * a.nI) return -100;                                           \
+        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
         fn<<<grid, block, dsmem, stream>>>(a);                                                           \
