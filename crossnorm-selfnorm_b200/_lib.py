@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libcnsn_b200.so")
 
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
 
@@ -51,6 +51,10 @@ SIGNATURES = {
     "cnsn_selfnorm_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS,
                                   POINTER(GateParams), POINTER(GateParams), c_int, c_void_p,
                                   POINTER(GateGrads), POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_selfnorm_block_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
+                                        c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_selfnorm_block_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
+                                        c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p,
@@ -253,6 +257,44 @@ class CudaBackend:
                                            ctypes.byref(gg), ctypes.byref(gf) if two else None,
                                            _p(ws), _stream(x)))
         return dx, out_g, out_f
+
+    # -- fused block: [x + res ->] SelfNorm [-> ReLU] ------------------------------------------
+    def selfnorm_block_fwd(self, x, res, relu, g, training, momentum, bn_eps, eps):
+        """Returns (y, z, save): z is x + res (what backward needs), or x itself when res is None."""
+        _require_cuda(x, res)
+        N, C, H, W = x.shape
+        keep = []
+        gs, g_rm, g_rv = self._gate_struct(g, keep)
+        save = torch.empty(lib().cnsn_selfnorm_save_floats(N, C, 0), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        z = torch.empty_like(x) if res is not None else x
+        with _on(x.device):
+            _check(lib().cnsn_selfnorm_block_fwd(_p(x), _p(res), _p(z) if res is not None else None, _p(y), int(relu),
+                                                 _dtype_code(x), N, C, H, W, ctypes.byref(gs), int(training),
+                                                 momentum, bn_eps, eps, _p(save), _stream(x)))
+        if training:
+            if g_rm is not g.run_mean:
+                g.run_mean.copy_(g_rm)
+            if g_rv is not g.run_var:
+                g.run_var.copy_(g_rv)
+        return y, z, save
+
+    def selfnorm_block_bwd(self, z, dy, relu, g, training, save):
+        _require_cuda(z, dy)
+        N, C, H, W = z.shape
+        keep = []
+        gs, _, _ = self._gate_struct(g, keep)
+        dev = z.device
+        buf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+        out_g = (buf[:2 * C].view(C, 2), buf[2 * C:3 * C], buf[3 * C:])
+        gg = GateGrads(*[_p(t).value for t in out_g])
+        ws = torch.empty(lib().cnsn_selfnorm_workspace_floats(N, C, 0), dtype=torch.float32, device=dev)
+        dz = torch.empty_like(z)
+        with _on(dev):
+            _check(lib().cnsn_selfnorm_block_bwd(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
+                                                 ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg),
+                                                 _p(ws), _stream(z)))
+        return dz, out_g
 
     # -- CrossNorm ------------------------------------------------------------------------
     def crossnorm_fwd(self, x, perm, chan_perm, cwin, swin, lam, eps):

@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import CrossNormFn, InstanceAffine, InstanceStats, SelfNormFn
+from .functional import CrossNormFn, InstanceAffine, InstanceStats, SelfNormBlockFn, SelfNormFn
 
 __all__ = ["calc_ins_mean_std", "instance_norm_mix", "cn_rand_bbox", "cn_op_2ins_space_chan",
            "CrossNorm", "SelfNorm", "CNSN"]
@@ -134,9 +134,16 @@ class SelfNorm(nn.Module):
     def _bufs(bn):
         return (bn.running_mean, bn.running_var, bn.num_batches_tracked)
 
-    def forward(self, x):
+    def forward(self, x, residual=None, relu=False):
+        """``forward(x)`` is the reference call.  ``forward(x, residual, relu)`` is the opt-in block fusion
+        relu?(SelfNorm(x + residual)) for pos='post' sites (one gate only)."""
         assert x.dim() == 4
         bn = self.g_bn
+        if residual is not None or relu:
+            assert self.f_fc is None, "the fused block supports the single-gate SelfNorm"
+            assert residual is None or residual.shape == x.shape
+            return SelfNormBlockFn.apply(x, residual, bool(relu), bn.training, float(bn.momentum), float(bn.eps), 1e-12,
+                                         self._bufs(bn), self.g_fc.weight, bn.weight, bn.bias)
         args = [x, bn.training, float(bn.momentum), float(bn.eps), 1e-12,          # eps :133
                 self._bufs(bn), self._bufs(self.f_bn) if self.f_fc is not None else None,
                 self.g_fc.weight, bn.weight, bn.bias]
@@ -153,9 +160,23 @@ class CNSN(nn.Module):
         self.crossnorm = crossnorm
         self.selfnorm = selfnorm
 
-    def forward(self, x):
-        if self.crossnorm and self.crossnorm.active:
-            x = self.crossnorm(x)
-        if self.selfnorm:
-            x = self.selfnorm(x)
-        return x
+    def forward(self, x, residual=None, relu=False):
+        """``forward(x)`` is the reference call (models/cnsn.py:159-164).  ``forward(x, residual, relu)`` computes
+        relu?(CNSN(x + residual)) -- the pos='post' block tail -- fusing add and ReLU into the SelfNorm kernels
+        whenever this step's CrossNorm does not fire at the site."""
+        fire = bool(self.crossnorm) and self.crossnorm.active
+        if residual is None and not relu:
+            if fire:
+                x = self.crossnorm(x)
+            if self.selfnorm:
+                x = self.selfnorm(x)
+            return x
+        if fire or not self.selfnorm:
+            if residual is not None:
+                x = torch.add(residual, x)
+            if fire:
+                x = self.crossnorm(x)
+            if self.selfnorm:
+                return self.selfnorm(x, None, relu)
+            return torch.relu(x) if relu else x
+        return self.selfnorm(x, residual, relu)

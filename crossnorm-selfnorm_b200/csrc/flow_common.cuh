@@ -97,6 +97,9 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return r;
 }
 
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns) {
     float2 v = fused::ll_peek(p);
     unsigned spins = 0;

@@ -34,11 +34,12 @@ namespace cnsn {
 namespace flow {
 
 constexpr int kT = 256;                 // threads per CTA
-constexpr int kUReg = 4;                // 128-bit loads in flight per thread and tensor (register path)
-constexpr int kUTma = 2;                // shared-memory reads batched per thread and tensor (TMA path)
+constexpr int kUReg = 4;                // 128-bit loads in flight per thread and tensor
 
 struct FArgs {
     const void* x; const void* dy; void* out;      // forward: dy == nullptr, out = y; backward: out = dx
+    const void* res; void* zout;                   // forward block fusion: y = f(x + res), the sum goes to zout
+    int relu;                                      // forward: y = max(y, 0); backward: dy masked where x <= 0
     int N, C, M;
     int nI;                 // items per channel and phase = ceil(N / I)
     int D;                  // look-ahead in channels (1..C)
@@ -126,31 +127,39 @@ __device__ __forceinline__ void channel_fold(const FArgs& a, unsigned c, float (
         if (a.trace && threadIdx.x == 0) a.trace[(size_t)t * 8 + (slot)] = gtime();             \
     } while (0)
 
-// TMA = true: the item's planes are fetched by cp.async.bulk into shared memory (one thread issues, the
-// whole item is in flight at once, no registers are tied up); TMA = false: 128-bit loads into registers.
-template <typename T, bool BWD, int TPI, bool TMA, int KU>
-__global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_sn_flow(const FArgs a) {
+// 128-bit load of data WRITTEN earlier in this kernel by another CTA (ordered by a release / acquire flag): the
+// coherent path, not ld.global.nc.
+__device__ __forceinline__ uint4 ldg_hint_coherent(const void* p, uint64_t pol) {
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p), "l"(pol) : "memory");
+    return r;
+}
+// Streaming store that keeps the line in L2 (the sum z = x + res is re-read by the A items).
+__device__ __forceinline__ void stg_hint(void* p, const uint4& v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
+}
+
+// L2-resident items.  Optional block fusion: forward with a.res != NULL reduces z = x + res,
+// writes z (backward needs it) and applies to z; a.relu clamps y at 0 (forward) / masks dy where z <= 0 (backward:
+// the gate is a sigmoid, so sign(g*z) = sign(z)).
+template <typename T, bool BWD, bool ADD, int TPI>
+__global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArgs a) {
+    static_assert(!(BWD && ADD), "the fused add is a forward feature");
     constexpr int I = kT / TPI;          // instances per item
     constexpr int V = VecOf<T>::n;
-    constexpr int kU = TMA ? kUTma : KU;
-    extern __shared__ __align__(128) unsigned char dsm[];    // TMA: [mbarrier | I planes of x | I planes of dy]
+    constexpr int kU = kUReg;
     __shared__ unsigned s_word;
     __shared__ float s_f[2][kT / 32];
     __shared__ Moments s_m[kT / 32];
-    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
 
     // ---- which item am I --------------------------------------------------------------------
     unsigned t = blockIdx.x;
-    if (TMA && threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     if (a.order == 0) {
         if (threadIdx.x == 0) s_word = atomicAdd(a.ticket, 1u);
         __syncthreads();
         t = s_word;
-    } else if (TMA) {
-        __syncthreads();
     }
     const unsigned nI = (unsigned)a.nI, D = (unsigned)a.D, C = (unsigned)a.C;
     bool isA;
@@ -173,61 +182,54 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
     const bool live = n < N;
     const size_t nc = (size_t)(live ? n : 0) * C + c;
     const int nv = M / V;
-    const uint4* px = reinterpret_cast<const uint4*>(static_cast<const T*>(a.x) + nc * M);
-    const uint4* pd = BWD ? reinterpret_cast<const uint4*>(static_cast<const T*>(a.dy) + nc * M) : nullptr;
+    constexpr bool add = ADD;                             // forward block fusion: x + res
+    const bool relu = a.relu != 0;
+    constexpr bool two = BWD || ADD;
+    // R items read x (and dy / res); A items read what gets applied: x, or the sum z written by the R items
+    const uint4* px = reinterpret_cast<const uint4*>(static_cast<const T*>((isA && add) ? a.zout : a.x) + nc * M);
+    const uint4* pd = two ? reinterpret_cast<const uint4*>(static_cast<const T*>(BWD ? a.dy : a.res) + nc * M) : nullptr;
     constexpr int kStep = TPI * kU;
-    // TMA: shared-memory addresses of this team's planes; warp 0 issues the bulk copies (lane i: instance i).
-    const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
-    const uint32_t sx = smem_u32(dsm) + 128u + (threadIdx.x / TPI) * pbytes;
-    const uint32_t sdy = sx + (unsigned)I * pbytes;
-    if (TMA && threadIdx.x < 32) {
-        const int first = (int)j * I;
-        const int nlive = min(I, N - first);
-        const uint64_t pol = isA ? l2_policy_evict_first() : (a.keep ? l2_policy_evict_last() : l2_policy_evict_normal());
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
-        __syncwarp();
-        for (int q = threadIdx.x; q < nlive; q += 32) {
-            const size_t off = ((size_t)(first + q) * C + c) * M;
-            unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
-        }
-    }
 
     if (!isA) {
         // =============================================================== R item
-        const uint64_t pol = a.keep ? l2_policy_evict_last() : 0;
+        const uint64_t pol_keep = l2_policy_evict_last();
+        const uint64_t pol_once = l2_policy_evict_first();
+        const bool keep = a.keep != 0 && !add;           // fused add: the inputs are not needed again, z is
+        uint4* pz = add ? reinterpret_cast<uint4*>(static_cast<T*>(a.zout) + nc * M) : nullptr;
         float sxy = 0.f, pre_g = 0.f, pre_s = 0.f;
         if (BWD && live && r == 0) { pre_g = a.gate[nc]; pre_s = a.shat[nc]; }   // issued ahead of the plane loads
         Moments acc = moments_zero();
-        if (TMA) fused::mbar_wait(bar, 0);
         for (int i0 = r; i0 < nv; i0 += kStep) {
             uint4 rx[kU], rd[kU];
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int i = i0 + u * TPI;
                 if (live && i < nv) {
-                    if (TMA) {
-                        rx[u] = lds128(sx + 16u * i);
-                        if (BWD) rd[u] = lds128(sdy + 16u * i);
-                    } else {
-                        rx[u] = a.keep ? ldg_hint(px + i, pol) : ldg_stream(px + i);
-                        if (BWD) rd[u] = a.keep ? ldg_hint(pd + i, pol) : ldg_stream(pd + i);
-                    }
+                    rx[u] = keep ? ldg_hint(px + i, pol_keep) : (add ? ldg_hint(px + i, pol_once) : ldg_stream(px + i));
+                    if (two) rd[u] = keep ? ldg_hint(pd + i, pol_keep) : (add ? ldg_hint(pd + i, pol_once) : ldg_stream(pd + i));
                 }
             }
 #pragma unroll
             for (int u = 0; u < kU; ++u) {
                 const int i = i0 + u * TPI;
                 if (live && i < nv) {
-                    float vx[V];
+                    float vx[V], vd[V];
                     unpack<T>(rx[u], vx);
+                    if (two) unpack<T>(rd[u], vd);
                     if (BWD) {
-                        float vd[V];
-                        unpack<T>(rd[u], vd);
 #pragma unroll
-                        for (int e = 0; e < V; ++e) sxy = fmaf(vd[e], vx[e], sxy);
+                        for (int e = 0; e < V; ++e) {
+                            const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                            sxy = fmaf(d, vx[e], sxy);
+                        }
                     } else {
+                        if (add) {
+#pragma unroll
+                            for (int e = 0; e < V; ++e) vx[e] += vd[e];
+                            const uint4 z = pack<T>(vx);
+                            stg_hint(pz + i, z, pol_keep);    // stays in L2 for the A item
+                            unpack<T>(z, vx);                 // statistics of the ROUNDED sum, as an unfused add gives
+                        }
                         fold<V>(acc, vx);
                     }
                 }
@@ -271,17 +273,14 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
         for (int u = 0; u < kU; ++u) {
             const int i = i0 + u * TPI;
             if (live && i < nv) {
-                if (TMA) {
-                    rx[u] = lds128(sx + 16u * i);
-                    if (BWD) rd[u] = lds128(sdy + 16u * i);
-                } else {
-                    rx[u] = ldg_hint(px + i, pol);       // L2 hit (read D channels ago), last use
-                    if (BWD) rd[u] = ldg_hint(pd + i, pol);
-                }
+                rx[u] = add ? ldg_hint_coherent(px + i, pol) : ldg_hint(px + i, pol);   // L2 hit, last use
+                if (BWD) rd[u] = ldg_hint(pd + i, pol);
             }
         }
     };
-    if (!TMA) issue(r);                                  // the plane loads do not depend on the channel
+    // With the fused add the planes are WRITTEN by this kernel's R items: their visibility comes with ready[c]
+    // (release / acquire), so the loads wait for the flag; otherwise they are issued under the flag wait.
+    if (!add) issue(r);
     // ... nor do the saved per-instance statistics and the parameters: fetch them under the flag wait too
     float p_w0 = 0.f, p_w1 = 0.f, p_ga = 0.f, p_b = 0.f, p_gt = 0.f, p_mu = 0.f, p_sd = 1.f;
     if (live) {
@@ -297,6 +296,7 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
         }
     }
     __syncthreads();
+    if (add) issue(r);
     float ca = 0.f, cb = 0.f, cc = 0.f;                   // out = ca*dy + cb*x + cc
     if (live) {
         const float2 cm = __ldcg(a.chan + c);
@@ -315,7 +315,6 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
             cb = gt;
         }
     }
-    if (TMA) { fused::mbar_wait(bar, 0); issue(r); }
     for (int i0 = r;;) {
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -325,7 +324,15 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
                 unpack<T>(rx[u], vx);
                 if (BWD) unpack<T>(rd[u], vd);
 #pragma unroll
-                for (int e = 0; e < V; ++e) vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : fmaf(cb, vx[e], 0.f);
+                for (int e = 0; e < V; ++e) {
+                    if (BWD) {
+                        const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                        vo[e] = fmaf(ca, d, fmaf(cb, vx[e], cc));
+                    } else {
+                        const float y = fmaf(cb, vx[e], 0.f);
+                        vo[e] = relu ? fmaxf(y, 0.f) : y;
+                    }
+                }
                 stg_stream(po + i, pack<T>(vo));
             }
         }
@@ -355,8 +362,10 @@ __global__ void __launch_bounds__(kT, TMA ? 6 : (KU > 4 ? 3 : (BWD ? 4 : 5))) k_
 // CTAs at once (checked on the host with the occupancy API) the lowest unfinished channel is always completely
 // resident, none of its CTAs waits before it has published, and it completes.  All N planes of a channel (and
 // the next few) live in shared memory across the GPU: N*M*sizeof(T)*tensors must fit a fraction of 148 x 227 KB.
-template <typename T, bool BWD, int TPI, int TH>
+template <typename T, bool BWD, bool ADD, int TPI, int TH>
 __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
+    static_assert(!(BWD && ADD), "the fused add is a forward feature");
+    constexpr bool two = BWD || ADD;                         // a second plane per instance: dy (backward) / res (fused add)
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
     constexpr int kHold = 4;                                 // published words a folding thread keeps in registers
@@ -387,13 +396,14 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         const int first = (int)j * I;
         const int nlive = min(I, N - first);
         const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        const T* second = static_cast<const T*>(BWD ? a.dy : a.res);
+        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (two ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
             fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+            if (two) fused::tma_load_1d(dst + (size_t)I * pbytes, second + off, pbytes, bar, pol);
         }
         // L2 prefetch for the CTA that will take this one's place: its TMA loads then hit L2 instead of paying
         // the HBM latency (and its tail) while its shared memory is already tied up.  Same L2 traffic.
@@ -404,7 +414,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
                 fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+                if (two) fused::tma_prefetch_l2(second + off, pbytes);
             }
         }
     }
@@ -423,6 +433,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     CNSN_FTRACE(1);                                          // 1 planes landed
 
     // ---- reduce out of shared memory -----------------------------------------------------------
+    const bool relu = a.relu != 0;
     float own_x = 0.f, own_y = 0.f;                          // this instance's published word
     if (BWD) {
         float s0 = 0.f, s1 = 0.f;
@@ -433,7 +444,10 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
                 unpack<T>(lds128(sx + 16u * i), vx);
                 unpack<T>(lds128(sdy + 16u * i), vd);
 #pragma unroll
-                for (int e = 0; e < V; ++e) { if (e & 1) s1 = fmaf(vd[e], vx[e], s1); else s0 = fmaf(vd[e], vx[e], s0); }
+                for (int e = 0; e < V; ++e) {
+                    const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                    if (e & 1) s1 = fmaf(d, vx[e], s1); else s0 = fmaf(d, vx[e], s0);
+                }
             }
         }
         const float sxy = team_sum<TPI>(s0 + s1, s_f[0]);
@@ -441,10 +455,21 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     } else {                                                 // exact two-pass: the plane is on chip
         float s0 = 0.f, s1 = 0.f;
         if (live) {
+            uint4* pz = ADD ? reinterpret_cast<uint4*>(static_cast<T*>(a.zout) + nc * M) : nullptr;
 #pragma unroll 4
             for (int i = r; i < nv; i += TPI) {
                 float vx[V];
                 unpack<T>(lds128(sx + 16u * i), vx);
+                if (ADD) {                                   // z = x + res: kept in place of x, and written out
+                    float vr[V];
+                    unpack<T>(lds128(sdy + 16u * i), vr);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) vx[e] += vr[e];
+                    const uint4 z = pack<T>(vx);
+                    sts128(sx + 16u * i, z);                 // thread-private slots: no barrier needed
+                    stg_stream(pz + i, z);
+                    unpack<T>(z, vx);                        // statistics of the rounded sum
+                }
 #pragma unroll
                 for (int e = 0; e < V; ++e) { if (e & 1) s1 += vx[e]; else s0 += vx[e]; }
             }
@@ -590,7 +615,15 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         unpack<T>(lds128(sx + 16u * i), vx);
         if (BWD) unpack<T>(lds128(sdy + 16u * i), vd);
 #pragma unroll
-        for (int e = 0; e < V; ++e) vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cb, vx[e], cc)) : fmaf(cb, vx[e], 0.f);
+        for (int e = 0; e < V; ++e) {
+            if (BWD) {
+                const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                vo[e] = fmaf(ca, d, fmaf(cb, vx[e], cc));
+            } else {
+                const float y = fmaf(cb, vx[e], 0.f);
+                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            }
+        }
         stg_stream(po + i, pack<T>(vo));
     }
     CNSN_FTRACE(5);                                          // 5 applied
@@ -618,20 +651,9 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     if (((size_t)a.M * esz) % 16) return -100;
     if (N < 1 || C < 1) return -100;
     const int nv = a.M * esz / 16;
-    // TMA mode: the item is I whole instances staged in shared memory, about CNSN_FLOW_ITEM_KB per CTA.
-    bool tma = env_int("CNSN_FLOW_TMA", 0) != 0;
     int tpi = pick_tpi(nv);
-    if (tma) {
-        const size_t inst_bytes = (size_t)a.M * esz * (BWD ? 2 : 1);
-        const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 24) << 10;
-        int inst = 1;
-        while (inst < 32 && (size_t)(2 * inst) * inst_bytes <= target) inst <<= 1;
-        tpi = kT / inst;
-        if (inst_bytes > (size_t)100 << 10) tma = false;     // one plane (pair) does not fit: register path
-    }
     if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kT && (v & (v - 1)) == 0) tpi = v; }
     const int I = kT / tpi;
-    if (tma && 128 + (size_t)I * a.M * esz * (BWD ? 2 : 1) > (size_t)200 << 10) tma = false;
     a.nI = (N + I - 1) / I;
     // Look-ahead: enough channels to cover the R items in flight plus the fold latency, bounded by L2.
     const size_t chan_bytes = (size_t)N * a.M * esz * (BWD ? 2 : 1);
@@ -654,21 +676,10 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     cudaError_t e = cudaMemsetAsync(a.done, 0, (2 * (size_t)C + 1) * sizeof(unsigned), stream);
     if (e != cudaSuccess) return (int)e;
     const dim3 grid((unsigned)items), block(kT);
-    const int ku = env_int("CNSN_FLOW_KU", kUReg);
-    const size_t dsmem = tma ? 128 + (size_t)I * a.M * esz * (BWD ? 2 : 1) : 0;
 #define CNSN_FLOW_CASE(TPI_)                                                                 \
     case TPI_:                                                                               \
-        if (tma) {                                                                           \
-            if (dsmem > 48 * 1024) {                                                         \
-                e = cudaFuncSetAttribute(k_sn_flow<T, BWD, TPI_, true, kUReg>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); \
-                if (e != cudaSuccess) return (int)e;                                         \
-            }                                                                                \
-            k_sn_flow<T, BWD, TPI_, true, kUReg><<<grid, block, dsmem, stream>>>(a);          \
-        } else if (ku == 8) {                                                                \
-            k_sn_flow<T, BWD, TPI_, false, 8><<<grid, block, 0, stream>>>(a);                 \
-        } else {                                                                             \
-            k_sn_flow<T, BWD, TPI_, false, kUReg><<<grid, block, 0, stream>>>(a);             \
-        }                                                                                    \
+        if (!BWD && a.res) k_sn_flow<T, false, true, TPI_><<<grid, block, 0, stream>>>(a);   \
+        else k_sn_flow<T, BWD, false, TPI_><<<grid, block, 0, stream>>>(a);                  \
         break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_FLOW_CASE(8) CNSN_FLOW_CASE(16) CNSN_FLOW_CASE(32) CNSN_FLOW_CASE(64) CNSN_FLOW_CASE(128) CNSN_FLOW_CASE(256)
@@ -676,8 +687,8 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     });
 #undef CNSN_FLOW_CASE
     if (getenv("CNSN_FLOW_DEBUG"))
-        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu order=%d tma=%d smem=%zu\n", BWD ? "bwd" : "fwd", tpi, I,
-                a.nI, D, items, a.order, (int)tma, dsmem);
+        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu order=%d add=%d relu=%d\n", BWD ? "bwd" : "fwd", tpi, I,
+                a.nI, D, items, a.order, a.res != nullptr, a.relu);
     return launch_status();
 }
 
@@ -690,7 +701,8 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     const int N = a.N, C = a.C;
     const int esz = (int)esize(dtype);
     if (((size_t)a.M * esz) % 16 || N < 1 || C < 1) return -100;
-    const size_t inst_bytes = (size_t)a.M * esz * (BWD ? 2 : 1);
+    const bool add = !BWD && a.res != nullptr;
+    const size_t inst_bytes = (size_t)a.M * esz * ((BWD || add) ? 2 : 1);
     const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
@@ -724,7 +736,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (trace_path && cudaMalloc(&a.trace, trace_bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, trace_bytes, stream);
 #define CNSN_RES_CASE(TPI_)                                                                              \
     case TPI_: {                                                                                         \
-        auto fn = k_sn_res<T, BWD, TPI_, kResT>;                                                         \
+        auto fn = add ? k_sn_res<T, false, !BWD, TPI_, kResT> : k_sn_res<T, BWD, false, TPI_, kResT>;    \
         e = prepare_kernel(fn, kResT, dsmem, &per_sm);                                                   \
         if (e != cudaSuccess) return (int)e;                                                             \
         /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
@@ -770,30 +782,32 @@ static bool use_resident(size_t chan_bytes, bool bwd) {
 size_t scratch_floats(int N, int C) { return 2 * (size_t)N * C + 36 * (size_t)C + 8; }
 
 // Both return 0 when launched, >0 cuda error, -100 when the path does not apply.
-int selfnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+int selfnorm_flow_fwd(const void* x, const void* res, void* z, void* y, int relu, int dtype, int N, int C, int H, int W,
                       const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
                       float* mu, float* sd, float* gate, float* shat, float* r, float* scratch,
                       cudaStream_t stream) {
-    if (!aligned16(x) || !aligned16(y)) return -100;
+    if (!aligned16(x) || !aligned16(y) || (res && (!aligned16(res) || !aligned16(z)))) return -100;
     FArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W;
+    a.res = res; a.zout = res ? z : nullptr; a.relu = relu;
     a.training = training; a.momentum = momentum; a.bn_eps = bn_eps; a.eps = eps;
     a.w = g->w; a.gamma = g->gamma; a.beta = g->beta; a.run_mean = g->run_mean; a.run_var = g->run_var; a.nbt = g->nbt;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
-    if (use_resident((size_t)N * H * W * esize(dtype), false)) {
+    if (use_resident((size_t)N * H * W * esize(dtype) * (res ? 2 : 1), false)) {
         const int rc = launch_res<false>(a, dtype, scratch, stream);
         if (rc != -100) return rc;
     }
     return launch<false>(a, dtype, scratch, stream);
 }
 
-int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dtype, int N, int C, int H, int W,
                       const cnsn_gate_params* g, int training,
                       float* mu, float* sd, float* gate, float* shat, float* r,
                       const cnsn_gate_grads* dg, float* scratch, cudaStream_t stream) {
     if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) return -100;
     FArgs a{};
     a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.M = H * W;
+    a.relu = relu;
     a.training = training;
     a.w = g->w; a.gamma = g->gamma;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;

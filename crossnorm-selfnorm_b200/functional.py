@@ -85,6 +85,32 @@ class SelfNormFn(torch.autograd.Function):
         return tuple(out)
 
 
+class SelfNormBlockFn(torch.autograd.Function):
+    """relu?(SelfNorm(x + res)) in one forward and one backward call: the residual add and
+    the ReLU around a pos='post' site of models/imagenet/resnet_cnsn.py:117-122 /
+    models/cifar/wideresnet_cnsn.py:93-96.  Saved for backward: the sum z and the fp32 statistics block."""
+
+    @staticmethod
+    def forward(ctx, x, res, relu, training, momentum, bn_eps, eps, g_bufs, g_w, g_gamma, g_beta):
+        x = _dense(x)
+        res = _dense(res) if res is not None else None
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
+        y, z, save = _lib.backend().selfnorm_block_fwd(x, res, relu, g, training, momentum, bn_eps, eps)
+        ctx.save_for_backward(z, g_w, g_gamma, g_beta)
+        ctx.sn_save = save
+        ctx.meta = (bool(relu), training, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        z, g_w, g_gamma, g_beta = ctx.saved_tensors
+        relu, training, has_res = ctx.meta
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
+        dz, gg = _lib.backend().selfnorm_block_bwd(z, _dense(dy), relu, g, training, ctx.sn_save)
+        return (dz, dz if has_res else None, None, None, None, None, None, None,
+                gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype))
+
+
 class CrossNormFn(torch.autograd.Function):
     """Device half of cn_op_2ins_space_chan (models/cnsn.py:58-91) and its backward."""
 

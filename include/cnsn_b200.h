@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CNSN_ABI_VERSION 2
+#define CNSN_ABI_VERSION 3
 
 enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
 
@@ -133,6 +133,28 @@ int cnsn_selfnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
                       int training, const float* save,
                       const cnsn_gate_grads* dg, const cnsn_gate_grads* df,
                       float* workspace, void* stream);
+
+/*
+ * Block fusion for the reference's pos='post' sites: the residual add in front of the site and
+ * the ReLU behind it, in the same kernels.  Replaces, in one forward and one backward call,
+ *     out += identity; out = self.cnsn(out); out = self.relu(out)      models/imagenet/resnet_cnsn.py:117-122
+ *     out = torch.add(x, out); return self.cnsn(out)                   models/cifar/wideresnet_cnsn.py:93-96
+ * (SelfNorm-only sites; a site whose CrossNorm fires takes the unfused sequence.)
+ *
+ *   forward : z = x + res (written to `z`, element type `dtype`; pass res = z = NULL for "no add"),
+ *             y = SelfNorm(z), and y = max(y, 0) when `relu`.
+ *   backward: dz = SelfNorm backward at z of dy masked where z <= 0 when `relu` (the gate is a sigmoid, so
+ *             relu(g*z) passes exactly where z > 0); dx = dres = dz.
+ * save / workspace / g / dg as for cnsn_selfnorm_fwd / _bwd.
+ */
+int cnsn_selfnorm_block_fwd(const void* x, const void* res, void* z, void* y, int relu, int dtype,
+                            int N, int C, int H, int W, const cnsn_gate_params* g,
+                            int training, float momentum, float bn_eps, float eps,
+                            float* save, void* stream);
+int cnsn_selfnorm_block_bwd(const void* z, const void* dy, void* dz, int relu, int dtype,
+                            int N, int C, int H, int W, const cnsn_gate_params* g,
+                            int training, const float* save, const cnsn_gate_grads* dg,
+                            float* workspace, void* stream);
 
 /* ---------------------------------------------------------------- CrossNorm --------------
  * Replaces cn_op_2ins_space_chan, models/cnsn.py:58-91 (+ instance_norm_mix :20-29), device

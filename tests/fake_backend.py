@@ -83,6 +83,18 @@ class OracleBackend:
                     _t(gr[tag + "_beta"], x, torch.float32))
         return _t(dx, x), pack("g"), pack("f") if f is not None else None
 
+    def selfnorm_block_fwd(self, x, res, relu, g, training, momentum, bn_eps, eps):
+        self.calls.append("selfnorm_block_fwd")
+        z = x if res is None else (x + res)
+        y, save = self.selfnorm_fwd(z, g, None, training, momentum, bn_eps, eps)
+        return (torch.relu(y) if relu else y), z, save
+
+    def selfnorm_block_bwd(self, z, dy, relu, g, training, save):
+        self.calls.append("selfnorm_block_bwd")
+        d = torch.where(z > 0, dy, torch.zeros_like(dy)) if relu else dy
+        dz, gg, _ = self.selfnorm_bwd(z, d, g, None, training, save)
+        return dz, gg
+
     @staticmethod
     def _plan(x, perm, chan_perm, cwin, swin):
         return {"perm": perm.cpu().numpy().astype(np.int64),

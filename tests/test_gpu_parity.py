@@ -153,6 +153,48 @@ def test_selfnorm_batch1_raises(mod):
     assert m(torch.randn(1, 4, 8, 8, device=DEV)).shape == (1, 4, 8, 8)
 
 
+# ------------------------------------------------------------------ fused block: add + SelfNorm + ReLU
+BLOCK_SHAPES = [((16, 8, 8, 8), torch.float32), ((64, 12, 28, 28), torch.float32), ((256, 8, 56, 56), torch.float32),
+                ((96, 40, 7, 7), torch.float32), ((64, 16, 14, 14), torch.bfloat16), ((256, 12, 56, 56), torch.bfloat16),
+                ((5, 3, 9, 14), torch.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", BLOCK_SHAPES)
+@pytest.mark.parametrize("add,relu", [(True, True), (True, False), (False, True)])
+@pytest.mark.parametrize("training", [True, False])
+def test_selfnorm_block_fusion_vs_oracle(mod, shape, dtype, add, relu, training):
+    """relu?(SelfNorm(x + res)) through cnsn_selfnorm_block_fwd/_bwd against the oracle applied to the unfused
+    sequence: shapes for the shared-memory-resident kernel, the L2 kernel (channel too large once two planes
+    per instance are resident) and the general path (7x7, 9x14 planes)."""
+    rs = np.random.RandomState(sum(shape))
+    x = O.varied_input(shape, seed=sum(shape) + 1, dtype=np.float32)
+    r = (rs.standard_normal(shape) * 0.7).astype(np.float32)
+    dy = rs.standard_normal(shape).astype(np.float32)
+    if dtype != torch.float32:
+        x, r, dy = (torch.from_numpy(v).to(dtype).float().numpy() for v in (x, r, dy))
+    params, bufs = H.random_sn_params(shape[1], seed=5)
+    m = H.make_selfnorm(mod, shape[1], params, bufs, DEV, False, training)
+    xt = torch.from_numpy(x).to(device=DEV, dtype=dtype).requires_grad_(True)
+    rt = torch.from_numpy(r).to(device=DEV, dtype=dtype).requires_grad_(True)
+    y = m(xt, rt if add else None, relu)
+    y.backward(torch.from_numpy(dy).to(device=DEV, dtype=dtype))
+    # oracle on the unfused sequence; the sum is rounded to the element type like torch.add's output
+    z = (torch.from_numpy(x).to(dtype) + torch.from_numpy(r).to(dtype)).float().numpy() if add else x
+    yo, nb = O.selfnorm_fwd(z.astype(np.float64), params, bufs, training)
+    mask = (yo > 0) if relu else np.ones_like(yo, dtype=bool)
+    dzo, gr = O.selfnorm_bwd(z.astype(np.float64), np.where(mask, dy, 0.0), params, bufs, training)
+    chk = close32 if dtype == torch.float32 else close16
+    chk(y.detach().double().cpu().numpy(), np.where(mask, yo, 0.0), "y")
+    chk(xt.grad.double().cpu().numpy(), dzo, "dx")
+    if add:
+        assert torch.equal(xt.grad, rt.grad)
+    tol = H.PARAM_RTOL if dtype == torch.float32 else 1e-4
+    assert H.relmax(m.g_fc.weight.grad.view(-1, 2).double().cpu().numpy(), gr["g_w"]) <= tol
+    assert H.relmax(m.g_bn.weight.grad.double().cpu().numpy(), gr["g_gamma"]) <= tol
+    assert H.relmax(m.g_bn.bias.grad.double().cpu().numpy(), gr["g_beta"]) <= tol
+    close32(m.g_bn.running_mean.double().cpu().numpy(), nb["g_rm"] if training else bufs["g_rm"], "running_mean")
+
+
 CN_SHAPES = [(8, 6, 12, 10), (4, 16, 8, 8), (6, 5, 7, 7), (16, 8, 32, 32), (3, 2, 72, 72), (5, 3, 9, 14), (37, 3, 20, 20)]
 
 

@@ -141,6 +141,36 @@ def test_cnsn_composition(mod):
     assert mod._fake.calls[1:] == ["crossnorm_fwd", "selfnorm_fwd"] and cn.active is False
 
 
+@pytest.mark.parametrize("fire", [False, True])
+@pytest.mark.parametrize("relu", [False, True])
+def test_cnsn_block_fusion_equals_unfused_sequence(mod, fire, relu):
+    """CNSN.forward(x, residual, relu) == relu?(CNSN(x + residual)) -- values, input gradients, parameter
+    gradients, running statistics, RNG consumption and the .active protocol -- whether or not CrossNorm fires."""
+    shape = (6, 4, 5, 5)
+    g = torch.Generator().manual_seed(7)
+    x0, r0, dy = (torch.randn(shape, generator=g, dtype=torch.float64) for _ in range(3))
+    res = []
+    for fused in (False, True):
+        torch.manual_seed(3)
+        np.random.seed(4)
+        blk = mod.CNSN(crossnorm=mod.CrossNorm(crop="both", beta=1), selfnorm=mod.SelfNorm(4)).double().train()
+        blk.crossnorm.active = fire
+        x, r = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+        if fused:
+            y = blk(x, r, relu)
+        else:
+            y = blk(torch.add(r, x))
+            y = torch.relu(y) if relu else y
+        y.backward(dy)
+        assert blk.crossnorm.active is False
+        res.append((y.detach(), x.grad, r.grad, blk.selfnorm.g_fc.weight.grad, blk.selfnorm.g_bn.weight.grad,
+                    blk.selfnorm.g_bn.running_var.clone(), torch.rand(1), np.random.rand()))
+    for a, b in zip(*res):
+        assert np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), atol=1e-12), (a, b)
+    if not fire:
+        assert "selfnorm_block_fwd" in mod._fake.calls and "selfnorm_block_bwd" in mod._fake.calls
+
+
 def test_selfnorm_state_dict_matches_reference(mod):
     ref = load_reference_cnsn()
     if ref is None:

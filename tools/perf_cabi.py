@@ -1,7 +1,9 @@
 """Kernel-limited timing of the C-ABI entry points: buffers allocated once, `reps` calls queued back to back,
 CUDA events around the batch (so host time per call is hidden as long as it is below the kernel time).
 
-    python tools/perf_cabi.py selfnorm|crossnorm N,C,H,W f32|bf16 [crop] [reps]
+    python tools/perf_cabi.py selfnorm|block|crossnorm N,C,H,W f32|bf16 [crop] [reps]
+`block` = cnsn_selfnorm_block_fwd/_bwd: relu(SelfNorm(x + res)), algorithmic bytes 4*S forward (x, res in; z, y out),
+3*S backward; the last line of its output times the unfused sequence (torch add, SelfNorm, torch relu) for context.
 Environment knobs (CNSN_SELFNORM_IMPL, CNSN_CROSSNORM_IMPL, CNSN_FLOW_*) are read by the library per call.
 """
 import ctypes
@@ -36,7 +38,7 @@ stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 f32 = dict(dtype=torch.float32, device=dev)
 
-if op == "selfnorm":
+if op in ("selfnorm", "block"):
     w = torch.randn(C, 2, **f32) * 0.5
     gamma, beta = torch.rand(C, **f32) + 0.5, torch.randn(C, **f32) * 0.1
     rm, rv = torch.zeros(C, **f32), torch.ones(C, **f32)
@@ -53,6 +55,17 @@ if op == "selfnorm":
     def bwd():
         L._check(h.cnsn_selfnorm_bwd(P(x), P(dy), P(dx), code, N, C, H, W, ctypes.byref(gp), None, TRAIN, P(save),
                                      ctypes.byref(gg), None, P(ws), stream))
+    if op == "block":
+        res = torch.randn(shape, device=dev, generator=g).to(dt)
+        z = torch.empty_like(x)
+
+        def fwd():  # noqa: F811
+            L._check(h.cnsn_selfnorm_block_fwd(P(x), P(res), P(z), P(y), 1, code, N, C, H, W, ctypes.byref(gp), TRAIN,
+                                               0.1, 1e-5, 1e-12, P(save), stream))
+
+        def bwd():  # noqa: F811
+            L._check(h.cnsn_selfnorm_block_bwd(P(z), P(dy), P(dx), 1, code, N, C, H, W, ctypes.byref(gp), TRAIN, P(save),
+                                               ctypes.byref(gg), P(ws), stream))
 else:
     perm = torch.randperm(N, generator=torch.Generator().manual_seed(3)).to(torch.int32).to(dev)
     rs = np.random.RandomState(4)
@@ -94,5 +107,21 @@ fwd()
 tf, hf = timeit(fwd)
 tb, hb = timeit(bwd)
 tag = " ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("CNSN_") or k == "PERF_EVAL")
+kf = 4 if op == "block" else 2
 print("%s %s %s crop=%s [%s] | fwd %.1f us (host %.1f) %.0f GB/s | bwd %.1f us (host %.1f) %.0f GB/s | fwd+bwd %.0f GB/s" % (
-    op, shape, str(dt).split(".")[-1], crop, tag or "-", tf, hf, 2 * S / tf / 1e3, tb, hb, 3 * S / tb / 1e3, 5 * S / (tf + tb) / 1e3))
+    op, shape, str(dt).split(".")[-1], crop, tag or "-", tf, hf, kf * S / tf / 1e3, tb, hb, 3 * S / tb / 1e3, (kf + 3) * S / (tf + tb) / 1e3))
+if op == "block":            # context: the same block tail unfused (torch add / relu around the fused SelfNorm kernels)
+    import cnsn_b200.cnsn as M
+    sn = M.SelfNorm(C).to(dev).train(bool(TRAIN))
+    xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+
+    def seq():
+        out = torch.relu(sn(torch.add(rr, xr)))
+        torch.autograd.grad(out, (xr, rr), dy)
+
+    def fus():
+        out = sn(xr, rr, True)
+        torch.autograd.grad(out, (xr, rr), dy)
+    t1, _ = timeit(seq)
+    t2, _ = timeit(fus)
+    print("   module API fwd+bwd: unfused (torch add, SelfNorm, torch relu) %.1f us | fused block %.1f us | x%.2f" % (t1, t2, t1 / t2))
