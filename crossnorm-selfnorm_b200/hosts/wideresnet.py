@@ -28,8 +28,9 @@ def _default_ops():
 class _PreActBlock(nn.Module):
     """BN-ReLU-conv3x3-BN-ReLU-conv3x3 with an additive shortcut and one CNSN site."""
 
-    def __init__(self, cin, cout, stride, pos, beta, crop, cnsn_type, drop_rate, ops):
+    def __init__(self, cin, cout, stride, pos, beta, crop, cnsn_type, drop_rate, ops, fuse_post=False):
         super().__init__()
+        self.fuse_post = bool(fuse_post) and pos == "post"
         assert cnsn_type in ("sn", "cn", "cnsn")
         assert pos in _POSITIONS
         self.pos, self.drop_rate, self.same = pos, drop_rate, cin == cout
@@ -66,6 +67,8 @@ class _PreActBlock(nn.Module):
             h = self.cnsn(h)
         elif self.pos == "identity":
             skip = self.cnsn(skip)
+        if self.fuse_post:                      # opt-in: the add runs inside the SelfNorm kernels
+            return self.cnsn(h, skip, False)
         h = torch.add(skip, h)
         return self.cnsn(h) if self.pos == "post" else h
 
@@ -82,13 +85,13 @@ class _Stage(nn.Module):
 
 class WideResNet(nn.Module):
     def __init__(self, depth, num_classes, widen_factor=1, drop_rate=0.0, active_num=None, pos=None, beta=None,
-                 crop=None, cnsn_type=None, ops=None, verbose=False):
+                 crop=None, cnsn_type=None, ops=None, verbose=False, fuse_post=False):
         super().__init__()
         ops = ops or _default_ops()
         assert (depth - 4) % 6 == 0
         per_stage = (depth - 4) // 6
         widths = [16, 16 * widen_factor, 32 * widen_factor, 64 * widen_factor]
-        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, drop_rate=drop_rate, ops=ops)
+        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, drop_rate=drop_rate, ops=ops, fuse_post=fuse_post)
         self.conv1 = nn.Conv2d(3, widths[0], 3, 1, 1, bias=False)
         self.block1 = _Stage(per_stage, widths[0], widths[1], 1, **kw)
         self.block2 = _Stage(per_stage, widths[1], widths[2], 2, **kw)

@@ -18,11 +18,11 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
-def wrn40_2(ops=None, num_classes=10, active_num=2, pos="post", beta=1, crop="both", cnsn_type="cnsn"):
+def wrn40_2(ops=None, num_classes=10, active_num=2, pos="post", beta=1, crop="both", cnsn_type="cnsn", fuse_post=False):
     """WideResNet-40-2 + CNSN with the hyper-parameters of cifar10-scripts/wideresnet/run-cnsn.sh."""
     from .hosts.wideresnet import WideResNet
     return WideResNet(40, num_classes, widen_factor=2, drop_rate=0.0, active_num=active_num, pos=pos, beta=beta,
-                      crop=crop, cnsn_type=cnsn_type, ops=ops)
+                      crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post)
 
 
 def cosine_lr(step, total_steps, lr_max, lr_min):
@@ -47,12 +47,12 @@ def train_step(net, images, targets, opt, sched, cn_prob):
     return float(loss.detach())
 
 
-def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None):
+def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False):
     """images/s of WideResNet-40-2 + CNSN training on synthetic CIFAR-shaped data (fp32, batch per GPU)."""
     import torch.distributed as dist
     torch.manual_seed(1 + rank)
     np.random.seed(1 + rank)                  # each rank draws its own perms / boxes / coins
-    net = wrn40_2(ops=ops).to(dev).train()
+    net = wrn40_2(ops=ops, fuse_post=fuse_post).to(dev).train()
     model = net
     if world > 1:
         # broadcast_buffers=False: SelfNorm / BatchNorm running statistics stay per replica, as under the
@@ -103,10 +103,69 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
            "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
            "batch_per_gpu": batch, "n_gpus": world, "dtype": "f32 (TF32 convolutions: %s)" % torch.backends.cudnn.allow_tf32,
            "config": "depth 40, widen 2, cnsn_type=cnsn, pos=post, crop=both, beta=1, active_num=2, cn_prob=%g, "
-                     "SGD nesterov lr 0.1 wd 5e-4, cosine LR, synthetic 32x32" % cn_prob,
+                     "SGD nesterov lr 0.1 wd 5e-4, cosine LR, synthetic 32x32, fuse_post=%s" % (cn_prob, bool(fuse_post)),
            "final_loss": loss, "params": sum(p.numel() for p in net.parameters())}
     if launches0 is not None:
         from . import _lib
         out["cnsn_kernel_launches"] = _lib.launch_count() - launches0
     out["param_checksum"] = float(sum(p.detach().double().sum() for p in net.parameters()))
     return out
+
+
+def resnet50_step(net, images, targets, opt, cn_prob, ops, beta=1, crop="neither"):
+    """One ``train_cn_image`` step of the reference's imagenet.py:205-230: a coin decides whether this batch goes
+    through image-space CrossNorm (``cn_op_2ins_space_chan(input, beta, crop)``) before the network; cross-entropy,
+    ``zero_grad``, ``backward``, SGD step, and a ``loss.item()`` read (host sync) every step, as there."""
+    if np.random.rand(1) < cn_prob:
+        images = ops.cn_op_2ins_space_chan(images, beta=beta, crop=crop)
+    loss = F.cross_entropy(net(images, aug=False), targets)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return float(loss.detach())
+
+
+def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5, fuse_post=True, ops=None):
+    """images/s of ResNet-50 + SelfNorm ('post') training with image-space CrossNorm on synthetic 224x224 data
+    (BASELINE config 4: batch 256 per GPU, SGD lr 0.1 momentum 0.9 wd 1e-4; imagenet-scripts/run-cnsn.sh)."""
+    import torch.distributed as dist
+    from . import _lib
+    from .hosts.resnet import resnet50
+    if ops is None:
+        from . import cnsn as ops
+    torch.manual_seed(1 + rank)
+    np.random.seed(1 + rank)
+    net = resnet50(fuse_post=fuse_post, ops=ops).to(dev).train()
+    model = net
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
+    opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(batch, 3, 224, 224, device=dev)
+    y = torch.randint(0, 1000, (batch,), device=dev)
+    launches0 = _lib.launch_count()
+    for _ in range(warmup):
+        resnet50_step(model, x, y, opt, cn_prob, ops)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    loss = 0.0
+    for _ in range(steps):
+        loss = resnet50_step(model, x, y, opt, cn_prob, ops)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"metric": "ResNet-50 + SelfNorm training images/s", "value": world * batch * steps / (ms * 1e-3),
+            "unit": "images/s", "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "batch_per_gpu": batch,
+            "n_gpus": world, "dtype": "f32 (TF32 convolutions: %s)" % torch.backends.cudnn.allow_tf32,
+            "config": "resnet50 cnsn_type=sn pos=post, image-space CrossNorm crop=neither beta=1 cn_prob=%g, SGD lr 0.1 "
+                      "momentum 0.9 wd 1e-4, synthetic 224x224, fuse_post=%s" % (cn_prob, bool(fuse_post)),
+            "final_loss": loss, "params": sum(p.numel() for p in net.parameters()),
+            "cnsn_kernel_launches": _lib.launch_count() - launches0}

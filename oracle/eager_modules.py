@@ -13,6 +13,16 @@ from . import eager_chain as E
 from .cnsn_oracle import rand_window
 
 
+def cn_op_2ins_space_chan(x, crop="neither", beta=1, bbx_thres=0.1, lam=None, chan=False):
+    """Function form (models/cnsn.py:58-91) for the image-space CrossNorm of the ImageNet step (imagenet.py:215)."""
+    assert crop in ("neither", "style", "content", "both")
+    perm = torch.randperm(x.size(0))
+    sw = rand_window(x.shape, beta, bbx_thres) if crop in ("style", "both") else None
+    cperm = torch.randperm(x.size(1)) if chan else None
+    cw = rand_window(x.shape, beta, bbx_thres) if crop in ("content", "both") else None
+    return E.crossnorm(x, perm, sw, cw, cperm, lam)
+
+
 class CrossNorm(nn.Module):
     def __init__(self, crop=None, beta=None):
         super().__init__()

@@ -19,7 +19,7 @@ def fake():
     L.set_backend_for_tests(old)
 
 
-def _reference_wrn():
+def _reference_host(module, attr):
     root = reference_root()
     if root is None:
         pytest.skip("reference checkout not present")
@@ -32,13 +32,61 @@ def _reference_wrn():
         import models
         sys.modules["models.cnsn"] = ref
         models.cnsn = ref
-        host = __import__("models.cifar.wideresnet_cnsn", fromlist=["x"])
+        host = __import__(module, fromlist=["x"])
     finally:
         sys.path.remove(root)
         for k in [k for k in sys.modules if k == "models" or k.startswith("models.")]:
             del sys.modules[k]
         sys.modules.update(saved)
-    return host.WideResNet
+    return getattr(host, attr)
+
+
+def _reference_wrn():
+    return _reference_host("models.cifar.wideresnet_cnsn", "WideResNet")
+
+
+@pytest.mark.parametrize("pos,cnsn_type,fuse", [("post", "sn", False), ("post", "sn", True), ("post", "cnsn", True),
+                                                ("pre", "cnsn", False), ("residual", "cnsn", False), ("identity", "sn", False)])
+def test_resnet_matches_reference_model(fake, pos, cnsn_type, fuse, capsys):
+    """ResNet bottleneck host vs models/imagenet/resnet_cnsn.py: same seed -> identical state dict; same inputs and
+    host RNG -> same logits and gradients, with and without the fused 'post' tail."""
+    from cnsn_b200.hosts import ResNet
+    RefResNet = _reference_host("models.imagenet.resnet_cnsn", "ResNet")
+    kw = dict(num_classes=7, active_num=1, pos=pos, beta=1, crop="both", cnsn_type=cnsn_type)
+    torch.manual_seed(0)
+    a = RefResNet([1, 1, 1, 1], **kw).double().train()
+    torch.manual_seed(0)
+    b = ResNet([1, 1, 1, 1], fuse_post=fuse, **kw).double().train()
+    capsys.readouterr()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    x = torch.randn(4, 3, 64, 64, dtype=torch.float64)
+    outs = []
+    for net in (a, b):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        o = net(x, aug="cn" in cnsn_type)
+        o.square().sum().backward()
+        outs.append(o)
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+    if fuse:
+        assert "selfnorm_block_fwd" in fake.calls
+    a.eval(), b.eval()
+    assert torch.allclose(a(x), b(x), atol=1e-8)
+
+
+def test_resnet50_census():
+    """ResNet-50 + SN ('post'): 16 SelfNorm sites with the channel counts of SURVEY.md 8 (cfg4)."""
+    from cnsn_b200.hosts import resnet50
+    import cnsn_b200.cnsn as m
+    net = resnet50()
+    widths = [k.g_bn.num_features for k in net.modules() if isinstance(k, m.SelfNorm)]
+    assert widths == [256] * 3 + [512] * 4 + [1024] * 6 + [2048] * 3
+    assert "layer1.0.cnsn.selfnorm.g_fc.weight" in net.state_dict() and "layer2.0.downsample.1.weight" in net.state_dict()
 
 
 @pytest.mark.parametrize("pos", ["post", "pre", "residual", "identity"])
