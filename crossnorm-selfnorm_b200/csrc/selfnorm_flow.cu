@@ -362,10 +362,16 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
 // CTAs at once (checked on the host with the occupancy API) the lowest unfinished channel is always completely
 // resident, none of its CTAs waits before it has published, and it completes.  All N planes of a channel (and
 // the next few) live in shared memory across the GPU: N*M*sizeof(T)*tensors must fit a fraction of 148 x 227 KB.
-template <typename T, bool BWD, bool ADD, int TPI, int TH>
+// DYG (backward only): dy is NOT staged in shared memory -- it is streamed from global memory twice (reduce:
+// L2 hit thanks to the predecessor's prefetch, marked evict-last; apply: L2 hit, evict-first) while x stays
+// resident.  Twice the instances fit on chip, at 7 L2 transactions per byte of S instead of 6 (both planes
+// resident) or 8 (k_sn_flow).  For channels whose x AND dy do not fit the GPU's shared memory.
+template <typename T, bool BWD, bool ADD, bool DYG, int TPI, int TH>
 __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     static_assert(!(BWD && ADD), "the fused add is a forward feature");
-    constexpr bool two = BWD || ADD;                         // a second plane per instance: dy (backward) / res (fused add)
+    static_assert(BWD || !DYG, "DYG is a backward variant");
+    constexpr bool two = (BWD && !DYG) || ADD;               // a second plane per instance in shared memory: dy / res
+    constexpr int kB = 4;                                    // DYG: 128-bit loads of dy in flight per thread
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
     constexpr int kHold = 4;                                 // published words a folding thread keeps in registers
@@ -403,7 +409,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
             fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (two) fused::tma_load_1d(dst + (size_t)I * pbytes, second + off, pbytes, bar, pol);
+            if (two) fused::tma_load_1d(dst + (size_t)I * pbytes, second + off, pbytes, bar, pol);   // not for DYG
         }
         // L2 prefetch for the CTA that will take this one's place: its TMA loads then hit L2 instead of paying
         // the HBM latency (and its tail) while its shared memory is already tied up.  Same L2 traffic.
@@ -414,7 +420,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
                 fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (two) fused::tma_prefetch_l2(second + off, pbytes);
+                if (two || DYG) fused::tma_prefetch_l2(second + off, pbytes);
             }
         }
     }
@@ -429,13 +435,48 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         p_b = a.beta[c];
         if (folder && threadIdx.x == 0) { p_rm = a.run_mean[c]; p_rv = a.run_var[c]; }
     }
+    // DYG: dy comes from global memory; the first batch is issued before the planes of x have landed
+    const uint4* gdy = DYG ? reinterpret_cast<const uint4*>(static_cast<const T*>(a.dy) + nc * M) : nullptr;
+    uint4 rdy[kB];
+    const uint64_t pol_keep = l2_policy_evict_last(), pol_once = l2_policy_evict_first();
+    auto issue_dy = [&](int i0, uint64_t pol) {
+#pragma unroll
+        for (int u = 0; u < kB; ++u) {
+            const int i = i0 + u * TPI;
+            if (live && i < nv) rdy[u] = ldg_hint(gdy + i, pol);
+        }
+    };
+    if (DYG) issue_dy(r, pol_keep);
     fused::mbar_wait(bar, 0);
     CNSN_FTRACE(1);                                          // 1 planes landed
 
     // ---- reduce out of shared memory -----------------------------------------------------------
     const bool relu = a.relu != 0;
     float own_x = 0.f, own_y = 0.f;                          // this instance's published word
-    if (BWD) {
+    if (BWD && DYG) {
+        float s0 = 0.f, s1 = 0.f;
+        for (int i0 = r;;) {
+#pragma unroll
+            for (int u = 0; u < kB; ++u) {
+                const int i = i0 + u * TPI;
+                if (live && i < nv) {
+                    float vx[V], vd[V];
+                    unpack<T>(lds128(sx + 16u * i), vx);
+                    unpack<T>(rdy[u], vd);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                        if (e & 1) s1 = fmaf(d, vx[e], s1); else s0 = fmaf(d, vx[e], s0);
+                    }
+                }
+            }
+            i0 += TPI * kB;
+            if (i0 - r >= nv) break;
+            issue_dy(i0, pol_keep);
+        }
+        const float sxy = team_sum<TPI>(s0 + s1, s_f[0]);
+        own_x = sxy * pre_g * (1.f - pre_g); own_y = pre_s;
+    } else if (BWD) {
         float s0 = 0.f, s1 = 0.f;
         if (live) {
 #pragma unroll 4
@@ -609,22 +650,46 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         cb = gt;
     }
     uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + nc * M);
-#pragma unroll 4
-    for (int i = r; i < nv; i += TPI) {
-        float vx[V], vd[V], vo[V];
-        unpack<T>(lds128(sx + 16u * i), vx);
-        if (BWD) unpack<T>(lds128(sdy + 16u * i), vd);
+    if (DYG) {                                               // second read of dy: L2 hit, last use
+        issue_dy(r, pol_once);
+        for (int i0 = r;;) {
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            if (BWD) {
-                const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
-                vo[e] = fmaf(ca, d, fmaf(cb, vx[e], cc));
-            } else {
-                const float y = fmaf(cb, vx[e], 0.f);
-                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            for (int u = 0; u < kB; ++u) {
+                const int i = i0 + u * TPI;
+                if (i < nv) {
+                    float vx[V], vd[V], vo[V];
+                    unpack<T>(lds128(sx + 16u * i), vx);
+                    unpack<T>(rdy[u], vd);
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                        vo[e] = fmaf(ca, d, fmaf(cb, vx[e], cc));
+                    }
+                    stg_stream(po + i, pack<T>(vo));
+                }
             }
+            i0 += TPI * kB;
+            if (i0 - r >= nv) break;
+            issue_dy(i0, pol_once);
         }
-        stg_stream(po + i, pack<T>(vo));
+    } else {
+#pragma unroll 4
+        for (int i = r; i < nv; i += TPI) {
+            float vx[V], vd[V], vo[V];
+            unpack<T>(lds128(sx + 16u * i), vx);
+            if (BWD) unpack<T>(lds128(sdy + 16u * i), vd);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                if (BWD) {
+                    const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                    vo[e] = fmaf(ca, d, fmaf(cb, vx[e], cc));
+                } else {
+                    const float y = fmaf(cb, vx[e], 0.f);
+                    vo[e] = relu ? fmaxf(y, 0.f) : y;
+                }
+            }
+            stg_stream(po + i, pack<T>(vo));
+        }
     }
     CNSN_FTRACE(5);                                          // 5 applied
 }
@@ -697,12 +762,13 @@ constexpr int kResT = 128;              // threads per CTA of the shared-memory-
 
 // Shared-memory-resident path.  Returns -100 when the shape does not fit (the caller uses the L2 path).
 template <bool BWD>
-static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
+static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, bool dy_from_global = false) {
     const int N = a.N, C = a.C;
     const int esz = (int)esize(dtype);
     if (((size_t)a.M * esz) % 16 || N < 1 || C < 1) return -100;
     const bool add = !BWD && a.res != nullptr;
-    const size_t inst_bytes = (size_t)a.M * esz * ((BWD || add) ? 2 : 1);
+    const bool dyg = BWD && dy_from_global;
+    const size_t inst_bytes = (size_t)a.M * esz * (((BWD && !dyg) || add) ? 2 : 1);
     const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
@@ -736,7 +802,8 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (trace_path && cudaMalloc(&a.trace, trace_bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, trace_bytes, stream);
 #define CNSN_RES_CASE(TPI_)                                                                              \
     case TPI_: {                                                                                         \
-        auto fn = add ? k_sn_res<T, false, !BWD, TPI_, kResT> : k_sn_res<T, BWD, false, TPI_, kResT>;    \
+        auto fn = add ? k_sn_res<T, false, !BWD, false, TPI_, kResT>                                     \
+                      : (dyg ? k_sn_res<T, BWD, false, BWD, TPI_, kResT> : k_sn_res<T, BWD, false, false, TPI_, kResT>); \
         e = prepare_kernel(fn, kResT, dsmem, &per_sm);                                                   \
         if (e != cudaSuccess) return (int)e;                                                             \
         /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
@@ -765,8 +832,8 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         cudaFree(a.trace);
     }
     if (getenv("CNSN_FLOW_DEBUG"))
-        fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu order=%d smem=%zu ctas/sm=%d\n", BWD ? "bwd" : "fwd", tpi,
-                inst, a.nI, items, a.order, dsmem, per_sm);
+        fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu order=%d smem=%zu ctas/sm=%d dyg=%d\n", BWD ? "bwd" : "fwd",
+                tpi, inst, a.nI, items, a.order, dsmem, per_sm, (int)dyg);
     return launch_status();
 }
 
@@ -812,8 +879,16 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
     a.w = g->w; a.gamma = g->gamma;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
     a.dw = dg->dw; a.dgamma = dg->dgamma; a.dbeta = dg->dbeta;
-    if (use_resident((size_t)N * H * W * esize(dtype) * 2, true)) {
-        const int rc = launch_res<true>(a, dtype, scratch, stream);
+    // backward: both planes resident when the channel is small, L2 items otherwise.  The third variant -- x
+    // resident, dy streamed through L2 (DYG) -- measured slower than both on B200 (0.50-0.61 ms against 0.476 /
+    // 0.511 at the north-star shape: two more L2 round trips per item outweigh the doubled capacity); it stays
+    // selectable.  CNSN_FLOW_BWD=res|dyg|l2 forces one (A/B measurements).
+    const size_t chan_x = (size_t)N * H * W * esize(dtype);
+    int mode = use_resident(2 * chan_x, true) ? 0 : 2;
+    if (const char* e = getenv("CNSN_FLOW_BWD")) mode = e[0] == 'r' ? 0 : e[0] == 'd' ? 1 : 2;
+    else if (const char* m = getenv("CNSN_FLOW_MODE")) mode = m[0] == 'r' ? 0 : 2;
+    if (mode < 2) {
+        const int rc = launch_res<true>(a, dtype, scratch, stream, mode == 1);
         if (rc != -100) return rc;
     }
     return launch<true>(a, dtype, scratch, stream);

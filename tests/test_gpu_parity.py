@@ -368,12 +368,12 @@ def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatc
     monkeypatch.delenv("CNSN_FLOW_D")
     monkeypatch.setenv("CNSN_FLOW_MODE", "l2")                                         # L2-resident second read (registers)
     fl3 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.setenv("CNSN_FLOW_TMA", "1")                                           # ... staged through shared memory by TMA
-    fl4 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_FLOW_TMA")
     monkeypatch.setenv("CNSN_FLOW_MODE", "res")                                        # shared-memory-resident planes
     fl5 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
     monkeypatch.delenv("CNSN_FLOW_MODE")
+    monkeypatch.setenv("CNSN_FLOW_BWD", "dyg")                                         # backward: x resident, dy through L2
+    fl4 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
+    monkeypatch.delenv("CNSN_FLOW_BWD")
     monkeypatch.delenv("CNSN_SELFNORM_IMPL")
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     chk = close32 if dtype == torch.float32 else close16
