@@ -157,6 +157,8 @@ def run_reference_arm(args, shape):
             from oracle import eager_modules
             train = bench_wrn(torch.device("cpu"), 1, 0, batch=64, steps=2, warmup=1, ops=eager_modules)
             train["sample"] = "batch 64 (of 512), 2 steps after 1 warm-up, CPU, eager-PyTorch CNSN (oracle/eager_modules.py)"
+            from cnsn_b200.train import bench_resnet50_cpu
+            train["resnet50"] = bench_resnet50_cpu(eager_modules, batch=16, steps=1, warmup=1)
         except Exception as e:
             train = {"error": repr(e)[:300]}
     line = {
@@ -370,10 +372,13 @@ def main():
     train = None
     if not args.no_train:
         try:
-            from cnsn_b200.train import bench_wrn
-            train = bench_wrn(dev, world, rank, batch=args.train_batch, steps=args.train_steps, warmup=5)
+            from cnsn_b200.train import bench_resnet50, bench_wrn
+            train = bench_wrn(dev, world, rank, batch=args.train_batch, steps=args.train_steps, warmup=5, fuse_post=True)
+            torch.cuda.empty_cache()
+            # BASELINE config 4: ResNet-50 + SelfNorm ('post'), image-space CrossNorm, 224x224, batch 256 per GPU
+            train["resnet50"] = bench_resnet50(dev, world, rank, batch=256, steps=8, warmup=3, fuse_post=True)
         except Exception as e:      # the headline must still be printed
-            train = {"error": repr(e)[:300]}
+            train = dict(train or {}, error=repr(e)[:300])
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

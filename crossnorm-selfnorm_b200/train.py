@@ -169,3 +169,24 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
                       "momentum 0.9 wd 1e-4, synthetic 224x224, fuse_post=%s" % (cn_prob, bool(fuse_post)),
             "final_loss": loss, "params": sum(p.numel() for p in net.parameters()),
             "cnsn_kernel_launches": _lib.launch_count() - launches0}
+
+
+def bench_resnet50_cpu(ops, batch=16, steps=1, warmup=1, cn_prob=0.5):
+    """The same ResNet-50 step on the host cores with a caller-supplied operator set (the CPU reference arm of
+    bench.py passes the eager-PyTorch restatement); a bounded sample of BASELINE config 4 (batch 16 of 256)."""
+    import time
+    from .hosts.resnet import resnet50
+    torch.manual_seed(1)
+    np.random.seed(1)
+    net = resnet50(fuse_post=False, ops=ops).train()
+    opt = torch.optim.SGD(net.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
+    x, y = torch.randn(batch, 3, 224, 224), torch.randint(0, 1000, (batch,))
+    for _ in range(warmup):
+        resnet50_step(net, x, y, opt, cn_prob, ops)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loss = resnet50_step(net, x, y, opt, cn_prob, ops)
+    dt = time.perf_counter() - t0
+    return {"metric": "ResNet-50 + SelfNorm training images/s", "value": batch * steps / dt, "unit": "images/s",
+            "ms_per_step": dt / steps * 1e3, "batch_per_gpu": batch, "final_loss": loss,
+            "sample": "batch %d (of 256), %d step(s) after %d warm-up, CPU, eager-PyTorch CNSN" % (batch, steps, warmup)}
