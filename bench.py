@@ -377,6 +377,10 @@ def main():
             torch.cuda.empty_cache()
             # BASELINE config 4: ResNet-50 + SelfNorm ('post'), image-space CrossNorm, 224x224, batch 256 per GPU
             train["resnet50"] = bench_resnet50(dev, world, rank, batch=256, steps=8, warmup=3, fuse_post=True)
+            torch.cuda.empty_cache()
+            # BASELINE config 5: the same network on 3 x 256 views per GPU with the JSD consistency step, bf16
+            from cnsn_b200.train import bench_resnet50_jsd
+            train["resnet50_jsd"] = bench_resnet50_jsd(dev, world, rank, batch=256, steps=4, warmup=2, fuse_post=True)
         except Exception as e:      # the headline must still be printed
             train = dict(train or {}, error=repr(e)[:300])
 

@@ -55,6 +55,8 @@ SIGNATURES = {
                                         c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "cnsn_selfnorm_block_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
                                         c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_jsd_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "cnsn_jsd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p,
@@ -295,6 +297,25 @@ class CudaBackend:
                                                  ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg),
                                                  _p(ws), _stream(z)))
         return dz, out_g
+
+    # -- JSD consistency --------------------------------------------------------------------
+    def jsd_fwd(self, z0, z1, z2):
+        _require_cuda(z0, z1, z2)
+        B, K = z0.shape
+        row = torch.empty(B, dtype=torch.float32, device=z0.device)
+        loss = torch.empty((), dtype=torch.float32, device=z0.device)
+        with _on(z0.device):
+            _check(lib().cnsn_jsd_fwd(_p(z0), _p(z1), _p(z2), _dtype_code(z0), B, K, _p(row), _p(loss), _stream(z0)))
+        return loss
+
+    def jsd_bwd(self, z0, z1, z2, gout):
+        _require_cuda(z0, z1, z2, gout)
+        B, K = z0.shape
+        d = [torch.empty_like(z) for z in (z0, z1, z2)]
+        with _on(z0.device):
+            _check(lib().cnsn_jsd_bwd(_p(z0), _p(z1), _p(z2), _dtype_code(z0), B, K, _p(gout), _p(d[0]), _p(d[1]), _p(d[2]),
+                                      _stream(z0)))
+        return d
 
     # -- CrossNorm ------------------------------------------------------------------------
     def crossnorm_fwd(self, x, perm, chan_perm, cwin, swin, lam, eps):

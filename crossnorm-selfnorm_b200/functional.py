@@ -130,3 +130,19 @@ class CrossNormFn(torch.autograd.Function):
         cwin, swin, lam = ctx.meta
         dx = _lib.backend().crossnorm_bwd(x, _dense(dy), perm, chan_perm, cwin, swin, lam, save)
         return dx, None, None, None, None, None, None
+
+
+class JsdConsistencyFn(torch.autograd.Function):
+    """The Jensen-Shannon consistency term of the 3-view steps (imagenet.py:367-376, cifar.py:173-182)."""
+
+    @staticmethod
+    def forward(ctx, z0, z1, z2):
+        z0, z1, z2 = (_dense(z) for z in (z0, z1, z2))
+        ctx.save_for_backward(z0, z1, z2)
+        return _lib.backend().jsd_fwd(z0, z1, z2)
+
+    @staticmethod
+    def backward(ctx, gout):
+        z0, z1, z2 = ctx.saved_tensors
+        d = _lib.backend().jsd_bwd(z0, z1, z2, gout.contiguous().float())
+        return tuple(d)

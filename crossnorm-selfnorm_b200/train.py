@@ -171,6 +171,68 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
             "cnsn_kernel_launches": _lib.launch_count() - launches0}
 
 
+def resnet50_jsd_step(net, images_all, targets, opt, cn_prob, ops, jsd, beta=1, crop="neither", autocast=True):
+    """One ``train_cn_image_consist`` step of the reference's imagenet.py:348-385: the three views of the batch are
+    concatenated, a coin sends the whole 3B batch through image-space CrossNorm, one forward, cross-entropy on the
+    clean third plus 12 x the Jensen-Shannon consistency of the three thirds."""
+    if np.random.rand(1) < cn_prob:
+        images_all = ops.cn_op_2ins_space_chan(images_all, beta=beta, crop=crop)
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        logits_all = net(images_all, aug=False)
+    lc, l1, l2 = torch.split(logits_all, targets.size(0))
+    loss = F.cross_entropy(lc, targets) + 12 * jsd(lc, l1, l2)
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    return float(loss.detach())
+
+
+def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0.5, fuse_post=True):
+    """images/s (clean images: the step processes 3x as many views) of ResNet-50 + SelfNorm with the 3-view JSD
+    consistency step, bf16 autocast (BASELINE config 5: 3 x 256 = 768 views per GPU)."""
+    import torch.distributed as dist
+    from . import _lib, cnsn as ops
+    from .hosts.resnet import resnet50
+    from .losses import jsd_consistency
+    torch.manual_seed(1 + rank)
+    np.random.seed(1 + rank)
+    net = resnet50(fuse_post=fuse_post).to(dev).train()
+    model = net
+    if world > 1:
+        model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
+    opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
+    x = torch.randn(3 * batch, 3, 224, 224, device=dev)
+    y = torch.randint(0, 1000, (batch,), device=dev)
+    launches0 = _lib.launch_count()
+    for _ in range(warmup):
+        resnet50_jsd_step(model, x, y, opt, cn_prob, ops, jsd_consistency)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    loss = 0.0
+    for _ in range(steps):
+        loss = resnet50_jsd_step(model, x, y, opt, cn_prob, ops, jsd_consistency)
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"metric": "ResNet-50 + SelfNorm + JSD (3 views) training images/s", "value": world * batch * steps / (ms * 1e-3),
+            "unit": "clean images/s", "views_per_s": 3 * world * batch * steps / (ms * 1e-3), "ms_per_step": ms / steps,
+            "steps": steps, "warmup": warmup, "batch_per_gpu": batch, "views_per_gpu": 3 * batch, "n_gpus": world,
+            "dtype": "bf16 autocast (fp32 parameters, fp32 SelfNorm statistics)",
+            "config": "resnet50 cnsn_type=sn pos=post, image-space CrossNorm cn_prob=%g, CE + 12 x JSD (cnsn_jsd kernels), SGD lr "
+                      "0.1 momentum 0.9 wd 1e-4, synthetic 224x224, fuse_post=%s" % (cn_prob, bool(fuse_post)),
+            "final_loss": loss, "cnsn_kernel_launches": _lib.launch_count() - launches0,
+            "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
+
+
 def bench_resnet50_cpu(ops, batch=16, steps=1, warmup=1, cn_prob=0.5):
     """The same ResNet-50 step on the host cores with a caller-supplied operator set (the CPU reference arm of
     bench.py passes the eager-PyTorch restatement); a bounded sample of BASELINE config 4 (batch 16 of 256)."""

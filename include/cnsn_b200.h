@@ -188,6 +188,18 @@ int cnsn_crossnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
                        const int* content, const int* style,
                        float lam, const float* save, float* workspace, void* stream);
 
+/* ---------------------------------------------------------------- JSD consistency -----------
+ * The Jensen-Shannon consistency term of the 3-view steps, imagenet.py:367-376 / cifar.py:173-182:
+ *   p_v = softmax(logits_v); lm = log(clamp(mean_v p_v, 1e-7, 1));
+ *   loss = (kl_div(lm, p_clean) + kl_div(lm, p_aug1) + kl_div(lm, p_aug2)) / 3      (reduction 'batchmean')
+ * z0, z1, z2: (B, K) dense logits of the clean / aug1 / aug2 views (element type `dtype`); row_loss: B floats of
+ * scratch; loss: 1 float.  Backward: gout is a DEVICE scalar (d total / d loss); d0..d2 receive d loss / d logits.
+ */
+int cnsn_jsd_fwd(const void* z0, const void* z1, const void* z2, int dtype, int B, int K,
+                 float* row_loss, float* loss, void* stream);
+int cnsn_jsd_bwd(const void* z0, const void* z1, const void* z2, int dtype, int B, int K,
+                 const float* gout, void* d0, void* d1, void* d2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
