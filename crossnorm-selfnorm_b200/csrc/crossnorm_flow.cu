@@ -46,23 +46,6 @@ struct CNArgs {
     unsigned* ticket;       // starts at 0xffffffff
 };
 
-template <typename T> __device__ __forceinline__ float lds_elem(uint32_t base, int e);
-template <> __device__ __forceinline__ float lds_elem<float>(uint32_t base, int e) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * e));
-    return v;
-}
-template <> __device__ __forceinline__ float lds_elem<__nv_bfloat16>(uint32_t base, int e) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * e));
-    return __uint_as_float((unsigned)v << 16);
-}
-template <> __device__ __forceinline__ float lds_elem<__half>(uint32_t base, int e) {
-    unsigned short v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * e));
-    return __half2float(__ushort_as_half(v));
-}
-
 // sum over a window of f(x [, dy]) for one shared-memory-resident instance; the team's threads split the work.
 // full: 128-bit reads over the flat plane; else element reads over the window's rows.
 template <typename T, bool TWO, typename F>

@@ -97,6 +97,24 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return r;
 }
 
+// one element of a shared-memory-resident plane, as float
+template <typename T> __device__ __forceinline__ float lds_elem(uint32_t base, int e);
+template <> __device__ __forceinline__ float lds_elem<float>(uint32_t base, int e) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(base + 4u * e));
+    return v;
+}
+template <> __device__ __forceinline__ float lds_elem<__nv_bfloat16>(uint32_t base, int e) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * e));
+    return __uint_as_float((unsigned)v << 16);
+}
+template <> __device__ __forceinline__ float lds_elem<__half>(uint32_t base, int e) {
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(base + 2u * e));
+    return __half2float(__ushort_as_half(v));
+}
+
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }

@@ -57,6 +57,7 @@ struct FArgs {
     unsigned* ready;        // [C]    channel constants are in chan[c]
     unsigned* ticket;       // [1]
     int poll_ns;            // sleep between polls of ready[c]
+    int kk;                 // channel-group kernel: adjacent channels per group
     int pf_dist;            // resident kernel: L2-prefetch the item pf_dist tickets ahead (0 = off)
     unsigned items;         // resident kernel: total tickets
     unsigned long long* trace;   // debug only (CNSN_FLOW_TRACE): [items][8] globaltimer stamps, else NULL
@@ -362,6 +363,93 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
 // CTAs at once (checked on the host with the occupancy API) the lowest unfinished channel is always completely
 // resident, none of its CTAs waits before it has published, and it completes.  All N planes of a channel (and
 // the next few) live in shared memory across the GPU: N*M*sizeof(T)*tensors must fit a fraction of 148 x 227 KB.
+// The CTA holding a channel's last ticket: poll the channel's N published words (they stay in registers), fold
+// them, publish the channel constants as one 8-byte word at `flag`, write the per-channel outputs (forward:
+// running statistics, r; backward: dgamma, dbeta, dw).  Whole CTA of TH threads; returns the constants.
+template <bool BWD, int TH>
+__device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float2* flag, float p_w0, float p_w1, float p_ga,
+                                               float p_b, float p_rm, float p_rv, float (*s_f)[TH / 32]) {
+    constexpr int kHold = 4;                                 // published words a folding thread keeps in registers
+    const int N = a.N, C = a.C;
+    const float2* pb = a.pub + (size_t)c * N;
+    const float invN = 1.f / N;
+    float2 hold[kHold];
+#pragma unroll
+    for (int u = 0; u < kHold; ++u) {
+        const int k = threadIdx.x + u * TH;
+        hold[u] = make_float2(0.f, 0.f);
+        if (k < N) hold[u] = poll_word(pb + k, 100);
+    }
+    for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100);   // N > kHold*TH: re-read below
+    float v[2] = {0.f, 0.f};
+    float2 cst;
+    if (!BWD) {
+        float m = p_rm, q = p_rv;
+        if (a.training) {
+#pragma unroll
+            for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) v[0] += fmaf(p_w0, hold[u].x, p_w1 * hold[u].y);
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] += fmaf(p_w0, p.x, p_w1 * p.y); }
+            cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[0]), reinterpret_cast<float(*)[TH / 32]>(s_f[0]));
+            m = v[0] / N;
+            v[1] = 0.f;
+#pragma unroll
+            for (int u = 0; u < kHold; ++u)
+                if (threadIdx.x + u * TH < N) { const float d = fmaf(p_w0, hold[u].x, p_w1 * hold[u].y) - m; v[1] = fmaf(d, d, v[1]); }
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
+                const float2 p = fused::ll_peek(pb + k);
+                const float d = fmaf(p_w0, p.x, p_w1 * p.y) - m;
+                v[1] = fmaf(d, d, v[1]);
+            }
+            cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[1]), reinterpret_cast<float(*)[TH / 32]>(s_f[1]));
+            q = v[1] / N;                                // biased variance normalises (BatchNorm semantics)
+        }
+        // eval: thread 0 holds the running statistics; the other threads' m, q are unused
+        const float rstd = 1.f / sqrtf(q + a.bn_eps);
+        cst = make_float2(m, rstd);
+        if (threadIdx.x == 0) {
+            fused::ll_publish(flag, cst.x, cst.y);       // the channel is ready: 8 bytes, no fence
+                        a.r[c] = rstd;
+            if (a.training) {
+                a.run_mean[c] = (1.f - a.momentum) * p_rm + a.momentum * m;
+                a.run_var[c] = (1.f - a.momentum) * p_rv + a.momentum * (q * N / (N - 1.f));
+                if (a.nbt && c == 0) *a.nbt += 1;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) { v[0] = fmaf(hold[u].x, hold[u].y, v[0]); v[1] += hold[u].x; }
+        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
+        cta_sums<2, TH>(v, s_f);
+        const float dgam = v[0], dbet = v[1];
+        const float k1 = a.training ? p_ga * dbet * invN : 0.f, k2 = a.training ? p_ga * dgam * invN : 0.f;
+        cst = make_float2(k1, k2);
+        if (threadIdx.x == 0) {
+            fused::ll_publish(flag, cst.x, cst.y);
+                        a.dgamma[c] = dgam; a.dbeta[c] = dbet;
+        }
+        // off the critical path: dw = (sum ds*mu, sum ds*sd)
+        v[0] = v[1] = 0.f;
+#pragma unroll
+        for (int u = 0; u < kHold; ++u) {
+            const int k = threadIdx.x + u * TH;
+            if (k < N) {
+                const size_t i = (size_t)k * C + c;
+                const float ds = p_b * (hold[u].x * p_ga - k1 - hold[u].y * k2);
+                v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
+            }
+        }
+        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
+            const float2 p = fused::ll_peek(pb + k);
+            const size_t i = (size_t)k * C + c;
+            const float ds = p_b * (p.x * p_ga - k1 - p.y * k2);
+            v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
+        }
+        cta_sums<2, TH>(v, s_f);
+        if (threadIdx.x == 0) { a.dw[2 * c] = v[0]; a.dw[2 * c + 1] = v[1]; }
+    }
+    return cst;
+}
+
 // DYG (backward only): dy is NOT staged in shared memory -- it is streamed from global memory twice (reduce:
 // L2 hit thanks to the predecessor's prefetch, marked evict-last; apply: L2 hit, evict-first) while x stays
 // resident.  Twice the instances fit on chip, at 7 L2 transactions per byte of S instead of 6 (both planes
@@ -374,7 +462,6 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     constexpr int kB = 4;                                    // DYG: 128-bit loads of dy in flight per thread
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
-    constexpr int kHold = 4;                                 // published words a folding thread keeps in registers
     extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
     __shared__ unsigned s_word;
     __shared__ float2 s_chan;
@@ -549,85 +636,9 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             }
         }
     } else if (folder) {
-        const float2* pb = a.pub + (size_t)c * N;
-        const float invN = 1.f / N;
-        float2 hold[kHold];
-#pragma unroll
-        for (int u = 0; u < kHold; ++u) {
-            const int k = threadIdx.x + u * TH;
-            hold[u] = make_float2(0.f, 0.f);
-            if (k < N) hold[u] = poll_word(pb + k, 100);
-        }
-        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100);   // N > kHold*TH: re-read below
-        CNSN_FTRACE(3);                                      // 3 (folder) all words of the channel seen
-        float v[2] = {0.f, 0.f};
-        float2 cst;
-        if (!BWD) {
-            float m = p_rm, q = p_rv;
-            if (a.training) {
-#pragma unroll
-                for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) v[0] += fmaf(p_w0, hold[u].x, p_w1 * hold[u].y);
-                for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] += fmaf(p_w0, p.x, p_w1 * p.y); }
-                cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[0]), reinterpret_cast<float(*)[TH / 32]>(s_f[0]));
-                m = v[0] / N;
-                v[1] = 0.f;
-#pragma unroll
-                for (int u = 0; u < kHold; ++u)
-                    if (threadIdx.x + u * TH < N) { const float d = fmaf(p_w0, hold[u].x, p_w1 * hold[u].y) - m; v[1] = fmaf(d, d, v[1]); }
-                for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
-                    const float2 p = fused::ll_peek(pb + k);
-                    const float d = fmaf(p_w0, p.x, p_w1 * p.y) - m;
-                    v[1] = fmaf(d, d, v[1]);
-                }
-                cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[1]), reinterpret_cast<float(*)[TH / 32]>(s_f[1]));
-                q = v[1] / N;                                // biased variance normalises (BatchNorm semantics)
-            }
-            // eval: thread 0 holds the running statistics; the other threads' m, q are unused
-            const float rstd = 1.f / sqrtf(q + a.bn_eps);
-            cst = make_float2(m, rstd);
-            if (threadIdx.x == 0) {
-                fused::ll_publish(flag, cst.x, cst.y);       // the channel is ready: 8 bytes, no fence
-                s_chan = cst;
-                a.r[c] = rstd;
-                if (a.training) {
-                    a.run_mean[c] = (1.f - a.momentum) * p_rm + a.momentum * m;
-                    a.run_var[c] = (1.f - a.momentum) * p_rv + a.momentum * (q * N / (N - 1.f));
-                    if (a.nbt && c == 0) *a.nbt += 1;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) { v[0] = fmaf(hold[u].x, hold[u].y, v[0]); v[1] += hold[u].x; }
-            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
-            cta_sums<2, TH>(v, s_f);
-            const float dgam = v[0], dbet = v[1];
-            const float k1 = a.training ? p_ga * dbet * invN : 0.f, k2 = a.training ? p_ga * dgam * invN : 0.f;
-            cst = make_float2(k1, k2);
-            if (threadIdx.x == 0) {
-                fused::ll_publish(flag, cst.x, cst.y);
-                s_chan = cst;
-                a.dgamma[c] = dgam; a.dbeta[c] = dbet;
-            }
-            // off the critical path: dw = (sum ds*mu, sum ds*sd)
-            v[0] = v[1] = 0.f;
-#pragma unroll
-            for (int u = 0; u < kHold; ++u) {
-                const int k = threadIdx.x + u * TH;
-                if (k < N) {
-                    const size_t i = (size_t)k * C + c;
-                    const float ds = p_b * (hold[u].x * p_ga - k1 - hold[u].y * k2);
-                    v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
-                }
-            }
-            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
-                const float2 p = fused::ll_peek(pb + k);
-                const size_t i = (size_t)k * C + c;
-                const float ds = p_b * (p.x * p_ga - k1 - p.y * k2);
-                v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);
-            }
-            cta_sums<2, TH>(v, s_f);
-            if (threadIdx.x == 0) { a.dw[2 * c] = v[0]; a.dw[2 * c + 1] = v[1]; }
-        }
+        const float2 cst = fold_publish<BWD, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
+        CNSN_FTRACE(3);                                      // 3 (folder) channel folded
+        if (threadIdx.x == 0) s_chan = cst;
     } else if (threadIdx.x == 0) {
         s_chan = poll_word(flag, a.poll_ns);
     }
@@ -692,6 +703,182 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         }
     }
     CNSN_FTRACE(5);                                          // 5 applied
+}
+
+// =============================================================================================
+// Channel-group variant of the shared-memory-resident kernel, for planes that are NOT a multiple of 16 bytes
+// (7x7 fp32 = 196 B, 14x14 bf16 = 392 B, 7x7 bf16 = 98 B: the last two stages of ResNet-50).  kk adjacent
+// channels of one sample are contiguous in NCHW and kk*M*sizeof(T) IS a multiple of 16 for some kk in {2,4,8}:
+// that run (a "super-plane") is what TMA fetches and what the apply phase streams out with 128-bit accesses,
+// looking up each element's channel in a per-instance coefficient table; the per-instance reductions read
+// shared memory element-wise.  An item = I samples x kk channels = 128 / TPI instances (TPI = 1, 2 or 4 threads
+// each, chosen so that an item is ~12-25 KB); tickets are group-major; the group's kk channels are folded by its
+// last kk tickets, one channel each (every CTA of the group is co-resident, see above).
+constexpr int kGrpT = 128;
+
+template <typename T, bool BWD, bool ADD, int TPI>
+__global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
+    static_assert(!(BWD && ADD), "the fused add is a forward feature");
+    constexpr int TH = kGrpT, P = kGrpT / TPI;
+    constexpr int V = VecOf<T>::n;
+    constexpr bool two = BWD || ADD;
+    extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I super-planes of x | I of dy / res]
+    __shared__ unsigned s_word;
+    __shared__ float4 s_coef[P];                             // per instance: out = .x*dy + .y*x + .z
+    __shared__ float s_f[2][TH / 32];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
+    if (threadIdx.x == 0) {
+        fused::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;
+    }
+    __syncthreads();
+    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned g = t / nI, j = t - g * nI;
+    const int N = a.N, C = a.C, M = a.M, kk = a.kk, I = P / kk;
+    const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T), sp = (unsigned)kk * pbytes;
+    const int first = (int)j * I, nlive = min(I, N - first);
+    const uint32_t sbase = smem_u32(dsm) + 128u;
+    const uint32_t soff2 = (unsigned)I * sp;                 // second tensor's region
+    if (threadIdx.x < 32) {                                  // lane q fetches sample q's run of kk planes
+        const uint64_t pol = l2_policy_evict_first();
+        const T* second = static_cast<const T*>(BWD ? a.dy : a.res);
+        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * sp * (two ? 2u : 1u));
+        __syncwarp();
+        for (int q = threadIdx.x; q < nlive; q += 32) {
+            const size_t off = ((size_t)(first + q) * C + (size_t)g * kk) * M;
+            unsigned char* dst = dsm + 128 + (size_t)q * sp;
+            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, sp, bar, pol);
+            if (two) fused::tma_load_1d(dst + soff2, second + off, sp, bar, pol);
+        }
+        const unsigned tf = t + (unsigned)a.pf_dist;
+        if (a.pf_dist && tf < a.items) {
+            const unsigned gf = tf / nI, jf = tf - gf * nI;
+            const int ff = (int)jf * I, nf = min(I, N - ff);
+            for (int q = threadIdx.x; q < nf; q += 32) {
+                const size_t off = ((size_t)(ff + q) * C + (size_t)gf * kk) * M;
+                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, sp);
+                if (two) fused::tma_prefetch_l2(second + off, sp);
+            }
+        }
+    }
+    // this team's instance
+    const int team = threadIdx.x / TPI, r = threadIdx.x % TPI;
+    const int q = team / kk, cl = team - q * kk;
+    const int n = first + q;
+    const bool live = q < nlive;
+    const unsigned c = g * (unsigned)kk + (unsigned)cl;
+    const size_t nc = (size_t)(live ? n : 0) * C + c;
+    const uint32_t sx = sbase + (unsigned)q * sp + (unsigned)cl * pbytes;
+    const uint32_t sdy = sx + soff2;
+    const bool folder = j == nI - 1;
+    const bool relu = a.relu != 0;
+    const bool batch_coupled = a.training != 0;
+    float pre_g = 0.f, pre_s = 0.f, p_w0, p_w1, p_ga, p_b, p_mu = 0.f, p_sd = 1.f;
+    p_w0 = a.w[2 * c]; p_w1 = a.w[2 * c + 1]; p_ga = a.gamma[c];
+    if (BWD) {
+        p_b = a.r[c];
+        if (live) { pre_g = a.gate[nc]; pre_s = a.shat[nc]; p_mu = a.mu[nc]; p_sd = a.sd[nc]; }
+    } else {
+        p_b = a.beta[c];
+    }
+    fused::mbar_wait(bar, 0);
+    const int vps = (int)(sp / 16u), nvec = nlive * vps;     // 128-bit vectors per super-plane / in the item
+    if (ADD) {                                               // z = x + res over the item, in place and written out
+        for (int vi = threadIdx.x; vi < nvec; vi += TH) {
+            float vx[V], vr[V];
+            unpack<T>(lds128(sbase + 16u * vi), vx);
+            unpack<T>(lds128(sbase + soff2 + 16u * vi), vr);
+#pragma unroll
+            for (int e = 0; e < V; ++e) vx[e] += vr[e];
+            const uint4 z = pack<T>(vx);
+            sts128(sbase + 16u * vi, z);
+            const int qv = vi / vps, w = vi - qv * vps;
+            uint4* pz = reinterpret_cast<uint4*>(static_cast<T*>(a.zout) + ((size_t)(first + qv) * C + (size_t)g * kk) * M) + w;
+            stg_stream(pz, z);
+        }
+        __syncthreads();
+    }
+    // ---- per-instance reduction, element-wise out of shared memory ---------------------------------
+    float own_x = 0.f, own_y = 0.f;
+    if (BWD) {
+        float s0 = 0.f;
+        if (live)
+            for (int e = r; e < M; e += TPI) {
+                const float x = lds_elem<T>(sx, e);
+                const float d = (relu && !(x > 0.f)) ? 0.f : lds_elem<T>(sdy, e);
+                s0 = fmaf(d, x, s0);
+            }
+        const float sxy = team_sum<TPI>(s0, s_f[0]);
+        own_x = sxy * pre_g * (1.f - pre_g); own_y = pre_s;
+    } else {
+        float s0 = 0.f;
+        if (live) for (int e = r; e < M; e += TPI) s0 += lds_elem<T>(sx, e);
+        const float mean = team_sum<TPI>(s0, s_f[0]) * (1.f / M);
+        s0 = 0.f;
+        if (live) for (int e = r; e < M; e += TPI) { const float d = lds_elem<T>(sx, e) - mean; s0 = fmaf(d, d, s0); }
+        const float m2 = team_sum<TPI>(s0, s_f[1]);
+        own_x = mean; own_y = sqrtf(m2 / (M - 1.f) + a.eps);
+        if (live && r == 0) { a.mu[nc] = own_x; a.sd[nc] = own_y; }
+    }
+    if (live && r == 0 && (BWD || batch_coupled)) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    // ---- channel constants ------------------------------------------------------------------------
+    if (BWD || batch_coupled) {                              // channel k of the group: folded by ticket nI-1-(k mod nI)
+        for (int k = (int)(nI - 1u - j); k < kk; k += (int)nI) {
+            const unsigned ch = g * (unsigned)kk + (unsigned)k;
+            const float w0 = a.w[2 * ch], w1 = a.w[2 * ch + 1], ga = a.gamma[ch];
+            const float pb2 = BWD ? a.r[ch] : 0.f;
+            float rm = 0.f, rv = 1.f;
+            if (!BWD && threadIdx.x == 0) { rm = a.run_mean[ch]; rv = a.run_var[ch]; }
+            fold_publish<BWD, TH>(a, ch, a.chan + 4u * ch, w0, w1, ga, pb2, rm, rv, s_f);
+        }
+    }
+    float2 cm;
+    if (batch_coupled) {
+        cm = poll_word(a.chan + 4u * c, a.poll_ns);          // 4 lanes per address; the folder's own words are there
+    } else if (BWD) {
+        cm = make_float2(0.f, 0.f);
+    } else {
+        const float rstd = 1.f / sqrtf(a.run_var[c] + a.bn_eps);
+        cm = make_float2(a.run_mean[c], rstd);
+        if (folder && q == 0 && r == 0) a.r[c] = rstd;
+    }
+    if (live && r == 0) {
+        if (BWD) {
+            const float ds = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
+            const float cb = ds * p_w1 * (1.f / (M - 1.f)) / p_sd;
+            s_coef[team] = make_float4(pre_g, cb, ds * p_w0 * (1.f / M) - cb * p_mu, 0.f);
+        } else {
+            const float sh = (fmaf(p_w0, own_x, p_w1 * own_y) - cm.x) * cm.y;
+            const float gt = 1.f / (1.f + expf(-fmaf(p_ga, sh, p_b)));
+            a.gate[nc] = gt; a.shat[nc] = sh;
+            s_coef[team] = make_float4(0.f, gt, 0.f, 0.f);
+        }
+    }
+    __syncthreads();
+    // ---- apply: the item's super-planes as flat 128-bit vectors ------------------------------------------
+    for (int vi = threadIdx.x; vi < nvec; vi += TH) {
+        const int qv = vi / vps, w = vi - qv * vps;
+        const int e0 = w * V, cl0 = e0 / M, bound = (cl0 + 1) * M;
+        const float4 k0 = s_coef[qv * kk + cl0];
+        const float4 k1 = (cl0 + 1 < kk) ? s_coef[qv * kk + cl0 + 1] : k0;     // a vector spans at most two planes (M >= V)
+        float vx[V], vd[V], vo[V];
+        unpack<T>(lds128(sbase + 16u * vi), vx);
+        if (BWD) unpack<T>(lds128(sbase + soff2 + 16u * vi), vd);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float4 k = (e0 + e < bound) ? k0 : k1;
+            if (BWD) {
+                const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                vo[e] = fmaf(k.x, d, fmaf(k.y, vx[e], k.z));
+            } else {
+                const float y = fmaf(k.y, vx[e], 0.f);
+                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            }
+        }
+        uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + ((size_t)(first + qv) * C + (size_t)g * kk) * M) + w;
+        stg_stream(po, pack<T>(vo));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -837,6 +1024,58 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     return launch_status();
 }
 
+
+// Channel-group path for planes that are not a multiple of 16 bytes.  Returns -100 when it does not apply.
+template <bool BWD>
+static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
+    const int N = a.N, C = a.C;
+    const int esz = (int)esize(dtype);
+    const size_t pb = (size_t)a.M * esz;
+    if (pb % 16 == 0 || N < 1 || C < 1 || a.M < 16 / esz * 2) return -100;
+    int kk = 0;
+    for (int k = 2; k <= 8; k <<= 1) if ((k * pb) % 16 == 0 && C % k == 0) { kk = k; break; }
+    if (!kk) return -100;
+    const bool add = !BWD && a.res != nullptr;
+    const size_t ib = pb * ((BWD || add) ? 2 : 1);               // bytes per instance in shared memory
+    const int tpi = (32 * ib >= 12288 || kk > 32) ? 4 : (64 * ib >= 12288 || kk > 64) ? 2 : 1;
+    const int I = (kGrpT / tpi) / kk;
+    if (I < 1) return -100;
+    const size_t dsmem = 128 + (size_t)I * kk * ib;
+    const DeviceShape ds = device_shape();
+    if (dsmem > (size_t)ds.smem_optin / 2) return -100;
+    a.kk = kk;
+    a.nI = (N + I - 1) / I;
+    a.D = 0;
+    a.order = env_int("CNSN_FLOW_ORDER", 0);
+    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    const unsigned long long items = (unsigned long long)(C / kk) * a.nI;
+    if (items > 0x7fffffffull) return -100;
+    a.items = (unsigned)items;
+    a.pub = reinterpret_cast<float2*>(scratch);
+    a.chan = a.pub + (size_t)N * C;
+    a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
+    a.done = nullptr; a.ready = nullptr; a.trace = nullptr;
+    const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
+    cudaError_t e = cudaSuccess;
+    int per_sm = 0;
+    CNSN_DISPATCH_DTYPE(dtype, T, {
+        auto fn = tpi == 4 ? (add ? k_sn_grp<T, false, !BWD, 4> : k_sn_grp<T, BWD, false, 4>)
+                : tpi == 2 ? (add ? k_sn_grp<T, false, !BWD, 2> : k_sn_grp<T, BWD, false, 2>)
+                           : (add ? k_sn_grp<T, false, !BWD, 1> : k_sn_grp<T, BWD, false, 1>);
+        e = prepare_kernel(fn, kGrpT, dsmem, &per_sm);
+        if (e != cudaSuccess) return (int)e;
+        if ((long long)per_sm * ds.sms < 2ll * a.nI) return -100;
+        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);
+        e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
+        if (e != cudaSuccess) return (int)e;
+        fn<<<dim3((unsigned)items), dim3(kGrpT), dsmem, stream>>>(a);
+    });
+    if (getenv("CNSN_FLOW_DEBUG"))
+        fprintf(stderr, "[cnsn flow/grp] %s kk=%d tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d add=%d\n", BWD ? "bwd" : "fwd", kk,
+                tpi, I, a.nI, items, dsmem, per_sm, (int)add);
+    return launch_status();
+}
+
 // Which kernel: the shared-memory-resident one when a channel (all N planes, x [and dy]) is a small enough part
 // of the GPU's shared memory -- measured cross-over on B200 (profiles/README.md): 1/8 of 148 x 200 KB forward,
 // 1/16 backward (the L2-resident backward is the stronger alternative).  CNSN_FLOW_MODE=res|l2 forces one.
@@ -857,9 +1096,11 @@ int selfnorm_flow_fwd(const void* x, const void* res, void* z, void* y, int relu
     FArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W;
     a.res = res; a.zout = res ? z : nullptr; a.relu = relu;
+    const bool odd = ((size_t)H * W * esize(dtype)) % 16 != 0;
     a.training = training; a.momentum = momentum; a.bn_eps = bn_eps; a.eps = eps;
     a.w = g->w; a.gamma = g->gamma; a.beta = g->beta; a.run_mean = g->run_mean; a.run_var = g->run_var; a.nbt = g->nbt;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
+    if (odd) return launch_grp<false>(a, dtype, scratch, stream);
     if (use_resident((size_t)N * H * W * esize(dtype) * (res ? 2 : 1), false)) {
         const int rc = launch_res<false>(a, dtype, scratch, stream);
         if (rc != -100) return rc;
@@ -884,6 +1125,7 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
     // 0.511 at the north-star shape: two more L2 round trips per item outweigh the doubled capacity); it stays
     // selectable.  CNSN_FLOW_BWD=res|dyg|l2 forces one (A/B measurements).
     const size_t chan_x = (size_t)N * H * W * esize(dtype);
+    if ((((size_t)H * W * esize(dtype)) % 16) != 0) return launch_grp<true>(a, dtype, scratch, stream);
     int mode = use_resident(2 * chan_x, true) ? 0 : 2;
     if (const char* e = getenv("CNSN_FLOW_BWD")) mode = e[0] == 'r' ? 0 : e[0] == 'd' ? 1 : 2;
     else if (const char* m = getenv("CNSN_FLOW_MODE")) mode = m[0] == 'r' ? 0 : 2;

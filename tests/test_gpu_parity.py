@@ -156,7 +156,7 @@ def test_selfnorm_batch1_raises(mod):
 # ------------------------------------------------------------------ fused block: add + SelfNorm + ReLU
 BLOCK_SHAPES = [((16, 8, 8, 8), torch.float32), ((64, 12, 28, 28), torch.float32), ((256, 8, 56, 56), torch.float32),
                 ((96, 40, 7, 7), torch.float32), ((64, 16, 14, 14), torch.bfloat16), ((256, 12, 56, 56), torch.bfloat16),
-                ((5, 3, 9, 14), torch.float32)]
+                ((5, 3, 9, 14), torch.float32), ((48, 16, 7, 7), torch.bfloat16), ((19, 8, 7, 7), torch.float32)]
 
 
 @pytest.mark.parametrize("shape,dtype", BLOCK_SHAPES)
@@ -334,7 +334,8 @@ def test_selfnorm_north_star_shape_properties(mod, impl, monkeypatch):
 # ------------------------------------------------------------------ fused persistent kernel (tensors >= 8 MB)
 FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.float32), ((256, 64, 14, 14), torch.float32),
                 ((256, 256, 7, 7), torch.float32), ((512, 32, 16, 16), torch.float32), ((96, 24, 28, 28), torch.float32),
-                ((256, 16, 56, 56), torch.bfloat16), ((300, 20, 20, 20), torch.float32), ((40, 6, 224, 224), torch.float32)]
+                ((256, 16, 56, 56), torch.bfloat16), ((300, 20, 20, 20), torch.float32), ((40, 6, 224, 224), torch.float32),
+                ((64, 16, 14, 14), torch.bfloat16), ((40, 24, 7, 7), torch.bfloat16), ((37, 12, 7, 7), torch.float32)]
 
 
 @pytest.mark.parametrize("shape,dtype", FUSED_SHAPES)
