@@ -30,6 +30,11 @@ class GateGrads(Structure):        # struct cnsn_gate_grads
     _fields_ = [("dw", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p)]
 
 
+class IbnParams(Structure):        # struct cnsn_ibn_params
+    _fields_ = [("in_w", c_void_p), ("in_b", c_void_p), ("bn_w", c_void_p), ("bn_b", c_void_p),
+                ("run_mean", c_void_p), ("run_var", c_void_p), ("nbt", c_void_p)]
+
+
 _I4 = c_int * 4
 _DIMS = [c_int, c_int, c_int, c_int]
 
@@ -55,6 +60,12 @@ SIGNATURES = {
                                         c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "cnsn_selfnorm_block_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
                                         c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
+    "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_ibn_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_float, c_float, c_float,
+                             c_void_p, c_void_p]),
+    "cnsn_ibn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
@@ -297,6 +308,45 @@ class CudaBackend:
                                                  ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg),
                                                  _p(ws), _stream(z)))
         return dz, out_g
+
+    # -- IBN ----------------------------------------------------------------------------------
+    @staticmethod
+    def _ibn_struct(p, keep):
+        vals = []
+        for name in ("in_w", "in_b", "bn_w", "bn_b", "run_mean", "run_var"):
+            t = p.get(name)
+            t = _f32(t) if t is not None else None
+            keep.append(t)
+            vals.append(_p(t).value)
+        vals.append(_p(p.get("nbt")).value)
+        return IbnParams(*vals)
+
+    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        keep = []
+        ps = self._ibn_struct(p, keep)
+        save = torch.empty(lib().cnsn_ibn_save_floats(N, C, half), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        with _on(x.device):
+            _check(lib().cnsn_ibn_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
+                                      momentum, eps_in, eps_bn, _p(save), _stream(x)))
+        return y, save
+
+    def ibn_bwd(self, x, dy, half, p, training, save):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        keep = []
+        ps = self._ibn_struct(p, keep)
+        dev = x.device
+        g = torch.empty(2 * C, dtype=torch.float32, device=dev)
+        d_in_w, d_in_b, d_bn_w, d_bn_b = g[:half], g[half:2 * half], g[2 * half:C + half], g[C + half:]
+        ws = torch.empty(lib().cnsn_ibn_workspace_floats(N, C), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        with _on(dev):
+            _check(lib().cnsn_ibn_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
+                                      _p(save), _p(d_in_w), _p(d_in_b), _p(d_bn_w), _p(d_bn_b), _p(ws), _stream(x)))
+        return dx, (d_in_w, d_in_b, d_bn_w, d_bn_b)
 
     # -- JSD consistency --------------------------------------------------------------------
     def jsd_fwd(self, z0, z1, z2):

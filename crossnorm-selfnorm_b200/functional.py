@@ -146,3 +146,24 @@ class JsdConsistencyFn(torch.autograd.Function):
         z0, z1, z2 = ctx.saved_tensors
         d = _lib.backend().jsd_bwd(z0, z1, z2, gout.contiguous().float())
         return tuple(d)
+
+
+class IbnFn(torch.autograd.Function):
+    """IBN.forward (models/imagenet/resnet_ibn_cnsn.py:38-44) and its backward, one kernel each."""
+
+    @staticmethod
+    def forward(ctx, x, half, training, momentum, eps_in, eps_bn, bufs, in_w, in_b, bn_w, bn_b):
+        x = _dense(x)
+        p = {"in_w": in_w, "in_b": in_b, "bn_w": bn_w, "bn_b": bn_b, "run_mean": bufs[0], "run_var": bufs[1], "nbt": bufs[2]}
+        y, save = _lib.backend().ibn_fwd(x, half, p, training, momentum, eps_in, eps_bn)
+        ctx.save_for_backward(x, in_w, bn_w)
+        ctx.ibn = (half, training, save)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, in_w, bn_w = ctx.saved_tensors
+        half, training, save = ctx.ibn
+        dx, g = _lib.backend().ibn_bwd(x, _dense(dy), half, {"in_w": in_w, "bn_w": bn_w}, training, save)
+        return (dx, None, None, None, None, None, None,
+                g[0].to(in_w.dtype), g[1].to(in_w.dtype), g[2].to(bn_w.dtype), g[3].to(bn_w.dtype))

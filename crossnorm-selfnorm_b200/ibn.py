@@ -1,0 +1,29 @@
+"""Instance-Batch Normalization with the reference's module surface.
+
+``IBN`` mirrors the class of ``models/imagenet/resnet_ibn_cnsn.py:24-44``: sub-modules ``IN``
+(``nn.InstanceNorm2d(half, affine=True)``) and ``BN`` (``nn.BatchNorm2d(planes - half)``) hold the parameters and
+buffers, so ``state_dict()`` keys match (``...bn1.IN.weight``, ``...bn1.BN.running_mean`` ...) and the IBN-Net /
+reference checkpoints load; the sub-modules are never called -- one CUDA kernel per direction handles both halves in
+place, without the reference's split / contiguous / cat copies.
+"""
+import torch.nn as nn
+
+from .functional import IbnFn
+
+__all__ = ["IBN"]
+
+
+class IBN(nn.Module):
+    def __init__(self, planes, ratio=0.5):
+        super().__init__()
+        self.half = int(planes * ratio)
+        self.IN = nn.InstanceNorm2d(self.half, affine=True)
+        self.BN = nn.BatchNorm2d(planes - self.half)
+
+    def forward(self, x):
+        assert x.dim() == 4
+        bn = self.BN
+        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        return IbnFn.apply(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps),
+                           (bn.running_mean, bn.running_var, bn.num_batches_tracked),
+                           self.IN.weight, self.IN.bias, bn.weight, bn.bias)

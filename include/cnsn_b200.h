@@ -188,6 +188,36 @@ int cnsn_crossnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
                        const int* content, const int* style,
                        float lam, const float* save, float* workspace, void* stream);
 
+/* ---------------------------------------------------------------- IBN ---------------------
+ * Instance-Batch Normalization, the IBN layer of models/imagenet/resnet_ibn_cnsn.py:24-44 (split along channels,
+ * nn.InstanceNorm2d(half, affine=True) on the first `half` channels, nn.BatchNorm2d(C - half) on the rest,
+ * concatenate), as one kernel per direction with no split / cat copies:
+ *   c <  half : y = (x - mean_nc) / sqrt(biased_var_nc + eps_in) * in_w[c] + in_b[c]          (always instance statistics)
+ *   c >= half : y = (x - m_c) / sqrt(v_c + eps_bn) * bn_w[c-half] + bn_b[c-half]; training: batch statistics over
+ *               (N,H,W), running_mean / running_var (unbiased) updated with `momentum`, nbt incremented; eval: running.
+ * Planes must be multiples of 16 bytes (CNSN_E_BADARG otherwise).  save: cnsn_ibn_save_floats() floats, written by
+ * forward, read by backward; workspace: cnsn_ibn_workspace_floats().  Parameter gradients are WRITTEN.
+ */
+typedef struct cnsn_ibn_params {
+    const float* in_w;     /* (half)     IN.weight */
+    const float* in_b;     /* (half)     IN.bias */
+    const float* bn_w;     /* (C - half) BN.weight */
+    const float* bn_b;     /* (C - half) BN.bias */
+    float* run_mean;       /* (C - half) BN.running_mean */
+    float* run_var;        /* (C - half) BN.running_var */
+    long long* nbt;        /* BN.num_batches_tracked or NULL */
+} cnsn_ibn_params;
+
+size_t cnsn_ibn_save_floats(int N, int C, int half);
+size_t cnsn_ibn_workspace_floats(int N, int C);
+int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, int half,
+                 const cnsn_ibn_params* p, int training, float momentum, float eps_in, float eps_bn,
+                 float* save, void* stream);
+int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W, int half,
+                 const cnsn_ibn_params* p, int training, const float* save,
+                 float* d_in_w, float* d_in_b, float* d_bn_w, float* d_bn_b,
+                 float* workspace, void* stream);
+
 /* ---------------------------------------------------------------- JSD consistency -----------
  * The Jensen-Shannon consistency term of the 3-view steps, imagenet.py:367-376 / cifar.py:173-182:
  *   p_v = softmax(logits_v); lm = log(clamp(mean_v p_v, 1e-7, 1));

@@ -1,0 +1,99 @@
+"""IBN layer: oracle vs the reference's module composition executed with PyTorch (CPU), kernel vs oracle (GPU),
+state-dict compatibility with the reference class."""
+import numpy as np
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import ibn_oracle as B
+
+
+class ReferenceIBN(nn.Module):
+    """The composition of models/imagenet/resnet_ibn_cnsn.py:24-44 (behavioural restatement for the pin)."""
+
+    def __init__(self, planes, ratio=0.5):
+        super().__init__()
+        self.half = int(planes * ratio)
+        self.IN = nn.InstanceNorm2d(self.half, affine=True)
+        self.BN = nn.BatchNorm2d(planes - self.half)
+
+    def forward(self, x):
+        a, b = torch.split(x, self.half, 1)
+        return torch.cat((self.IN(a.contiguous()), self.BN(b.contiguous())), 1)
+
+
+def _case(shape, seed):
+    rs = np.random.RandomState(seed)
+    N, C, H, W = shape
+    half = C // 2
+    x = rs.standard_normal(shape) * (0.5 + rs.rand(N, C, 1, 1)) + rs.standard_normal((N, C, 1, 1))
+    dy = rs.standard_normal(shape)
+    p = {"in_w": rs.uniform(0.5, 1.5, half), "in_b": rs.uniform(-0.5, 0.5, half),
+         "bn_w": rs.uniform(0.5, 1.5, C - half), "bn_b": rs.uniform(-0.5, 0.5, C - half)}
+    bufs = {"rm": rs.uniform(-1, 1, C - half), "rv": rs.uniform(0.5, 2, C - half)}
+    return x, dy, half, p, bufs
+
+
+def _load(m, p, bufs):
+    with torch.no_grad():
+        m.IN.weight.copy_(torch.from_numpy(p["in_w"])); m.IN.bias.copy_(torch.from_numpy(p["in_b"]))
+        m.BN.weight.copy_(torch.from_numpy(p["bn_w"])); m.BN.bias.copy_(torch.from_numpy(p["bn_b"]))
+        m.BN.running_mean.copy_(torch.from_numpy(bufs["rm"])); m.BN.running_var.copy_(torch.from_numpy(bufs["rv"]))
+    return m
+
+
+@pytest.mark.parametrize("shape", [(4, 6, 5, 5), (3, 8, 4, 6), (2, 2, 3, 3)])
+@pytest.mark.parametrize("training", [True, False])
+def test_oracle_matches_reference_composition(shape, training):
+    x, dy, half, p, bufs = _case(shape, sum(shape))
+    m = _load(ReferenceIBN(shape[1]).double(), p, bufs).train(training)
+    xt = torch.from_numpy(x).requires_grad_(True)
+    y = m(xt)
+    y.backward(torch.from_numpy(dy))
+    yo, rm, rv = B.ibn_fwd(x, half, p, bufs, training)
+    dxo, giw, gib, gbw, gbb = B.ibn_bwd(x, dy, half, p, bufs, training)
+    assert np.allclose(y.detach().numpy(), yo, atol=1e-11)
+    assert np.allclose(xt.grad.numpy(), dxo, atol=1e-10)
+    for a, b in ((m.IN.weight.grad, giw), (m.IN.bias.grad, gib), (m.BN.weight.grad, gbw), (m.BN.bias.grad, gbb)):
+        assert np.allclose(a.numpy(), b, atol=1e-9)
+    assert np.allclose(m.BN.running_mean.numpy(), rm, atol=1e-12) and np.allclose(m.BN.running_var.numpy(), rv, atol=1e-12)
+
+
+def test_ibn_state_dict_matches_reference_class():
+    from cnsn_b200.ibn import IBN
+    torch.manual_seed(0)
+    a = ReferenceIBN(64)
+    torch.manual_seed(0)
+    b = IBN(64)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb) and all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((8, 16, 8, 8), torch.float32), ((64, 32, 28, 28), torch.float32),
+                                         ((256, 8, 56, 56), torch.float32), ((33, 10, 12, 12), torch.float32),
+                                         ((600, 6, 4, 4), torch.float32), ((64, 16, 16, 16), torch.bfloat16)])
+@pytest.mark.parametrize("training", [True, False])
+def test_ibn_kernel_vs_oracle(shape, dtype, training):
+    from cnsn_b200.ibn import IBN
+    x, dy, half, p, bufs = _case(shape, sum(shape) + 1)
+    if dtype != torch.float32:
+        x, dy = (torch.from_numpy(v).to(dtype).double().numpy() for v in (x, dy))
+    m = _load(IBN(shape[1]), {k: v.astype(np.float32) for k, v in p.items()}, {k: v.astype(np.float32) for k, v in bufs.items()})
+    m = m.cuda().train(training)
+    xt = torch.from_numpy(x).to(device="cuda", dtype=dtype).requires_grad_(True)
+    y = m(xt)
+    y.backward(torch.from_numpy(dy).to(device="cuda", dtype=dtype))
+    p32 = {k: v.astype(np.float32).astype(np.float64) for k, v in p.items()}
+    b32 = {k: v.astype(np.float32).astype(np.float64) for k, v in bufs.items()}
+    yo, rm, rv = B.ibn_fwd(x, half, p32, b32, training)
+    dxo, giw, gib, gbw, gbb = B.ibn_bwd(x, dy, half, p32, b32, training)
+    atol, rtol = (1e-5, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    assert np.allclose(y.detach().double().cpu().numpy(), yo, atol=atol, rtol=rtol)
+    assert np.allclose(xt.grad.double().cpu().numpy(), dxo, atol=atol, rtol=rtol)
+    ptol = 1e-5 if dtype == torch.float32 else 1e-3
+    for a, b in ((m.IN.weight.grad, giw), (m.IN.bias.grad, gib), (m.BN.weight.grad, gbw), (m.BN.bias.grad, gbb)):
+        assert np.abs(a.double().cpu().numpy() - b).max() <= ptol * max(np.abs(b).max(), 1e-6)
+    assert np.allclose(m.BN.running_mean.double().cpu().numpy(), rm, atol=1e-5)
+    assert np.allclose(m.BN.running_var.double().cpu().numpy(), rv, atol=1e-5, rtol=1e-5)
+    assert int(m.BN.num_batches_tracked) == (1 if training else 0)
