@@ -27,11 +27,17 @@ def _default_ops():
 class Bottleneck(nn.Module):
     """1x1 reduce, 3x3 (carries the stride), 1x1 expand, additive shortcut, ReLU; one optional CNSN site."""
 
-    def __init__(self, cin, planes, stride, shortcut, pos, beta, crop, cnsn_type, ops, fuse_post):
+    def __init__(self, cin, planes, stride, shortcut, pos, beta, crop, cnsn_type, ops, fuse_post, ibn=None, ibn_host=False):
         super().__init__()
+        assert ibn in (None, "a"), "IBN-b (instance norm after the residual add) is not built"
         cout = planes * _EXPANSION
+        self.ibn_variant = bool(ibn_host)                # wiring of resnet_ibn_cnsn.py (every block of that host)
         self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
-        self.bn1 = nn.BatchNorm2d(planes)
+        if ibn == "a":                                   # models/imagenet/resnet_ibn_cnsn.py:53-56
+            from ..ibn import IBN
+            self.bn1 = IBN(planes)
+        else:
+            self.bn1 = nn.BatchNorm2d(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
         self.bn2 = nn.BatchNorm2d(planes)
         self.conv3 = nn.Conv2d(planes, cout, 1, bias=False)
@@ -50,6 +56,8 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         h = self.cnsn(x) if self.pos == "pre" else x
+        if self.ibn_variant and self.pos == "pre" and self.downsample is not None:
+            x = h                                        # the IBN host feeds the projection from the site's output (:98-99,:112-113)
         h = self.relu(self.bn1(self.conv1(h)))
         h = self.relu(self.bn2(self.conv2(h)))
         h = self.bn3(self.conv3(h))
@@ -68,14 +76,15 @@ class Bottleneck(nn.Module):
 
 class ResNet(nn.Module):
     def __init__(self, layers, num_classes=1000, active_num=1, pos=None, beta=None, crop=None, cnsn_type=None,
-                 ops=None, fuse_post=False, zero_init_residual=False):
+                 ops=None, fuse_post=False, zero_init_residual=False, ibn_cfg=(None, None, None, None)):
         super().__init__()
         ops = ops or _default_ops()
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
-        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post)
+        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post,
+                  ibn_host=any(v is not None for v in ibn_cfg))
         width = 64
         stages = []
         for i, (planes, count) in enumerate(zip((64, 128, 256, 512), layers)):
@@ -87,7 +96,7 @@ class ResNet(nn.Module):
                 if b == 0 and (s != 1 or width != planes * _EXPANSION):
                     shortcut = nn.Sequential(nn.Conv2d(width, planes * _EXPANSION, 1, s, bias=False),
                                              nn.BatchNorm2d(planes * _EXPANSION))
-                blocks.append(Bottleneck(width, planes, s, shortcut, **kw))
+                blocks.append(Bottleneck(width, planes, s, shortcut, ibn=ibn_cfg[i], **kw))
                 width = planes * _EXPANSION
             stages.append(nn.Sequential(*blocks))
         self.layer1, self.layer2, self.layer3, self.layer4 = stages
@@ -98,7 +107,7 @@ class ResNet(nn.Module):
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
-            elif isinstance(m, nn.BatchNorm2d):
+            elif isinstance(m, (nn.BatchNorm2d, nn.InstanceNorm2d)):
                 nn.init.constant_(m.weight, 1)
                 nn.init.constant_(m.bias, 0)
             elif isinstance(m, ops.CrossNorm):
@@ -128,3 +137,9 @@ class ResNet(nn.Module):
 def resnet50(active_num=1, pos="post", beta=1, crop="neither", cnsn_type="sn", **kw):
     """ResNet-50 + CNSN; the defaults are imagenet-scripts/run-cnsn.sh's model flags (SelfNorm at 'post')."""
     return ResNet([3, 4, 6, 3], active_num=active_num, pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, **kw)
+
+
+def resnet50_ibn_a(active_num=1, pos="post", beta=1, crop="neither", cnsn_type="sn", **kw):
+    """ResNet-50-IBN-a + CNSN (models/imagenet/resnet_ibn_cnsn.py:262-275): IBN replaces bn1 in stages 1-3."""
+    return ResNet([3, 4, 6, 3], active_num=active_num, pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type,
+                  ibn_cfg=("a", "a", "a", None), **kw)

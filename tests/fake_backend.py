@@ -7,6 +7,7 @@ import numpy as np
 import torch
 
 from oracle import cnsn_oracle as O
+from oracle import ibn_oracle as IB
 
 
 def _np(t):
@@ -94,6 +95,24 @@ class OracleBackend:
         d = torch.where(z > 0, dy, torch.zeros_like(dy)) if relu else dy
         dz, gg, _ = self.selfnorm_bwd(z, d, g, None, training, save)
         return dz, gg
+
+    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
+        self.calls.append("ibn_fwd")
+        pp = {k: _np(p[k]) for k in ("in_w", "in_b", "bn_w", "bn_b")}
+        bufs = {"rm": _np(p["run_mean"]), "rv": _np(p["run_var"])}
+        y, rm, rv = IB.ibn_fwd(_np(x), half, pp, bufs, training, momentum, eps_in, eps_bn)
+        if training:
+            p["run_mean"].copy_(_t(rm, p["run_mean"]))
+            p["run_var"].copy_(_t(rv, p["run_var"]))
+            if p.get("nbt") is not None:
+                p["nbt"] += 1
+        return _t(y, x), {"bufs": bufs, "eps": (eps_in, eps_bn)}
+
+    def ibn_bwd(self, x, dy, half, p, training, save):
+        self.calls.append("ibn_bwd")
+        pp = {"in_w": _np(p["in_w"]), "bn_w": _np(p["bn_w"])}
+        dx, a, b, c, d = IB.ibn_bwd(_np(x), _np(dy), half, pp, save["bufs"], training, *save["eps"])
+        return _t(dx, x), tuple(_t(v, x, torch.float32) for v in (a, b, c, d))
 
     @staticmethod
     def _plan(x, perm, chan_perm, cwin, swin):

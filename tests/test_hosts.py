@@ -79,6 +79,36 @@ def test_resnet_matches_reference_model(fake, pos, cnsn_type, fuse, capsys):
     assert torch.allclose(a(x), b(x), atol=1e-8)
 
 
+@pytest.mark.parametrize("pos", ["post", "pre"])
+def test_resnet_ibn_a_matches_reference_model(fake, pos, capsys):
+    """ResNet-IBN-a host vs models/imagenet/resnet_ibn_cnsn.py: identical state dict for equal seeds, identical
+    logits and gradients (the IBN layers run through cnsn_ibn_fwd/_bwd, here the oracle-backed stand-in)."""
+    from cnsn_b200.hosts import ResNet
+    RefResNet = _reference_host("models.imagenet.resnet_ibn_cnsn", "ResNet")
+    kw = dict(num_classes=7, active_num=1, pos=pos, beta=1, crop="both", cnsn_type="cnsn")
+    torch.manual_seed(0)
+    a = RefResNet(layers=[1, 1, 1, 1], ibn_cfg=("a", "a", "a", None), **kw).double().train()
+    torch.manual_seed(0)
+    b = ResNet([1, 1, 1, 1], ibn_cfg=("a", "a", "a", None), **kw).double().train()
+    capsys.readouterr()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    x = torch.randn(4, 3, 224, 224, dtype=torch.float64)[:, :, :224:1, :224:1]
+    outs = []
+    for net in (a, b):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        o = net(x, aug=True)
+        o.square().sum().backward()
+        outs.append(o)
+    assert "ibn_fwd" in fake.calls and "ibn_bwd" in fake.calls
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+
+
 def test_resnet50_census():
     """ResNet-50 + SN ('post'): 16 SelfNorm sites with the channel counts of SURVEY.md 8 (cfg4)."""
     from cnsn_b200.hosts import resnet50
