@@ -167,3 +167,28 @@ def test_train_step_on_cpu_with_eager_ops():
     from oracle import eager_modules
     r = bench_wrn(torch.device("cpu"), 1, 0, batch=8, steps=2, warmup=1, cn_prob=1.0, ops=eager_modules)
     assert r["value"] > 0 and np.isfinite(r["final_loss"]) and r["params"] == 2248922
+
+
+def test_reference_checkpoint_round_trip(fake, tmp_path, capsys):
+    """A checkpoint written the way the reference writes them (DataParallel 'module.' keys inside a training dict, or a
+    bare state dict) loads into the host model; values identical, nothing missing, extras returned."""
+    from cnsn_b200.hosts import ResNet
+    from cnsn_b200.utils import load_reference_checkpoint
+    RefResNet = _reference_host("models.imagenet.resnet_cnsn", "ResNet")
+    kw = dict(num_classes=5, active_num=1, pos="post", beta=1, crop="both", cnsn_type="sn")
+    torch.manual_seed(3)
+    ref = RefResNet([1, 1, 1, 1], **kw)
+    capsys.readouterr()
+    wrapped = {"module." + k: v for k, v in ref.state_dict().items()}
+    path = tmp_path / "ckpt.pth.tar"
+    torch.save({"epoch": 7, "best_err1": 23.4, "state_dict": wrapped}, path)
+    torch.manual_seed(9)
+    net = ResNet([1, 1, 1, 1], **kw)
+    missing, unexpected, extras = load_reference_checkpoint(net, str(path))
+    assert missing == [] and unexpected == [] and extras["epoch"] == 7
+    for k, v in ref.state_dict().items():
+        assert torch.equal(net.state_dict()[k], v), k
+    # bare state dict with an extra head (strict=False, as imagenet.py:518-521)
+    bare = dict(ref.state_dict(), **{"aux.weight": torch.zeros(1)})
+    missing, unexpected, _ = load_reference_checkpoint(net, bare)
+    assert missing == [] and unexpected == ["aux.weight"]
