@@ -13,10 +13,15 @@ One "step" = one forward + one backward pass of the hot path over one synthetic 
              against MEASURED_PEAKS.json's HBM copy bandwidth
   e2e        the same metric through the nn.Module API with HOST (pinned) buffers: per step
              H2D of x and dy, forward, backward, D2H of y and dx inside the timed region
+             (double-buffered over three streams, as a data loader would feed it)
   cpu_baseline / --impl reference
              the eager-PyTorch op chain of the reference (oracle/eager_chain.py, bit-identical
              to models/cnsn.py on CPU) timed on this box's host cores on a bounded sample
-  train      secondary: WideResNet-40-2 + CNSN training step images/s (DDP over NCCL when N>1)
+  crossnorm  secondary: CrossNorm fwd+bwd through cn_op_2ins_space_chan (BASELINE config 2, a WideResNet
+             site with crops, a north-star-sized tensor)
+  train      secondary: training-step images/s, DDP over NCCL when N>1: WideResNet-40-2 + CNSN (config 3),
+             train.resnet50 = ResNet-50 + SN batch 256/GPU (config 4), train.resnet50_jsd = the 3-view JSD
+             step in bf16 (config 5)
 
 Multi-GPU: the CNSN path has no cross-GPU exchange -- every rank runs the same
 per-GPU workload on its own shard ("weak" scaling, no data-path collective); only the secondary

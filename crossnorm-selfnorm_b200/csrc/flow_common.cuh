@@ -14,7 +14,7 @@ namespace flow {
 
 using fused::smem_u32;
 
-constexpr unsigned kSpin = 1u << 22;    // bounded polls (>= 64 ns each): trap instead of hanging the GPU
+constexpr unsigned kSpin = 1u << 25;    // bounded polls (>= 64 ns each, i.e. seconds): trap instead of hanging the GPU
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
