@@ -102,6 +102,18 @@ def launch_count():
     return int(lib().cnsn_launch_count())
 
 
+_SIZES = {}
+
+
+def _size(fn_name, *dims):
+    """Workspace / save sizes are pure functions of the dims: one ctypes call per distinct shape."""
+    key = (fn_name,) + dims
+    v = _SIZES.get(key)
+    if v is None:
+        v = _SIZES[key] = int(getattr(lib(), fn_name)(*dims))
+    return v
+
+
 def _check(rc):
     if rc == 0:
         return
@@ -229,7 +241,7 @@ class CudaBackend:
         keep = []
         gs, g_rm, g_rv = self._gate_struct(g, keep)
         fs, f_rm, f_rv = self._gate_struct(f, keep) if two else (None, None, None)
-        save = torch.empty(lib().cnsn_selfnorm_save_floats(N, C, int(two)), dtype=torch.float32, device=x.device)
+        save = torch.empty(_size("cnsn_selfnorm_save_floats", N, C, int(two)), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         with _on(x.device):
             _check(lib().cnsn_selfnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W,
@@ -261,7 +273,7 @@ class CudaBackend:
         out_f = grad_block() if two else None
         gg = GateGrads(*[_p(t).value for t in out_g])
         gf = GateGrads(*[_p(t).value for t in out_f]) if two else None
-        ws = torch.empty(lib().cnsn_selfnorm_workspace_floats(N, C, int(two)), dtype=torch.float32, device=dev)
+        ws = torch.empty(_size("cnsn_selfnorm_workspace_floats", N, C, int(two)), dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
         with _on(dev):
             _check(lib().cnsn_selfnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,
@@ -278,7 +290,7 @@ class CudaBackend:
         N, C, H, W = x.shape
         keep = []
         gs, g_rm, g_rv = self._gate_struct(g, keep)
-        save = torch.empty(lib().cnsn_selfnorm_save_floats(N, C, 0), dtype=torch.float32, device=x.device)
+        save = torch.empty(_size("cnsn_selfnorm_save_floats", N, C, 0), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         z = torch.empty_like(x) if res is not None else x
         with _on(x.device):
@@ -301,7 +313,7 @@ class CudaBackend:
         buf = torch.empty(4 * C, dtype=torch.float32, device=dev)
         out_g = (buf[:2 * C].view(C, 2), buf[2 * C:3 * C], buf[3 * C:])
         gg = GateGrads(*[_p(t).value for t in out_g])
-        ws = torch.empty(lib().cnsn_selfnorm_workspace_floats(N, C, 0), dtype=torch.float32, device=dev)
+        ws = torch.empty(_size("cnsn_selfnorm_workspace_floats", N, C, 0), dtype=torch.float32, device=dev)
         dz = torch.empty_like(z)
         with _on(dev):
             _check(lib().cnsn_selfnorm_block_bwd(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
@@ -371,7 +383,7 @@ class CudaBackend:
     def crossnorm_fwd(self, x, perm, chan_perm, cwin, swin, lam, eps):
         _require_cuda(x, perm, chan_perm)
         N, C, H, W = x.shape
-        save = torch.empty(lib().cnsn_crossnorm_save_floats(N, C), dtype=torch.float32, device=x.device)
+        save = torch.empty(_size("cnsn_crossnorm_save_floats", N, C), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         with _on(x.device):
             _check(lib().cnsn_crossnorm_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, _p(perm), _p(chan_perm),
@@ -381,7 +393,7 @@ class CudaBackend:
     def crossnorm_bwd(self, x, dy, perm, chan_perm, cwin, swin, lam, save):
         _require_cuda(x, dy)
         N, C, H, W = x.shape
-        ws = torch.empty(lib().cnsn_crossnorm_workspace_floats(N, C), dtype=torch.float32, device=x.device)
+        ws = torch.empty(_size("cnsn_crossnorm_workspace_floats", N, C), dtype=torch.float32, device=x.device)
         dx = torch.empty_like(x)
         with _on(x.device):
             _check(lib().cnsn_crossnorm_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W,

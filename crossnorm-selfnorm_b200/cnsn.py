@@ -61,13 +61,46 @@ def cn_rand_bbox(size, beta, bbx_thres):
             return bbx1, bby1, bbx2, bby2
 
 
+class _PinnedRing:
+    """A few persistent pinned int32 staging blocks per device for permutation uploads: no pinned allocation per
+    call, and a block is reused only after the copy that read it has completed (CUDA event)."""
+    SLOTS, WORDS = 16, 4096
+
+    def __init__(self):
+        self.buf = torch.empty((self.SLOTS, self.WORDS), dtype=torch.int32, pin_memory=True)
+        self.events = [None] * self.SLOTS
+        self.next = 0
+
+    def upload(self, idx, device):
+        n = idx.numel()
+        if n > self.WORDS:
+            host = torch.empty(n, dtype=torch.int32, pin_memory=True)
+            host.copy_(idx)
+            return host.to(device, non_blocking=True)
+        i = self.next
+        self.next = (i + 1) % self.SLOTS
+        if self.events[i] is not None:
+            self.events[i].synchronize()              # almost always already complete (16 uploads ago)
+        host = self.buf[i, :n]
+        host.copy_(idx)
+        out = host.to(device, non_blocking=True)
+        ev = self.events[i] or torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self.events[i] = ev
+        return out
+
+
+_rings = {}
+
+
 def _to_device_i32(idx, device):
     """Upload a host permutation without the reference's blocking pageable copy (:62)."""
     if device.type != "cuda":
         return idx.to(torch.int32)
-    host = torch.empty(idx.numel(), dtype=torch.int32, pin_memory=True)   # cached pinned block, no cudaHostAlloc
-    host.copy_(idx)
-    return host.to(device, non_blocking=True)
+    ring = _rings.get(device)
+    if ring is None:
+        ring = _rings[device] = _PinnedRing()
+    return ring.upload(idx, device)
 
 
 def cn_op_2ins_space_chan(x, crop='neither', beta=1, bbx_thres=0.1, lam=None, chan=False):
