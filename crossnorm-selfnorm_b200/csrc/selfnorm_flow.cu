@@ -199,6 +199,14 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
         uint4* pz = add ? reinterpret_cast<uint4*>(static_cast<T*>(a.zout) + nc * M) : nullptr;
         float sxy = 0.f, pre_g = 0.f, pre_s = 0.f;
         if (BWD && live && r == 0) { pre_g = a.gate[nc]; pre_s = a.shat[nc]; }   // issued ahead of the plane loads
+        // L2 prefetch (cp.async.bulk.prefetch) of the planes the R item pf_dist channels ahead will read: its
+        // loads then find them in L2 and the item holds its registers for an L2, not an HBM, round trip.
+        if (a.pf_dist && c + (unsigned)a.pf_dist < C && r == 0 && live) {
+            const size_t off = ((size_t)n * C + c + (unsigned)a.pf_dist) * M;
+            const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
+            fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+            if (two) fused::tma_prefetch_l2(static_cast<const T*>(BWD ? a.dy : a.res) + off, pbytes);
+        }
         Moments acc = moments_zero();
         for (int i0 = r; i0 < nv; i0 += kStep) {
             uint4 rx[kU], rd[kU];
@@ -917,6 +925,7 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     a.D = D;
     a.order = env_int("CNSN_FLOW_ORDER", 0);
     a.keep = env_int("CNSN_FLOW_KEEP", 1);
+    a.pf_dist = env_int("CNSN_FLOW_RPF", 0);               // R items: L2 prefetch distance in channels (0 = off)
     const unsigned long long items = 2ull * C * a.nI;
     if (items > 0x7fffffffull) return -100;
     // scratch: pub [C][N] float2 | chan [C] float2 | done [C] | ready [C] | ticket
