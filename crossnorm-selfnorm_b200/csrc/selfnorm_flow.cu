@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
 // that run (a "super-plane") is what TMA fetches and what the apply phase streams out with 128-bit accesses,
 // looking up each element's channel in a per-instance coefficient table; the per-instance reductions read
 // shared memory element-wise.  An item = I samples x kk channels = 128 / TPI instances (TPI = 1, 2 or 4 threads
-// each, chosen so that an item is ~12-25 KB); tickets are group-major; the group's kk channels are folded by its
+// each, chosen so that an item is ~20-40 KB); tickets are group-major; the group's kk channels are folded by its
 // last kk tickets, one channel each (every CTA of the group is co-resident, see above).
 constexpr int kGrpT = 128;
 
@@ -1046,7 +1046,8 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (!kk) return -100;
     const bool add = !BWD && a.res != nullptr;
     const size_t ib = pb * ((BWD || add) ? 2 : 1);               // bytes per instance in shared memory
-    const int tpi = (32 * ib >= 12288 || kk > 32) ? 4 : (64 * ib >= 12288 || kk > 64) ? 2 : 1;
+    const size_t want = (size_t)env_int("CNSN_FLOW_GRP_KB", 20) << 10;      // item size aimed at
+    const int tpi = (32 * ib >= want || kk > 32) ? 4 : (64 * ib >= want || kk > 64) ? 2 : 1;
     const int I = (kGrpT / tpi) / kk;
     if (I < 1) return -100;
     const size_t dsmem = 128 + (size_t)I * kk * ib;
