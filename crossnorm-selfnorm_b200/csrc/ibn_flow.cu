@@ -250,19 +250,19 @@ template <bool BWD>
 static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     const int N = a.N, C = a.C;
     const int esz = (int)esize(dtype);
-    if (((size_t)a.M * esz) % 16) return CNSN_E_BADARG;      // no general path for this operator (documented)
+    if (((size_t)a.M * esz) % 16) return CNSN_E_UNSUPPORTED;      // no general path for this operator (documented)
     const size_t inst_bytes = (size_t)a.M * esz * (BWD ? 2 : 1);
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= (25u << 10) + 512 && 2 * inst <= N) inst <<= 1;
     const int tpi = kIbnT / inst;
     const size_t dsmem = 128 + (size_t)inst * inst_bytes;
     const DeviceShape ds = device_shape();
-    if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_BADARG;
+    if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_UNSUPPORTED;
     a.nI = (N + inst - 1) / inst;
     a.order = env_int("CNSN_FLOW_ORDER", 0);
     a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
     const unsigned long long items = (unsigned long long)C * a.nI;
-    if (items > 0x7fffffffull) return CNSN_E_BADARG;
+    if (items > 0x7fffffffull) return CNSN_E_UNSUPPORTED;
     a.items = (unsigned)items;
     a.pub = reinterpret_cast<float2*>(scratch);
     a.chan = a.pub + (size_t)N * C;
@@ -275,7 +275,7 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         auto fn = k_ibn_res<T, BWD, TPI_>;                                                               \
         e = prepare_kernel(fn, kIbnT, dsmem, &per_sm);                                                   \
         if (e != cudaSuccess) return (int)e;                                                             \
-        if ((long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_BADARG;   /* a channel must be co-resident */ \
+        if ((long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;   /* a channel must be co-resident */ \
         a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);                                        \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
@@ -283,7 +283,7 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_IBN_CASE(8) CNSN_IBN_CASE(16) CNSN_IBN_CASE(32) CNSN_IBN_CASE(64) CNSN_IBN_CASE(128)
-        default: return CNSN_E_BADARG;
+        default: return CNSN_E_UNSUPPORTED;
     });
 #undef CNSN_IBN_CASE
     return launch_status();

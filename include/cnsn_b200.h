@@ -39,7 +39,9 @@ enum {
     CNSN_E_BADARG = -1,   /* null pointer, non-positive dim, bad dtype, bad window, bad perm ptr */
     CNSN_E_WORKSPACE = -2,/* workspace too small */
     CNSN_E_BATCH1 = -3,   /* SelfNorm training with N == 1 (reference: BatchNorm1d ValueError) */
-    CNSN_E_ALIGN = -4     /* tensor base pointer not aligned to its element size */
+    CNSN_E_ALIGN = -4,    /* tensor base pointer not aligned to its element size */
+    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_ibn_*: planes must be
+                             16-byte multiples and a channel's N planes must fit the GPU's shared memory) */
 };
 
 /* Library / ABI identification. */

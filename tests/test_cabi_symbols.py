@@ -46,3 +46,11 @@ def test_argument_validation_without_gpu():
     assert h.cnsn_selfnorm_save_floats(4, 16, 0) == 4 * 64 + 16 + 2 * 64 + 36 * 16 + 8
     assert h.cnsn_selfnorm_save_floats(4, 16, 1) == 6 * 64 + 32 + 2 * 64 + 36 * 16 + 8
     assert h.cnsn_crossnorm_save_floats(4, 16) == 256 + 2 * 64 + 8
+
+
+def test_error_strings_cover_every_code():
+    import cnsn_b200._lib as L
+    h = L.lib()
+    for code in (0, -1, -2, -3, -4, -5):
+        assert h.cnsn_error_string(code).decode() not in ("", "cnsn: unknown error"), code
+    assert "unknown" in h.cnsn_error_string(-99).decode()
