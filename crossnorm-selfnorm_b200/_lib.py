@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(_PKG, "libcnsn_b200.so")
 
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
 
@@ -68,6 +68,13 @@ SIGNATURES = {
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnsn_site_save_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_site_workspace_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_site_supported": (c_int, [c_int, *_DIMS]),
+    "cnsn_site_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, POINTER(c_int), POINTER(c_int), c_float, c_float,
+                              POINTER(GateParams), c_float, c_float, c_float, c_int, c_void_p, c_void_p]),
+    "cnsn_site_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, POINTER(c_int), POINTER(c_int), c_float, c_int,
+                              POINTER(GateParams), c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p,
@@ -400,6 +407,49 @@ class CudaBackend:
                                             _p(perm), _p(chan_perm), _I4(*cwin), _I4(*swin), lam,
                                             _p(save), _p(ws), _stream(x)))
         return dx
+
+
+    # -- fused site: CrossNorm -> SelfNorm ---------------------------------------------------
+    def site_supported(self, x):
+        """True when cnsn_site_fwd/_bwd can run this shape on x's device (cached per shape)."""
+        if not x.is_cuda:
+            return False
+        N, C, H, W = x.shape
+        with _on(x.device):
+            return bool(_size("cnsn_site_supported", _dtype_code(x), N, C, H, W))
+
+    def site_fwd(self, x, perm, cwin, swin, lam, cn_eps, g, momentum, bn_eps, sn_eps, relu=False):
+        _require_cuda(x, perm)
+        N, C, H, W = x.shape
+        keep = []
+        gs, g_rm, g_rv = self._gate_struct(g, keep)
+        save = torch.empty(_size("cnsn_site_save_floats", N, C), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        with _on(x.device):
+            _check(lib().cnsn_site_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, _p(perm), _I4(*cwin), _I4(*swin),
+                                       lam, cn_eps, ctypes.byref(gs), momentum, bn_eps, sn_eps, int(relu), _p(save),
+                                       _stream(x)))
+        if g_rm is not g.run_mean:
+            g.run_mean.copy_(g_rm)
+        if g_rv is not g.run_var:
+            g.run_var.copy_(g_rv)
+        return y, save
+
+    def site_bwd(self, x, dy, perm, cwin, swin, lam, g, save, relu=False):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        keep = []
+        gs, _, _ = self._gate_struct(g, keep)
+        dev = x.device
+        buf = torch.empty(4 * C, dtype=torch.float32, device=dev)
+        out_g = (buf[:2 * C].view(C, 2), buf[2 * C:3 * C], buf[3 * C:])
+        gg = GateGrads(*[_p(t).value for t in out_g])
+        ws = torch.empty(_size("cnsn_site_workspace_floats", N, C), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        with _on(dev):
+            _check(lib().cnsn_site_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, _p(perm), _I4(*cwin), _I4(*swin),
+                                       lam, int(relu), ctypes.byref(gs), _p(save), ctypes.byref(gg), _p(ws), _stream(x)))
+        return dx, out_g
 
 
 _backend = None

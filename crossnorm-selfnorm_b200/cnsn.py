@@ -15,7 +15,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import CrossNormFn, InstanceAffine, InstanceStats, SelfNormBlockFn, SelfNormFn
+from .functional import CnsnSiteFn, CrossNormFn, InstanceAffine, InstanceStats, SelfNormBlockFn, SelfNormFn
 
 __all__ = ["calc_ins_mean_std", "instance_norm_mix", "cn_rand_bbox", "cn_op_2ins_space_chan",
            "CrossNorm", "SelfNorm", "CNSN"]
@@ -111,6 +111,14 @@ def cn_op_2ins_space_chan(x, crop='neither', beta=1, bbx_thres=0.1, lam=None, ch
     device work (two statistics sets, permuted restyle, copy-through outside the content box) is one
     fused CUDA forward and one fused backward.
     """
+    perm_d, cperm_d, cwin, swin = _draw_plan(x, crop, beta, bbx_thres, chan)
+    return CrossNormFn.apply(x, perm_d, cperm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5)
+
+
+def _draw_plan(x, crop, beta, bbx_thres, chan):
+    """The host-side draws of one cn_op_2ins_space_chan call, in the reference's order (models/cnsn.py:61-77,
+    SURVEY.md A.3); the permutations are uploaded as int32.  Returns (perm, chan_perm | None, content, style)
+    with windows as (h0, h1, w0, w1)."""
     assert crop in _CROPS                                   # :61
     assert x.dim() == 4
     N, C, H, W = x.shape
@@ -125,7 +133,7 @@ def cn_op_2ins_space_chan(x, crop='neither', beta=1, bbx_thres=0.1, lam=None, ch
         cwin = (int(a1), int(a2), int(b1), int(b2))
     perm_d = _to_device_i32(perm, x.device)
     cperm_d = _to_device_i32(chan_perm, x.device) if chan else None
-    return CrossNormFn.apply(x, perm_d, cperm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5)
+    return perm_d, cperm_d, cwin, swin
 
 
 class CrossNorm(nn.Module):
@@ -200,6 +208,8 @@ class CNSN(nn.Module):
         fire = bool(self.crossnorm) and self.crossnorm.active
         if residual is None and not relu:
             if fire:
+                if self._site_fusable(x):
+                    return self._site(x, False)
                 x = self.crossnorm(x)
             if self.selfnorm:
                 x = self.selfnorm(x)
@@ -208,8 +218,38 @@ class CNSN(nn.Module):
             if residual is not None:
                 x = torch.add(residual, x)
             if fire:
+                if self._site_fusable(x):
+                    return self._site(x, relu)
                 x = self.crossnorm(x)
             if self.selfnorm:
                 return self.selfnorm(x, None, relu)
             return torch.relu(x) if relu else x
         return self.selfnorm(x, residual, relu)
+
+    fuse_site = True    # class-wide switch (A/B measurements, tests): False -> always the two-operator sequence
+
+    def _site_fusable(self, x):
+        """Both operators fire at this call and one fused kernel per direction can serve it: the CrossNorm is the
+        stock partial of cn_op_2ins_space_chan without channel permutation, the SelfNorm is single-gate and in
+        training mode, and the shape fits the resident kernels (cnsn_site_supported)."""
+        cn, sn = self.crossnorm, self.selfnorm
+        if not (CNSN.fuse_site and sn and cn.training and cn.active and x.dim() == 4):
+            return False
+        op = getattr(cn, "cn_op", None)
+        if not (isinstance(sn, SelfNorm) and sn.f_fc is None and sn.g_bn.training and isinstance(op, functools.partial)
+                and op.func is cn_op_2ins_space_chan and not op.args and not op.keywords.get("chan", False)):
+            return False
+        return _lib.backend().site_supported(x)
+
+    def _site(self, x, relu):
+        """``relu?(selfnorm(crossnorm(x)))`` in one kernel per direction; the host draws are those of
+        ``crossnorm(x)`` (same RNG consumption), and the one-shot ``active`` flag is consumed (models/cnsn.py:108)."""
+        cn, sn = self.crossnorm, self.selfnorm
+        kw = cn.cn_op.keywords
+        perm_d, _, cwin, swin = _draw_plan(x, kw.get("crop", "neither"), kw.get("beta", 1), kw.get("bbx_thres", 0.1), False)
+        lam = kw.get("lam")
+        cn.active = False
+        bn = sn.g_bn
+        return CnsnSiteFn.apply(x, perm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5, bool(relu),
+                                float(bn.momentum), float(bn.eps), 1e-12, SelfNorm._bufs(bn),
+                                sn.g_fc.weight, bn.weight, bn.bias)

@@ -46,53 +46,6 @@ struct CNArgs {
     unsigned* ticket;       // starts at 0xffffffff
 };
 
-// sum over a window of f(x [, dy]) for one shared-memory-resident instance; the team's threads split the work.
-// full: 128-bit reads over the flat plane; else element reads over the window's rows.
-template <typename T, bool TWO, typename F>
-__device__ __forceinline__ void window_accumulate(uint32_t sx, uint32_t sdy, int W, int M, const Window& win, bool full,
-                                                  int r, int tpi, F f) {
-    constexpr int V = VecOf<T>::n;
-    if (full) {
-        const int nv = M / V;
-#pragma unroll 4
-        for (int i = r; i < nv; i += tpi) {
-            float vx[V], vd[V];
-            unpack<T>(lds128(sx + 16u * i), vx);
-            if (TWO) unpack<T>(lds128(sdy + 16u * i), vd);
-#pragma unroll
-            for (int e = 0; e < V; ++e) f(vx[e], TWO ? vd[e] : 0.f, e);
-        }
-    } else {
-        const int cols = win.cols(), area = win.area();
-        int hh = r / cols, ww = r - hh * cols;               // one division per thread, then incremental
-        const int dh = tpi / cols, dw = tpi - dh * cols;
-        for (int i = r; i < area; i += tpi) {
-            const int o = (win.h0 + hh) * W + win.w0 + ww;
-            f(lds_elem<T>(sx, o), TWO ? lds_elem<T>(sdy, o) : 0.f, i);
-            hh += dh; ww += dw;
-            if (ww >= cols) { ww -= cols; ++hh; }
-        }
-    }
-}
-
-// exact two-pass (mean, sqrt(unbiased var + eps)) of one window; every thread of the CTA must call it
-template <typename T, int TPI>
-__device__ __forceinline__ float2 window_stats(uint32_t sx, int W, int M, const Window& win, bool full, int r, bool live,
-                                               float eps, float* sm0, float* sm1) {
-    const float cnt = (float)win.area();
-    float s0 = 0.f, s1 = 0.f;
-    if (live) window_accumulate<T, false>(sx, 0u, W, M, win, full, r, TPI, [&](float x, float, int e) { if (e & 1) s1 += x; else s0 += x; });
-    const float mean = team_sum<TPI>(s0 + s1, sm0) / cnt;
-    s0 = s1 = 0.f;
-    if (live) window_accumulate<T, false>(sx, 0u, W, M, win, full, r, TPI, [&](float x, float, int e) {
-        const float d = x - mean;
-        if (e & 1) s1 = fmaf(d, d, s1); else s0 = fmaf(d, d, s0);
-    });
-    const float m2 = team_sum<TPI>(s0 + s1, sm1);
-    // a 1-element window yields 0/0 = NaN exactly like torch.var
-    return make_float2(mean, sqrtf(m2 / (cnt - 1.f) + eps));
-}
-
 template <typename T, bool BWD, int TPI>
 __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
     constexpr int TH = kCnT;

@@ -1,0 +1,470 @@
+// site_flow.cu -- a CNSN site whose CrossNorm AND SelfNorm both fire (CNSN.forward, models/cnsn.py:159-164:
+// `x = self.crossnorm(x); x = self.selfnorm(x)`) as ONE shared-memory-resident dataflow kernel per direction
+// (SURVEY.md 8f-2).  The unfused sequence moves 4*S forward (x -> z, z -> y) and 6*S backward; here the
+// CrossNorm output z never leaves the chip: 2*S forward, 3*S backward, and backward keeps no z at all (it is
+// rebuilt from x and the O(N*C) CrossNorm statistics).
+//
+// It is the composition of crossnorm_flow.cu's and selfnorm_flow.cu's resident items (same tickets, same polled
+// 8-byte words, same deadlock argument: every wait is for an item of the same channel, a channel's items are
+// consecutive tickets and all co-resident, and nothing waits before it has published what its stage owes):
+//
+//   forward  CTA(ticket t): channel c = t / nI, instances j*I .. j*I+I-1
+//     1. cp.async.bulk the planes of x into shared memory                                   (TMA)
+//     2. (mu, sd) over the content and the style window; publish the style pair at cn[c][i]; poll cn[c][p(i)]
+//     3. z = CrossNorm(x) IN PLACE in shared memory (rounded to T, exactly what the unfused sequence stores);
+//        exact two-pass (mu_z, sd_z) of the whole plane; publish at sn[c][i]
+//     4. the channel's last ticket folds the N words (BatchNorm1d batch statistics, running statistics) and
+//        publishes the channel constants; everyone else polls them
+//     5. y = g * z (max(., 0) when the block's ReLU is fused in) out of shared memory, streamed out
+//   backward: x and dy resident
+//     1. z rebuilt on the fly from x and the saved statistics; sum dy*z -> sn[c][i]; channel fold (dgamma, dbeta,
+//        dw, the two batch-norm-backward scalars)
+//     2. dz = g*dy + b*(z - mu_z) + a IN PLACE of dy
+//     3. CrossNorm backward of (x, dz): S1, S2 over the content window scattered to cn[c][p(i)], poll cn[c][i],
+//        dx out of shared memory, streamed out
+//
+// Training mode only (CrossNorm never fires in eval mode, models/cnsn.py:104).  Shapes outside the resident path
+// (planes that are not 16-byte multiples, channels too large for the GPU's shared memory, channel permutation,
+// is_two): cnsn_site_supported() says so and the host runs the two operators one after the other.
+#include <stdio.h>
+
+#include "selfnorm_fold.cuh"
+
+namespace cnsn {
+namespace flow {
+
+constexpr int kSiteT = 128;             // threads per CTA
+
+struct SiteArgs {
+    FArgs sn;               // SelfNorm half: x / dy / out, N, C, M, nI, parameters, save block, sn words (pub), chan, ticket
+    int H, W;
+    Window cw, sw;          // content / style window
+    float lam, cn_eps;
+    const int* perm;        // [N] style source of every sample
+    float* mu_c; float* sd_c; float* mu_s; float* sd_s;     // CrossNorm save block
+    float2* pub_cn;         // [C][N] CrossNorm words, pre-filled with the sentinel
+};
+
+template <int TPI>
+__device__ __forceinline__ void team_sync() {
+    if (TPI <= 32) __syncwarp(); else __syncthreads();
+}
+
+// One 16-byte vector of the CrossNorm output: ca*x + cb inside the content window, x outside, rounded to T.
+template <typename T>
+__device__ __forceinline__ void cn_vec(const float (&vx)[VecOf<T>::n], float (&vz)[VecOf<T>::n], int i, int W,
+                                       const Window& cw, bool cfull, float ca, float cb) {
+    constexpr int V = VecOf<T>::n;
+    if (cfull) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) vz[e] = fmaf(ca, vx[e], cb);
+    } else {
+        int h = (i * V) / W, w = i * V - h * W;              // one division per vector
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            vz[e] = cw.has(h, w) ? fmaf(ca, vx[e], cb) : vx[e];
+            if (++w == W) { w = 0; ++h; }
+        }
+    }
+    if (sizeof(T) < 4) unpack<T>(pack<T>(vz), vz);
+}
+
+template <typename T, bool BWD, int TPI>
+__global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
+    constexpr int TH = kSiteT;
+    constexpr int I = TH / TPI;
+    constexpr int V = VecOf<T>::n;
+    const FArgs& a = s.sn;
+    extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
+    __shared__ unsigned s_word;
+    __shared__ float2 s_chan;
+    __shared__ float s_f[4][TH / 32];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
+    if (threadIdx.x == 0) {
+        fused::mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;   // the counter starts at 0xffffffff
+    }
+    __syncthreads();
+    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned c = t / nI, j = t - c * nI;
+    const int N = a.N, C = a.C, H = s.H, W = s.W, M = a.M;
+    const int n = (int)j * I + (int)(threadIdx.x / TPI);
+    const int r = threadIdx.x % TPI;
+    const bool live = n < N;
+    const size_t nc = (size_t)(live ? n : 0) * C + c;
+    const int nv = M / V;
+    const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
+    const uint32_t sx = smem_u32(dsm) + 128u + (threadIdx.x / TPI) * pbytes;
+    const uint32_t sdy = sx + (unsigned)I * pbytes;
+    if (threadIdx.x < 32) {                                  // lane q fetches instance q of the item
+        const int first = (int)j * I;
+        const int nlive = min(I, N - first);
+        const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
+        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        __syncwarp();
+        for (int q = threadIdx.x; q < nlive; q += 32) {
+            const size_t off = ((size_t)(first + q) * C + c) * M;
+            unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
+            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+        }
+        // L2 prefetch for the CTA that will take this one's place (see selfnorm_flow.cu)
+        const unsigned tf = t + (unsigned)a.pf_dist;
+        if (a.pf_dist && tf < a.items) {
+            const unsigned cf = tf / nI, jf = tf - cf * nI;
+            const int ff = (int)jf * I, nf = min(I, N - ff);
+            for (int q = threadIdx.x; q < nf; q += 32) {
+                const size_t off = ((size_t)(ff + q) * C + cf) * M;
+                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+            }
+        }
+    }
+    // everything that does not depend on other instances is fetched under the TMA latency
+    const Window cw = s.cw, sw = s.sw;
+    const bool cfull = cw.full(H, W), sfull = sw.full(H, W);
+    const bool same = cw.h0 == sw.h0 && cw.h1 == sw.h1 && cw.w0 == sw.w0 && cw.w1 == sw.w1;
+    const float lam = s.lam;
+    const bool relu = a.relu != 0;                           // block tail: y = max(y, 0) / dy masked where z <= 0
+    const bool folder = j == nI - 1;                         // holds the channel's last ticket
+    const int src_n = live ? s.perm[n] : 0;
+    const float p_w0 = a.w[2 * c], p_w1 = a.w[2 * c + 1], p_ga = a.gamma[c];
+    float p_b, p_rm = 0.f, p_rv = 1.f;
+    float pre_g = 0.f, pre_s = 0.f, p_mu = 0.f, p_sd = 1.f;                   // backward: SelfNorm save block
+    float muc = 0.f, sdc = 1.f, mus = 0.f, sds = 1.f, mus_src = 0.f, sds_src = 1.f;   // backward: CrossNorm save block
+    if (BWD) {
+        p_b = a.r[c];
+        if (live) {
+            pre_g = a.gate[nc]; pre_s = a.shat[nc]; p_mu = a.mu[nc]; p_sd = a.sd[nc];
+            muc = s.mu_c[nc]; sdc = s.sd_c[nc]; mus = s.mu_s[nc]; sds = s.sd_s[nc];
+            const size_t sc = (size_t)src_n * C + c;
+            mus_src = s.mu_s[sc]; sds_src = s.sd_s[sc];
+        }
+    } else {
+        p_b = a.beta[c];
+        if (folder && threadIdx.x == 0) { p_rm = a.run_mean[c]; p_rv = a.run_var[c]; }
+    }
+    fused::mbar_wait(bar, 0);
+
+    float2* flag = a.chan + 4u * c;                          // one 32-byte sector per channel
+    uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + nc * M);
+    if (!BWD) {
+        // ---- CrossNorm statistics, pairwise exchange ---------------------------------------------------
+        const float2 stc = window_stats<T, TPI>(sx, W, M, cw, cfull, r, live, s.cn_eps, s_f[0], s_f[1]);
+        float2 sts = stc;
+        if (!same) sts = window_stats<T, TPI>(sx, W, M, sw, sfull, r, live, s.cn_eps, s_f[2], s_f[3]);
+        if (live && r == 0) {
+            s.mu_c[nc] = stc.x; s.sd_c[nc] = stc.y; s.mu_s[nc] = sts.x; s.sd_s[nc] = sts.y;
+            fused::ll_publish(s.pub_cn + (size_t)c * N + n, sts.x, sts.y);
+        }
+        float ca = 1.f, cb = 0.f;
+        if (live) {
+            const float2 ps = poll_word(s.pub_cn + (size_t)c * N + src_n, a.poll_ns);   // the team polls one address
+            const float A = ps.y / stc.y;
+            ca = lam + (1.f - lam) * A;
+            cb = (1.f - lam) * (ps.x - stc.x * A);
+        }
+        // ---- z = CrossNorm(x) in place (thread-private slots), SelfNorm statistics of z --------------------
+        float s0 = 0.f, s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V], vz[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
+                sts128(sx + 16u * i, pack<T>(vz));
+#pragma unroll
+                for (int e = 0; e < V; ++e) { if (e & 1) s1 += vz[e]; else s0 += vz[e]; }
+            }
+        }
+        const float mean = team_sum<TPI>(s0 + s1, s_f[0]) * (1.f / M);
+        s0 = s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vz[V];
+                unpack<T>(lds128(sx + 16u * i), vz);
+#pragma unroll
+                for (int e = 0; e < V; ++e) { const float d = vz[e] - mean; if (e & 1) s1 = fmaf(d, d, s1); else s0 = fmaf(d, d, s0); }
+            }
+        }
+        const float m2 = team_sum<TPI>(s0 + s1, s_f[1]);
+        const float own_x = mean, own_y = sqrtf(m2 / (M - 1.f) + a.eps);
+        if (live && r == 0) {
+            a.mu[nc] = own_x; a.sd[nc] = own_y;
+            fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+        }
+        // ---- channel constants ---------------------------------------------------------------------------
+        if (folder) {
+            const float2 cst = fold_publish<false, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
+            if (threadIdx.x == 0) s_chan = cst;
+        } else if (threadIdx.x == 0) {
+            s_chan = poll_word(flag, a.poll_ns);
+        }
+        __syncthreads();
+        if (!live) return;
+        const float2 cm = s_chan;
+        const float sh = (fmaf(p_w0, own_x, p_w1 * own_y) - cm.x) * cm.y;
+        const float gt = 1.f / (1.f + expf(-fmaf(p_ga, sh, p_b)));
+        if (r == 0) { a.gate[nc] = gt; a.shat[nc] = sh; }
+#pragma unroll 4
+        for (int i = r; i < nv; i += TPI) {
+            float vz[V], vo[V];
+            unpack<T>(lds128(sx + 16u * i), vz);
+#pragma unroll
+            for (int e = 0; e < V; ++e) {
+                const float y = fmaf(gt, vz[e], 0.f);
+                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            }
+            stg_stream(po + i, pack<T>(vo));
+        }
+    } else {
+        // ---- SelfNorm backward at z (rebuilt from x): sum dy*z, channel fold -------------------------------
+        const float A = sds_src / sdc;
+        const float ca = lam + (1.f - lam) * A;
+        const float cb = (1.f - lam) * (mus_src - muc * A);
+        float s0 = 0.f, s1 = 0.f;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V], vd[V], vz[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+                unpack<T>(lds128(sdy + 16u * i), vd);
+                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float d = (relu && !(vz[e] > 0.f)) ? 0.f : vd[e];
+                    if (e & 1) s1 = fmaf(d, vz[e], s1); else s0 = fmaf(d, vz[e], s0);
+                }
+            }
+        }
+        const float sxy = team_sum<TPI>(s0 + s1, s_f[0]);
+        const float own_x = sxy * pre_g * (1.f - pre_g), own_y = pre_s;
+        if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+        if (folder) {
+            const float2 cst = fold_publish<true, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
+            if (threadIdx.x == 0) s_chan = cst;
+        } else if (threadIdx.x == 0) {
+            s_chan = poll_word(flag, a.poll_ns);
+        }
+        __syncthreads();
+        const float2 cm = s_chan;
+        // ---- dz = kg*dy + kb*z + kc in place of dy (thread-private slots) -----------------------------------
+        const float dsn = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
+        const float kb = dsn * p_w1 * (1.f / (M - 1.f)) / p_sd;
+        const float kc = dsn * p_w0 * (1.f / M) - kb * p_mu;
+        if (live) {
+#pragma unroll 4
+            for (int i = r; i < nv; i += TPI) {
+                float vx[V], vd[V], vz[V];
+                unpack<T>(lds128(sx + 16u * i), vx);
+                unpack<T>(lds128(sdy + 16u * i), vd);
+                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    const float d = (relu && !(vz[e] > 0.f)) ? 0.f : vd[e];
+                    vd[e] = fmaf(pre_g, d, fmaf(kb, vz[e], kc));
+                }
+                sts128(sdy + 16u * i, pack<T>(vd));
+            }
+        }
+        team_sync<TPI>();                                    // the window sums below read other threads' slots
+        // ---- CrossNorm backward of (x, dz): as crossnorm_flow.cu ---------------------------------------------
+        float t0 = 0.f, t1 = 0.f, a0 = 0.f, a1 = 0.f;
+        if (live) window_accumulate<T, true>(sx, sdy, W, M, cw, cfull, r, TPI, [&](float x, float d, int e) {
+            if (e & 1) { a1 = fmaf(d, x - muc, a1); t1 += d; } else { a0 = fmaf(d, x - muc, a0); t0 += d; }
+        });
+        const float asum = team_sum<TPI>(a0 + a1, s_f[2]);
+        const float tsum = team_sum<TPI>(t0 + t1, s_f[3]);
+        const float S1 = (1.f - lam) * tsum;
+        const float S2 = (1.f - lam) * asum / sdc;
+        if (live && r == 0) fused::ll_publish(s.pub_cn + (size_t)c * N + src_n, S1, S2);
+        if (!live) return;
+        const float2 ds = poll_word(s.pub_cn + (size_t)c * N + n, a.poll_ns);     // (dmu_s, dsd_s) of this instance
+        const float Mc = (float)cw.area(), Ms = (float)sw.area();
+        // inside the content window: dx = p*dz + q*x + r0
+        const float p = lam + (1.f - lam) * A;
+        const float q = -A * S2 / ((Mc - 1.f) * sdc);
+        const float r0 = -A * S1 / Mc - q * muc;
+        // inside the style window (this instance as somebody's style source): dx += u*x + v
+        const float u = ds.y / ((Ms - 1.f) * sds);
+        const float v = ds.x / Ms - u * mus;
+        const bool both_full = cfull && sfull;
+        const float qq = q + u, rr = r0 + v;
+#pragma unroll 4
+        for (int i = r; i < nv; i += TPI) {
+            float vx[V], vd[V], vo[V];
+            unpack<T>(lds128(sx + 16u * i), vx);
+            unpack<T>(lds128(sdy + 16u * i), vd);
+            if (both_full) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) vo[e] = fmaf(p, vd[e], fmaf(qq, vx[e], rr));
+            } else {
+                int h = (i * V) / W, w = i * V - h * W;
+#pragma unroll
+                for (int e = 0; e < V; ++e) {
+                    float val = cw.has(h, w) ? fmaf(p, vd[e], fmaf(q, vx[e], r0)) : vd[e];
+                    if (sw.has(h, w)) val += fmaf(u, vx[e], v);
+                    vo[e] = val;
+                    if (++w == W) { w = 0; ++h; }
+                }
+            }
+            stg_stream(po + i, pack<T>(vo));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct SiteShape { int inst, tpi, nI; size_t dsmem; };
+
+// Item geometry (as the resident SelfNorm / CrossNorm kernels); false when the resident path does not apply.
+static bool site_shape(int dtype, int N, int C, int M, bool bwd, SiteShape& g) {
+    const int esz = (int)esize(dtype);
+    if (((size_t)M * esz) % 16 || N < 2 || C < 1 || M < 2) return false;
+    const size_t inst_bytes = (size_t)M * esz * (bwd ? 2 : 1);
+    const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
+    int inst = 1;
+    while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
+    g.inst = inst;
+    g.tpi = kSiteT / inst;
+    g.dsmem = 128 + (size_t)inst * inst_bytes;
+    g.nI = (N + inst - 1) / inst;
+    if (g.dsmem > (size_t)device_shape().smem_optin / 2) return false;       // at least two CTAs per SM
+    if ((unsigned long long)C * g.nI > 0x7fffffffull) return false;
+    return true;
+}
+
+// prepare (once per kernel and shared-memory size) and optionally launch; -100 when the shape does not fit
+template <bool BWD>
+static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stream, bool dry_run) {
+    FArgs& a = s.sn;
+    const int N = a.N, C = a.C;
+    SiteShape g;
+    if (!site_shape(dtype, N, C, a.M, BWD, g)) return -100;
+    const int sms = device_shape().sms;
+    a.nI = g.nI;
+    a.order = env_int("CNSN_FLOW_ORDER", 0);
+    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.items = (unsigned)((unsigned long long)C * g.nI);
+    // scratch: sn words [C][N] | channel words [C] x 4 (one 32-byte sector each) | ticket | cn words [C][N]; all 0xff
+    a.pub = reinterpret_cast<float2*>(scratch);
+    a.chan = a.pub + (size_t)N * C;
+    a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
+    s.pub_cn = a.chan + 4 * (size_t)C + 1;
+    const size_t fill_bytes = (2 * (size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
+    const dim3 grid(a.items), block(kSiteT);
+    cudaError_t e = cudaSuccess;
+    int per_sm = 0;
+#define CNSN_SITE_CASE(TPI_)                                                                             \
+    case TPI_: {                                                                                         \
+        auto fn = k_site_res<T, BWD, TPI_>;                                                              \
+        e = prepare_kernel(fn, kSiteT, g.dsmem, &per_sm);                                                \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        if ((long long)per_sm * sms < 2ll * g.nI) return -100;    /* a whole channel must be co-resident */ \
+        if (dry_run) return 0;                                                                           \
+        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
+        e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
+        if (e != cudaSuccess) return (int)e;                                                             \
+        fn<<<grid, block, g.dsmem, stream>>>(s);                                                         \
+    } break;
+    CNSN_DISPATCH_DTYPE(dtype, T, switch (g.tpi) {
+        CNSN_SITE_CASE(8) CNSN_SITE_CASE(16) CNSN_SITE_CASE(32) CNSN_SITE_CASE(64) CNSN_SITE_CASE(128)
+        default: return -100;
+    });
+#undef CNSN_SITE_CASE
+    if (getenv("CNSN_FLOW_DEBUG"))
+        fprintf(stderr, "[cnsn flow/site] %s tpi=%d I=%d nI=%d items=%u smem=%zu ctas/sm=%d\n", BWD ? "bwd" : "fwd", g.tpi, g.inst,
+                g.nI, a.items, g.dsmem, per_sm);
+    return launch_status();
+}
+
+static size_t site_scratch_floats(int N, int C) { return 4 * (size_t)N * C + 8 * (size_t)C + 8; }
+
+struct SiteSave {             // offsets (in floats) into the save block
+    size_t mu_c, sd_c, mu_s, sd_s, mu, sd, g, shat, r, scratch, total;
+    SiteSave(int N, int C) {
+        const size_t nc = (size_t)N * C;
+        mu_c = 0; sd_c = nc; mu_s = 2 * nc; sd_s = 3 * nc;
+        mu = 4 * nc; sd = 5 * nc; g = 6 * nc; shat = 7 * nc; r = 8 * nc;
+        scratch = (r + (size_t)C + 1) & ~(size_t)1;           // 8-byte aligned
+        total = scratch + site_scratch_floats(N, C);
+    }
+};
+
+}  // namespace flow
+}  // namespace cnsn
+
+using namespace cnsn;
+using flow::SiteArgs;
+using flow::SiteSave;
+
+extern "C" size_t cnsn_site_save_floats(int N, int C) { return SiteSave(N, C).total; }
+extern "C" size_t cnsn_site_workspace_floats(int N, int C) { return flow::site_scratch_floats(N, C); }
+
+static int site_check(const void* x, const void* out, int dtype, int N, int C, int H, int W, const int* perm,
+                      const int* content, const int* style, Window& cw, Window& sw) {
+    if (!x || !out || !perm || !content || !style || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    cw = Window{content[0], content[1], content[2], content[3]};
+    sw = Window{style[0], style[1], style[2], style[3]};
+    if (check_window(cw, H, W) || check_window(sw, H, W)) return CNSN_E_BADARG;
+    if (N < 2) return CNSN_E_BATCH1;                 // BatchNorm1d raises ValueError in the reference
+    if (!aligned16(x) || !aligned16(out)) return CNSN_E_UNSUPPORTED;
+    return 0;
+}
+
+extern "C" int cnsn_site_supported(int dtype, int N, int C, int H, int W) {
+    if (check_dims(N, C, H, W) || dtype < CNSN_F32 || dtype > CNSN_F16) return 0;
+    SiteArgs s{};
+    s.sn.N = N; s.sn.C = C; s.sn.M = H * W; s.H = H; s.W = W;
+    if (flow::launch_site<false>(s, dtype, nullptr, nullptr, true) != 0) return 0;
+    return flow::launch_site<true>(s, dtype, nullptr, nullptr, true) == 0 ? 1 : 0;
+}
+
+extern "C" int cnsn_site_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                             const int* perm, const int* content, const int* style, float lam, float cn_eps,
+                             const cnsn_gate_params* g, float momentum, float bn_eps, float sn_eps, int relu,
+                             float* save, void* stream) {
+    Window cw, sw;
+    const int rc = site_check(x, y, dtype, N, C, H, W, perm, content, style, cw, sw);
+    if (rc) return rc;
+    if (!save || !g || !g->w || !g->gamma || !g->beta || !g->run_mean || !g->run_var) return CNSN_E_BADARG;
+    const SiteSave L(N, C);
+    SiteArgs s{};
+    flow::FArgs& a = s.sn;
+    a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W;
+    a.training = 1; a.momentum = momentum; a.bn_eps = bn_eps; a.eps = sn_eps; a.relu = relu ? 1 : 0;
+    a.w = g->w; a.gamma = g->gamma; a.beta = g->beta; a.run_mean = g->run_mean; a.run_var = g->run_var; a.nbt = g->nbt;
+    a.mu = save + L.mu; a.sd = save + L.sd; a.gate = save + L.g; a.shat = save + L.shat; a.r = save + L.r;
+    s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = cn_eps; s.perm = perm;
+    s.mu_c = save + L.mu_c; s.sd_c = save + L.sd_c; s.mu_s = save + L.mu_s; s.sd_s = save + L.sd_s;
+    const int frc = flow::launch_site<false>(s, dtype, save + L.scratch, (cudaStream_t)stream, false);
+    return frc == -100 ? CNSN_E_UNSUPPORTED : frc;
+}
+
+extern "C" int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                             const int* perm, const int* content, const int* style, float lam, int relu,
+                             const cnsn_gate_params* g, const float* save, const cnsn_gate_grads* dg,
+                             float* workspace, void* stream) {
+    Window cw, sw;
+    const int rc = site_check(x, dx, dtype, N, C, H, W, perm, content, style, cw, sw);
+    if (rc) return rc;
+    if (!dy || !save || !workspace || !g || !g->w || !g->gamma || !dg || !dg->dw || !dg->dgamma || !dg->dbeta) return CNSN_E_BADARG;
+    if (!aligned16(dy)) return CNSN_E_UNSUPPORTED;
+    const SiteSave L(N, C);
+    float* sv = const_cast<float*>(save);
+    SiteArgs s{};
+    flow::FArgs& a = s.sn;
+    a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.M = H * W;
+    a.training = 1; a.relu = relu ? 1 : 0;
+    a.w = g->w; a.gamma = g->gamma;
+    a.mu = sv + L.mu; a.sd = sv + L.sd; a.gate = sv + L.g; a.shat = sv + L.shat; a.r = sv + L.r;
+    a.dw = dg->dw; a.dgamma = dg->dgamma; a.dbeta = dg->dbeta;
+    s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = 0.f; s.perm = perm;
+    s.mu_c = sv + L.mu_c; s.sd_c = sv + L.sd_c; s.mu_s = sv + L.mu_s; s.sd_s = sv + L.sd_s;
+    const int frc = flow::launch_site<true>(s, dtype, workspace, (cudaStream_t)stream, false);
+    return frc == -100 ? CNSN_E_UNSUPPORTED : frc;
+}

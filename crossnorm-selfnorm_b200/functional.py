@@ -132,6 +132,30 @@ class CrossNormFn(torch.autograd.Function):
         return dx, None, None, None, None, None, None
 
 
+class CnsnSiteFn(torch.autograd.Function):
+    """A CNSN site whose CrossNorm and SelfNorm both fire (CNSN.forward, models/cnsn.py:159-164) as one forward
+    and one backward kernel (SURVEY.md 8f-2).  Saved for backward: x, the permutation and O(N*C) fp32 statistics;
+    the CrossNorm output is never materialised."""
+
+    @staticmethod
+    def forward(ctx, x, perm, cwin, swin, lam, cn_eps, relu, momentum, bn_eps, sn_eps, g_bufs, g_w, g_gamma, g_beta):
+        x = _dense(x)
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
+        y, save = _lib.backend().site_fwd(x, perm, cwin, swin, lam, cn_eps, g, momentum, bn_eps, sn_eps, relu)
+        ctx.save_for_backward(x, g_w, g_gamma, g_beta)
+        ctx.site = (perm, cwin, swin, lam, bool(relu), save)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, g_w, g_gamma, g_beta = ctx.saved_tensors
+        perm, cwin, swin, lam, relu, save = ctx.site
+        g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
+        dx, gg = _lib.backend().site_bwd(x, _dense(dy), perm, cwin, swin, lam, g, save, relu)
+        return (dx, None, None, None, None, None, None, None, None, None, None,
+                gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype))
+
+
 class JsdConsistencyFn(torch.autograd.Function):
     """The Jensen-Shannon consistency term of the 3-view steps (imagenet.py:367-376, cifar.py:173-182)."""
 

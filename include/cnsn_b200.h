@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define CNSN_ABI_VERSION 3
+#define CNSN_ABI_VERSION 4
 
 enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
 
@@ -40,8 +40,8 @@ enum {
     CNSN_E_WORKSPACE = -2,/* workspace too small */
     CNSN_E_BATCH1 = -3,   /* SelfNorm training with N == 1 (reference: BatchNorm1d ValueError) */
     CNSN_E_ALIGN = -4,    /* tensor base pointer not aligned to its element size */
-    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_ibn_*: planes must be
-                             16-byte multiples and a channel's N planes must fit the GPU's shared memory) */
+    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_ibn_*, cnsn_site_*: planes must
+                             be 16-byte multiples and a channel's N planes must fit the GPU's shared memory) */
 };
 
 /* Library / ABI identification. */
@@ -189,6 +189,38 @@ int cnsn_crossnorm_bwd(const void* x, const void* dy, void* dx, int dtype,
                        const int* perm, const int* chan_perm,
                        const int* content, const int* style,
                        float lam, const float* save, float* workspace, void* stream);
+
+/* ---------------------------------------------------------------- fused CNSN site --------
+ * A site whose CrossNorm AND SelfNorm both fire in one step -- CNSN.forward, models/cnsn.py:159-164:
+ *     if self.crossnorm and self.crossnorm.active: x = self.crossnorm(x)
+ *     if self.selfnorm:                            x = self.selfnorm(x)
+ * as one kernel per direction: the CrossNorm output never leaves the chip (2*S forward and 3*S
+ * backward of HBM traffic instead of 4*S and 6*S), and backward keeps x plus O(N*C) statistics only.
+ *
+ *   forward : y = SelfNorm(CrossNorm(x)); arguments as cnsn_crossnorm_fwd (no channel permutation) and
+ *             cnsn_selfnorm_fwd (single gate, TRAINING mode -- CrossNorm never fires in eval mode, :104).
+ *             cn_eps: models/cnsn.py:8 (1e-5); sn_eps: :133 (1e-12).  Running statistics / nbt are updated.
+ *             relu != 0: y = max(y, 0) -- the ReLU behind a pos='post' site (resnet_cnsn.py:122) in the same kernel.
+ *   backward: dx of the composition (dy masked where the CrossNorm output is <= 0 when relu); parameter
+ *             gradients are WRITTEN.
+ * save: cnsn_site_save_floats() floats = [mu_c | sd_c | mu_s | sd_s | mu_z | sd_z | g | shat] (N*C each), r (C),
+ * exchange area.  workspace: cnsn_site_workspace_floats() floats.
+ * Shapes: planes must be multiples of 16 bytes and a channel's N planes (x and dy) must fit the GPU's shared
+ * memory; cnsn_site_supported() returns 1 when both directions can run for the shape on the current device,
+ * else 0 (the caller then runs cnsn_crossnorm_* and cnsn_selfnorm_* one after the other -- identical results);
+ * the entry points return CNSN_E_UNSUPPORTED for such shapes and CNSN_E_BATCH1 for N == 1.
+ */
+size_t cnsn_site_save_floats(int N, int C);
+size_t cnsn_site_workspace_floats(int N, int C);
+int cnsn_site_supported(int dtype, int N, int C, int H, int W);
+int cnsn_site_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                  const int* perm, const int* content, const int* style, float lam, float cn_eps,
+                  const cnsn_gate_params* g, float momentum, float bn_eps, float sn_eps, int relu,
+                  float* save, void* stream);
+int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                  const int* perm, const int* content, const int* style, float lam, int relu,
+                  const cnsn_gate_params* g, const float* save, const cnsn_gate_grads* dg,
+                  float* workspace, void* stream);
 
 /* ---------------------------------------------------------------- IBN ---------------------
  * Instance-Batch Normalization, the IBN layer of models/imagenet/resnet_ibn_cnsn.py:24-44 (split along channels,

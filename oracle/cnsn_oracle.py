@@ -309,6 +309,27 @@ def selfnorm_bwd(x, dy, params, buffers, training=True, eps=SN_EPS, bn_eps=BN_EP
 
 
 # --------------------------------------------------------------------------------------
+# a7: CNSN with both operators firing (the fused site)             models/cnsn.py:159-164
+# --------------------------------------------------------------------------------------
+def site_fwd(x, plan, params, buffers, lam=None, training=True, cn_eps=CN_EPS, eps=SN_EPS,
+             bn_eps=BN_EPS, momentum=BN_MOMENTUM):
+    """CNSN.forward when the site's CrossNorm is active: ``x = crossnorm(x); x = selfnorm(x)``
+    (models/cnsn.py:160-163).  Returns (y, z, new_buffers) with z the CrossNorm output."""
+    z = crossnorm_fwd(x, plan, lam, cn_eps)
+    y, nb = selfnorm_fwd(z, params, buffers, training, eps, bn_eps, momentum)
+    return y, z, nb
+
+
+def site_bwd(x, dy, plan, params, buffers, lam=None, training=True, cn_eps=CN_EPS, eps=SN_EPS,
+             bn_eps=BN_EPS):
+    """Backward of site_fwd: the chain rule through SelfNorm (at z) and then CrossNorm (at x), as
+    autograd composes them for models/cnsn.py:160-163.  Returns (dx, grads)."""
+    z = crossnorm_fwd(x, plan, lam, cn_eps)
+    dz, grads = selfnorm_bwd(z, dy, params, buffers, training, eps, bn_eps)
+    return crossnorm_bwd(x, dz, plan, lam, cn_eps), grads
+
+
+# --------------------------------------------------------------------------------------
 # inputs used by the parity tests and the bench (SURVEY.md 8d, Appendix C.4)
 # --------------------------------------------------------------------------------------
 def varied_input(shape, seed=0, dtype=np.float32, relu=False):

@@ -128,3 +128,24 @@ class OracleBackend:
     def crossnorm_bwd(self, x, dy, perm, chan_perm, cwin, swin, lam, save):
         self.calls.append("crossnorm_bwd")
         return _t(O.crossnorm_bwd(_np(x), _np(dy), self._plan(x, perm, chan_perm, cwin, swin), lam), x)
+
+    # fused site: the oracle's composition (models/cnsn.py:159-164)
+    def site_supported(self, x):
+        return True
+
+    def site_fwd(self, x, perm, cwin, swin, lam, cn_eps, g, momentum, bn_eps, sn_eps, relu=False):
+        self.calls.append("site_fwd")
+        z, _ = self.crossnorm_fwd(x, perm, None, cwin, swin, lam, cn_eps)
+        self.calls.pop()
+        y, save = self.selfnorm_fwd(z, g, None, True, momentum, bn_eps, sn_eps)
+        self.calls.pop()
+        return (torch.relu(y) if relu else y), save
+
+    def site_bwd(self, x, dy, perm, cwin, swin, lam, g, save, relu=False):
+        self.calls.append("site_bwd")
+        z, _ = self.crossnorm_fwd(x, perm, None, cwin, swin, lam, 1e-5)
+        d = torch.where(z > 0, dy, torch.zeros_like(dy)) if relu else dy
+        dz, gg, _ = self.selfnorm_bwd(z, d, g, None, True, save)
+        dx = self.crossnorm_bwd(x, dz, perm, None, cwin, swin, lam, None)
+        del self.calls[-3:]
+        return dx, gg

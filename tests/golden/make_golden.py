@@ -114,6 +114,61 @@ def crossnorm_case(shape, seed, crop, chan, lam, dtype_tag="f32"):
     return out
 
 
+def site_case(shape, seed, crop):
+    """The reference's CNSN module with both operators firing (models/cnsn.py:152-164): CrossNorm(crop, beta=1)
+    with ``active = True`` followed by SelfNorm, training mode; plan recorded as in crossnorm_case."""
+    N, C, H, W = shape
+    x = varied_input(shape, seed=seed, dtype=np.float32)
+    dy = np.random.RandomState(seed + 100).standard_normal(shape).astype(np.float32)
+    out = {"x": x, "dy": dy, "crop": np.array(crop), "chan": np.array(False), "lam": np.array(np.nan),
+           "torch_seed": np.array(seed + 1), "numpy_seed": np.array(seed + 2)}
+    for prec, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        torch.manual_seed(seed)
+        sn = ref.SelfNorm(C)
+        with torch.no_grad():
+            gen = torch.Generator().manual_seed(seed + 7)
+            sn.g_bn.weight.copy_(torch.rand(C, generator=gen) + 0.5)
+            sn.g_bn.bias.copy_(torch.rand(C, generator=gen) - 0.5)
+            sn.g_bn.running_mean.copy_(torch.rand(C, generator=gen) * 2 - 1)
+            sn.g_bn.running_var.copy_(torch.rand(C, generator=gen) * 1.5 + 0.5)
+        m = ref.CNSN(ref.CrossNorm(crop=crop, beta=1), sn).to(dt).train(True)
+        if prec == "f32":
+            out["g_w"] = np32(sn.g_fc.weight)[:, 0, :]
+            out["g_gamma"] = np32(sn.g_bn.weight)
+            out["g_beta"] = np32(sn.g_bn.bias)
+            out["g_rm"] = np32(sn.g_bn.running_mean)
+            out["g_rv"] = np32(sn.g_bn.running_var)
+        m.crossnorm.active = True
+        torch.manual_seed(seed + 1)
+        np.random.seed(seed + 2)
+        xt = torch.from_numpy(x).to(dt).requires_grad_(True)
+        y = m(xt)
+        assert m.crossnorm.active is False                      # one-shot flag consumed (:108)
+        y.backward(torch.from_numpy(dy).to(dt))
+        cv = np32 if prec == "f32" else np64
+        out["y_" + prec] = cv(y)
+        out["dx_" + prec] = cv(xt.grad)
+        out["dg_w_" + prec] = cv(sn.g_fc.weight.grad)[:, 0, :]
+        out["dg_gamma_" + prec] = cv(sn.g_bn.weight.grad)
+        out["dg_beta_" + prec] = cv(sn.g_bn.bias.grad)
+        out["g_rm_after_" + prec] = cv(sn.g_bn.running_mean)
+        out["g_rv_after_" + prec] = cv(sn.g_bn.running_var)
+    torch.manual_seed(seed + 1)
+    np.random.seed(seed + 2)
+    out["perm"] = torch.randperm(N).numpy()
+    sw = cw = (-1, -1, -1, -1)
+    if crop in ("style", "both"):
+        b = ref.cn_rand_bbox(x.shape, beta=1, bbx_thres=0.1)
+        sw = (int(b[0]), int(b[2]), int(b[1]), int(b[3]))
+    out["chan_perm"] = np.zeros(0, np.int64)
+    if crop in ("content", "both"):
+        b = ref.cn_rand_bbox(x.shape, beta=1, bbx_thres=0.1)
+        cw = (int(b[0]), int(b[2]), int(b[1]), int(b[3]))
+    out["style_window"] = np.array(sw)
+    out["content_window"] = np.array(cw)
+    return out
+
+
 def stats_case(shape, seed, eps):
     x = varied_input(shape, seed=seed, dtype=np.float32, relu=True)
     out = {"x": x, "eps": np.array(eps)}
@@ -170,13 +225,18 @@ def main():
     cases["crossnorm_cfg2small_bf16"] = crossnorm_case((8, 4, 32, 32), 70, "neither", False, None, "bf16")
     cases["crossnorm_both_7x7"] = crossnorm_case((8, 16, 7, 7), 80, "both", False, None)
     cases["crossnorm_both_bf16"] = crossnorm_case((8, 8, 16, 16), 90, "both", False, None, "bf16")
+    for crop in ("neither", "style", "content", "both"):
+        cases[f"site_{crop}"] = site_case((8, 6, 12, 8), 200 + len(crop), crop)
     cases["stats_eps1e-5"] = stats_case((5, 9, 11, 13), 20, 1e-5)
     cases["stats_eps1e-12"] = stats_case((4, 8, 56, 56), 21, 1e-12)
     cases["rng_stream"] = rng_stream_case(1, [((128, 32, 32, 32), "both"), ((128, 64, 16, 16), "both"),
                                               ((128, 128, 8, 8), "style"), ((64, 3, 224, 224), "content"),
                                               ((16, 8, 7, 7), "both"), ((16, 8, 9, 5), "neither")])
     total = 0
+    only = sys.argv[1] if len(sys.argv) > 1 else ""       # optional name prefix: regenerate a subset
     for name, d in cases.items():
+        if not name.startswith(only):
+            continue
         path = os.path.join(HERE, name + ".npz")
         np.savez_compressed(path, **d)
         total += os.path.getsize(path)

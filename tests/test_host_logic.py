@@ -138,7 +138,76 @@ def test_cnsn_composition(mod):
     assert mod._fake.calls == ["selfnorm_fwd"]          # inactive CrossNorm is not even called (cnsn.py:160)
     cn.active = True
     blk(x)
-    assert mod._fake.calls[1:] == ["crossnorm_fwd", "selfnorm_fwd"] and cn.active is False
+    assert mod._fake.calls[1:] == ["site_fwd"] and cn.active is False       # both fire: one fused call (8f-2)
+    cn.active = True
+    mod.CNSN.fuse_site = False
+    try:
+        blk(x)
+    finally:
+        mod.CNSN.fuse_site = True
+    assert mod._fake.calls[2:] == ["crossnorm_fwd", "selfnorm_fwd"] and cn.active is False
+    cn.active = True
+    blk.eval()
+    assert blk(x) is not None and mod._fake.calls[4:] == ["selfnorm_fwd"] and cn.active is False   # eval: CN is a no-op
+
+
+@pytest.mark.parametrize("crop", ["neither", "style", "content", "both"])
+@pytest.mark.parametrize("tail", [None, "relu", "res+relu"])
+def test_cnsn_site_fusion_equals_two_operator_sequence(mod, crop, tail):
+    """When both operators fire, CNSN.forward takes ONE fused call per direction; values, gradients, parameter
+    gradients, running statistics, RNG consumption and the .active protocol equal the two-operator sequence."""
+    shape = (6, 4, 6, 4)
+    g = torch.Generator().manual_seed(11)
+    x0, r0, dy = (torch.randn(shape, generator=g, dtype=torch.float64) for _ in range(3))
+    res = []
+    for fused in (False, True):
+        mod.CNSN.fuse_site = fused
+        try:
+            torch.manual_seed(5)
+            np.random.seed(6)
+            blk = mod.CNSN(crossnorm=mod.CrossNorm(crop=crop, beta=1), selfnorm=mod.SelfNorm(4)).double().train()
+            blk.crossnorm.active = True
+            x, r = x0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+            n0 = len(mod._fake.calls)
+            if tail is None:
+                y = blk(x)
+            else:
+                y = blk(x, r if tail == "res+relu" else None, True)
+            y.backward(dy)
+        finally:
+            mod.CNSN.fuse_site = True
+        calls = mod._fake.calls[n0:]
+        assert ("site_fwd" in calls and "site_bwd" in calls) == fused and ("crossnorm_fwd" in calls) != fused
+        assert blk.crossnorm.active is False
+        res.append((y.detach(), x.grad, r.grad if tail == "res+relu" else x.grad, blk.selfnorm.g_fc.weight.grad,
+                    blk.selfnorm.g_bn.weight.grad, blk.selfnorm.g_bn.bias.grad, blk.selfnorm.g_bn.running_mean.clone(),
+                    blk.selfnorm.g_bn.running_var.clone(), blk.selfnorm.g_bn.num_batches_tracked.clone(),
+                    torch.rand(1), np.random.rand()))
+    for a, b in zip(*res):
+        assert np.allclose(np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64), atol=1e-12), (a, b)
+
+
+@pytest.mark.parametrize("name", H.golden_names("site_"))
+def test_cnsn_site_wiring_golden(mod, name):
+    """The reference's CNSN module with both operators firing (fixture from the unmodified reference): same seeds,
+    same draws, same outputs and gradients through the fused-site host path."""
+    g = H.golden(name)
+    params, bufs = H.sn_params_from_golden(g)
+    C = g["x"].shape[1]
+    sn = H.make_selfnorm(mod, C, params, bufs, "cpu").double()
+    blk = mod.CNSN(mod.CrossNorm(crop=str(g["crop"]), beta=1), sn).train()
+    blk.crossnorm.active = True
+    torch.manual_seed(int(g["torch_seed"]))
+    np.random.seed(int(g["numpy_seed"]))
+    x = torch.from_numpy(g["x"]).double().requires_grad_(True)
+    y = blk(x)
+    y.backward(torch.from_numpy(g["dy"]).double())
+    assert "site_fwd" in mod._fake.calls and "site_bwd" in mod._fake.calls
+    assert H.maxabs(y.detach().numpy(), g["y_f64"]) < 1e-9 and H.maxabs(x.grad.numpy(), g["dx_f64"]) < 1e-9
+    # the backend hands parameter gradients back as fp32 tensors (as the CUDA one does)
+    assert H.relmax(sn.g_fc.weight.grad.view(C, 2).numpy(), g["dg_w_f64"]) < 1e-6
+    assert H.relmax(sn.g_bn.weight.grad.numpy(), g["dg_gamma_f64"]) < 1e-6
+    assert H.maxabs(sn.g_bn.running_var.numpy(), g["g_rv_after_f64"]) < 1e-6
 
 
 @pytest.mark.parametrize("fire", [False, True])
@@ -241,7 +310,9 @@ def test_dropin_wideresnet_matches_reference(mod):
         out = net(x, aug=True)
         out.square().sum().backward()
         outs.append(out)
-    assert "crossnorm_fwd" in mod._fake.calls and "selfnorm_bwd" in mod._fake.calls
+    # both active sites take the fused CrossNorm -> SelfNorm call, the other sites the plain SelfNorm
+    assert mod._fake.calls.count("site_fwd") == 2 and mod._fake.calls.count("site_bwd") == 2
+    assert "selfnorm_bwd" in mod._fake.calls and "crossnorm_fwd" not in mod._fake.calls
     assert torch.allclose(outs[0], outs[1], atol=1e-8)
     for (ka, pa), (kb, pb) in zip(na.named_parameters(), nb.named_parameters()):
         assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka

@@ -45,6 +45,22 @@ def test_crossnorm_oracle_matches_reference_golden(name):
         assert np.array_equal(p2["chan_perm"], plan["chan_perm"])
 
 
+@pytest.mark.parametrize("name", H.golden_names("site_"))
+def test_site_oracle_matches_reference_golden(name):
+    """The reference's CNSN module with both operators firing (models/cnsn.py:159-164) pins the composed oracle
+    (the checker of the fused CrossNorm -> SelfNorm site kernels)."""
+    g = H.golden(name)
+    plan = H.plan_from_golden(g)
+    params, bufs = H.sn_params_from_golden(g)
+    y, _, nb = O.site_fwd(g["x"], plan, params, bufs)
+    dx, gr = O.site_bwd(g["x"], g["dy"], plan, params, bufs)
+    assert H.maxabs(y, g["y_f64"]) < TOL64 and H.maxabs(dx, g["dx_f64"]) < TOL64
+    for k in ("w", "gamma", "beta"):
+        assert H.relmax(gr["g_" + k], g[f"dg_{k}_f64"]) < 1e-8, k
+    assert H.maxabs(nb["g_rm"], g["g_rm_after_f64"]) < TOL64 and H.maxabs(nb["g_rv"], g["g_rv_after_f64"]) < TOL64
+    assert H.maxabs(g["y_f32"], y) < 1e-5 and H.maxabs(g["dx_f32"], dx) < 1e-5
+
+
 @pytest.mark.parametrize("name", H.golden_names("stats_"))
 def test_stats_oracle_matches_reference_golden(name):
     g = H.golden(name)
