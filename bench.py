@@ -19,6 +19,7 @@ One "step" = one forward + one backward pass of the hot path over one synthetic 
              to models/cnsn.py on CPU) timed on this box's host cores on a bounded sample
   crossnorm  secondary: CrossNorm fwd+bwd through cn_op_2ins_space_chan (BASELINE config 2, a WideResNet
              site with crops, a north-star-sized tensor)
+  site       secondary: a CNSN site with both operators firing, fused site kernels vs the two-operator sequence
   train      secondary: training-step images/s, DDP over NCCL when N>1: WideResNet-40-2 + CNSN (config 3),
              train.resnet50 = ResNet-50 + SN batch 256/GPU (config 4), train.resnet50_jsd = the 3-view JSD
              step in bf16 (config 5)
@@ -213,6 +214,50 @@ def bench_crossnorm(torch, M, dev, steps=30):
     return out
 
 
+def bench_site(torch, M, dev, steps=20):
+    """A CNSN site whose CrossNorm AND SelfNorm fire (models/cnsn.py:159-164) through CNSN.forward: the fused site
+    kernels (one launch per direction, 5*S algorithmic bytes) against this package's two-operator sequence, on a
+    WideResNet-40-2 site of BASELINE config 3 and on a north-star-sized tensor."""
+    import numpy as np
+    out = {}
+    for name, shape, dt, crop in (("wrn_512x32x32x32_f32_both", (512, 32, 32, 32), torch.float32, "both"),
+                                  ("large_256x256x56x56_f32_neither", (256, 256, 56, 56), torch.float32, "neither")):
+        N, C = shape[:2]
+        x = (torch.randn(shape, device=dev) * (0.5 + torch.rand(N, C, 1, 1, device=dev))).to(dt).requires_grad_(True)
+        dy = torch.randn(shape, device=dev).to(dt)
+        S = x.numel() * x.element_size()
+        blk = M.CNSN(M.CrossNorm(crop=crop, beta=1), M.SelfNorm(C)).to(dev).train()
+        torch.manual_seed(0)
+        np.random.seed(0)
+        res = {}
+        for fused in (True, False):
+            M.CNSN.fuse_site = fused
+            try:
+                for _ in range(3):
+                    blk.crossnorm.active = True
+                    torch.autograd.grad(blk(x), x, dy)
+                ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+                torch.cuda.synchronize()
+                for e in ev:
+                    blk.crossnorm.active = True
+                    e[0].record()
+                    y = blk(x)
+                    e[1].record()
+                    torch.autograd.grad(y, x, dy)
+                    e[2].record()
+                torch.cuda.synchronize()
+            finally:
+                M.CNSN.fuse_site = True
+            f = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2]
+            b = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2]
+            res["fused" if fused else "sequence"] = {"fwd_us": f * 1e3, "bwd_us": b * 1e3}
+        t1 = res["fused"]["fwd_us"] + res["fused"]["bwd_us"]
+        t0 = res["sequence"]["fwd_us"] + res["sequence"]["bwd_us"]
+        out[name] = dict(res, bytes_5S=5 * S, gbs=5 * S / (t1 * 1e-6) / 1e9, speedup_vs_sequence=t0 / t1)
+        del x, dy, blk
+    return out
+
+
 # ----------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -373,6 +418,14 @@ def main():
             crossnorm = {"error": repr(e)[:300]}
         torch.cuda.empty_cache()
 
+    site = None
+    if not args.no_crossnorm:
+        try:
+            site = bench_site(torch, M, dev)
+        except Exception as e:
+            site = {"error": repr(e)[:300]}
+        torch.cuda.empty_cache()
+
     # ---- secondary: WRN-40-2 + CNSN training step
     train = None
     if not args.no_train:
@@ -415,6 +468,7 @@ def main():
             "gpu_launches": launches,
             "cpu_baseline": cpu,
             "crossnorm": crossnorm,
+            "site": site,
             "train": train,
         }
         print(json.dumps(line), flush=True)
