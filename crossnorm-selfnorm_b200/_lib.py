@@ -73,7 +73,7 @@ SIGNATURES = {
     "cnsn_site_supported": (c_int, [c_int, *_DIMS]),
     "cnsn_site_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, POINTER(c_int), POINTER(c_int), c_float, c_float,
                               POINTER(GateParams), c_float, c_float, c_float, c_int, c_void_p, c_void_p]),
-    "cnsn_site_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, POINTER(c_int), POINTER(c_int), c_float, c_int,
+    "cnsn_site_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, POINTER(c_int), POINTER(c_int), c_float, c_float, c_int,
                               POINTER(GateParams), c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_crossnorm_save_floats": (c_size_t, [c_int, c_int]),
     "cnsn_crossnorm_workspace_floats": (c_size_t, [c_int, c_int]),
@@ -435,7 +435,7 @@ class CudaBackend:
             g.run_var.copy_(g_rv)
         return y, save
 
-    def site_bwd(self, x, dy, perm, cwin, swin, lam, g, save, relu=False):
+    def site_bwd(self, x, dy, perm, cwin, swin, lam, cn_eps, g, save, relu=False):
         _require_cuda(x, dy)
         N, C, H, W = x.shape
         keep = []
@@ -448,7 +448,8 @@ class CudaBackend:
         dx = torch.empty_like(x)
         with _on(dev):
             _check(lib().cnsn_site_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, _p(perm), _I4(*cwin), _I4(*swin),
-                                       lam, int(relu), ctypes.byref(gs), _p(save), ctypes.byref(gg), _p(ws), _stream(x)))
+                                       lam, cn_eps, int(relu), ctypes.byref(gs), _p(save), ctypes.byref(gg), _p(ws),
+                                       _stream(x)))
         return dx, out_g
 
 

@@ -16,12 +16,13 @@
 //     4. the channel's last ticket folds the N words (BatchNorm1d batch statistics, running statistics) and
 //        publishes the channel constants; everyone else polls them
 //     5. y = g * z (max(., 0) when the block's ReLU is fused in) out of shared memory, streamed out
-//   backward: x and dy resident
-//     1. z rebuilt on the fly from x and the saved statistics; sum dy*z -> sn[c][i]; channel fold (dgamma, dbeta,
-//        dw, the two batch-norm-backward scalars)
-//     2. dz = g*dy + b*(z - mu_z) + a IN PLACE of dy
-//     3. CrossNorm backward of (x, dz): S1, S2 over the content window scattered to cn[c][p(i)], poll cn[c][i],
-//        dx out of shared memory, streamed out
+//   backward: x and dy resident, TWO passes over shared memory in all
+//     1. one reduction pass over (x, dy): z is affine in x per region, so three sums (over the content window:
+//        d*(x - mu_c) and d; outside it: d*x) give SelfNorm's sum dy*z AND -- dz = g*dy + b*(z - mu_z) + a being
+//        affine in (dy, x) as well -- CrossNorm's S1, S2 in closed form; neither z nor dz is materialised
+//     2. sum dy*z -> sn[c][i]; channel fold (dgamma, dbeta, dw, the two batch-norm-backward scalars)
+//     3. S1, S2 scattered to cn[c][p(i)], poll cn[c][i]; dx = affine in (dy, x) per region out of shared memory,
+//        streamed out
 //
 // Training mode only (CrossNorm never fires in eval mode, models/cnsn.py:104).  Shapes outside the resident path
 // (planes that are not 16-byte multiples, channels too large for the GPU's shared memory, channel permutation,
@@ -44,11 +45,6 @@ struct SiteArgs {
     float* mu_c; float* sd_c; float* mu_s; float* sd_s;     // CrossNorm save block
     float2* pub_cn;         // [C][N] CrossNorm words, pre-filled with the sentinel
 };
-
-template <int TPI>
-__device__ __forceinline__ void team_sync() {
-    if (TPI <= 32) __syncwarp(); else __syncthreads();
-}
 
 // One 16-byte vector of the CrossNorm output: ca*x + cb inside the content window, x outside, rounded to T.
 template <typename T>
@@ -220,26 +216,53 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
             stg_stream(po + i, pack<T>(vo));
         }
     } else {
-        // ---- SelfNorm backward at z (rebuilt from x): sum dy*z, channel fold -------------------------------
+        // ---- ONE reduction pass over (x, dy) feeds both operators -----------------------------------------
+        // z is affine in x per region (ca*x + cb inside the content window, x outside), so with d = dy (masked where
+        // z <= 0 when the ReLU is fused in) three sums give everything the two backward passes need:
+        //   Ac = sum_cw d*(x - mu_c), Tc = sum_cw d, Po = sum_outside d*x
+        //   SelfNorm:  sum d*z = ca*(Ac + mu_c*Tc) + cb*Tc + Po
+        //   CrossNorm: dz = g*d + kb*z + kc is affine in (d, x) too, and over the content window sum (x - mu_c) = 0,
+        //              sum (x - mu_c)^2 = (Mc - 1)*(sd_c^2 - eps)  =>  sum_cw dz and sum_cw dz*(x - mu_c) in closed
+        //              form: dz is never materialised and there is no second reduction pass.
         const float A = sds_src / sdc;
         const float ca = lam + (1.f - lam) * A;
         const float cb = (1.f - lam) * (mus_src - muc * A);
-        float s0 = 0.f, s1 = 0.f;
+        float a0 = 0.f, a1 = 0.f, t0 = 0.f, t1 = 0.f, o0 = 0.f, o1 = 0.f;
         if (live) {
 #pragma unroll 4
             for (int i = r; i < nv; i += TPI) {
-                float vx[V], vd[V], vz[V];
+                float vx[V], vd[V];
                 unpack<T>(lds128(sx + 16u * i), vx);
                 unpack<T>(lds128(sdy + 16u * i), vd);
-                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
+                if (relu) {
+                    float vz[V];
+                    cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
 #pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const float d = (relu && !(vz[e] > 0.f)) ? 0.f : vd[e];
-                    if (e & 1) s1 = fmaf(d, vz[e], s1); else s0 = fmaf(d, vz[e], s0);
+                    for (int e = 0; e < V; ++e) vd[e] = vz[e] > 0.f ? vd[e] : 0.f;
+                }
+                if (cfull) {
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        if (e & 1) { a1 = fmaf(vd[e], vx[e] - muc, a1); t1 += vd[e]; } else { a0 = fmaf(vd[e], vx[e] - muc, a0); t0 += vd[e]; }
+                    }
+                } else {
+                    int h = (i * V) / W, w = i * V - h * W;
+#pragma unroll
+                    for (int e = 0; e < V; ++e) {
+                        if (cw.has(h, w)) {
+                            if (e & 1) { a1 = fmaf(vd[e], vx[e] - muc, a1); t1 += vd[e]; } else { a0 = fmaf(vd[e], vx[e] - muc, a0); t0 += vd[e]; }
+                        } else {
+                            if (e & 1) o1 = fmaf(vd[e], vx[e], o1); else o0 = fmaf(vd[e], vx[e], o0);
+                        }
+                        if (++w == W) { w = 0; ++h; }
+                    }
                 }
             }
         }
-        const float sxy = team_sum<TPI>(s0 + s1, s_f[0]);
+        const float Ac = team_sum<TPI>(a0 + a1, s_f[0]);
+        const float Tc = team_sum<TPI>(t0 + t1, s_f[1]);
+        const float Po = cfull ? 0.f : team_sum<TPI>(o0 + o1, s_f[2]);      // cfull is uniform over the grid
+        const float sxy = fmaf(ca, fmaf(muc, Tc, Ac), fmaf(cb, Tc, Po));
         const float own_x = sxy * pre_g * (1.f - pre_g), own_y = pre_s;
         if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
         if (folder) {
@@ -249,62 +272,48 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
             s_chan = poll_word(flag, a.poll_ns);
         }
         __syncthreads();
+        if (!live) return;
         const float2 cm = s_chan;
-        // ---- dz = kg*dy + kb*z + kc in place of dy (thread-private slots) -----------------------------------
+        // ---- dz = pre_g*d + kb*z + kc; CrossNorm's sums of it in closed form, pairwise exchange -----------------
         const float dsn = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
         const float kb = dsn * p_w1 * (1.f / (M - 1.f)) / p_sd;
         const float kc = dsn * p_w0 * (1.f / M) - kb * p_mu;
-        if (live) {
-#pragma unroll 4
-            for (int i = r; i < nv; i += TPI) {
-                float vx[V], vd[V], vz[V];
-                unpack<T>(lds128(sx + 16u * i), vx);
-                unpack<T>(lds128(sdy + 16u * i), vd);
-                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
-#pragma unroll
-                for (int e = 0; e < V; ++e) {
-                    const float d = (relu && !(vz[e] > 0.f)) ? 0.f : vd[e];
-                    vd[e] = fmaf(pre_g, d, fmaf(kb, vz[e], kc));
-                }
-                sts128(sdy + 16u * i, pack<T>(vd));
-            }
-        }
-        team_sync<TPI>();                                    // the window sums below read other threads' slots
-        // ---- CrossNorm backward of (x, dz): as crossnorm_flow.cu ---------------------------------------------
-        float t0 = 0.f, t1 = 0.f, a0 = 0.f, a1 = 0.f;
-        if (live) window_accumulate<T, true>(sx, sdy, W, M, cw, cfull, r, TPI, [&](float x, float d, int e) {
-            if (e & 1) { a1 = fmaf(d, x - muc, a1); t1 += d; } else { a0 = fmaf(d, x - muc, a0); t0 += d; }
-        });
-        const float asum = team_sum<TPI>(a0 + a1, s_f[2]);
-        const float tsum = team_sum<TPI>(t0 + t1, s_f[3]);
-        const float S1 = (1.f - lam) * tsum;
-        const float S2 = (1.f - lam) * asum / sdc;
-        if (live && r == 0) fused::ll_publish(s.pub_cn + (size_t)c * N + src_n, S1, S2);
-        if (!live) return;
-        const float2 ds = poll_word(s.pub_cn + (size_t)c * N + n, a.poll_ns);     // (dmu_s, dsd_s) of this instance
         const float Mc = (float)cw.area(), Ms = (float)sw.area();
-        // inside the content window: dx = p*dz + q*x + r0
+        const float zx = kb * ca, zc = fmaf(kb, cb, kc);      // inside the content window: dz = pre_g*d + zx*x + zc
+        const float sum_dz = fmaf(pre_g, Tc, Mc * fmaf(zx, muc, zc));
+        const float sum_dzx = fmaf(pre_g, Ac, zx * (Mc - 1.f) * (sdc * sdc - s.cn_eps));
+        const float S1 = (1.f - lam) * sum_dz;
+        const float S2 = (1.f - lam) * sum_dzx / sdc;
+        if (r == 0) fused::ll_publish(s.pub_cn + (size_t)c * N + src_n, S1, S2);
+        const float2 ds = poll_word(s.pub_cn + (size_t)c * N + n, a.poll_ns);     // (dmu_s, dsd_s) of this instance
+        // CrossNorm backward inside the content window: dx = p*dz + q*x + r0; as somebody's style source: += u*x + v
         const float p = lam + (1.f - lam) * A;
         const float q = -A * S2 / ((Mc - 1.f) * sdc);
         const float r0 = -A * S1 / Mc - q * muc;
-        // inside the style window (this instance as somebody's style source): dx += u*x + v
         const float u = ds.y / ((Ms - 1.f) * sds);
         const float v = ds.x / Ms - u * mus;
+        const float in_d = p * pre_g, in_x = fmaf(p, zx, q), in_c = fmaf(p, zc, r0);   // dx = in_d*d + in_x*x + in_c
         const bool both_full = cfull && sfull;
-        const float qq = q + u, rr = r0 + v;
+        const float bx = in_x + u, bc = in_c + v;
 #pragma unroll 4
         for (int i = r; i < nv; i += TPI) {
             float vx[V], vd[V], vo[V];
             unpack<T>(lds128(sx + 16u * i), vx);
             unpack<T>(lds128(sdy + 16u * i), vd);
+            if (relu) {
+                float vz[V];
+                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
+#pragma unroll
+                for (int e = 0; e < V; ++e) vd[e] = vz[e] > 0.f ? vd[e] : 0.f;
+            }
             if (both_full) {
 #pragma unroll
-                for (int e = 0; e < V; ++e) vo[e] = fmaf(p, vd[e], fmaf(qq, vx[e], rr));
+                for (int e = 0; e < V; ++e) vo[e] = fmaf(in_d, vd[e], fmaf(bx, vx[e], bc));
             } else {
                 int h = (i * V) / W, w = i * V - h * W;
 #pragma unroll
                 for (int e = 0; e < V; ++e) {
-                    float val = cw.has(h, w) ? fmaf(p, vd[e], fmaf(q, vx[e], r0)) : vd[e];
+                    float val = cw.has(h, w) ? fmaf(in_d, vd[e], fmaf(in_x, vx[e], in_c)) : fmaf(pre_g, vd[e], fmaf(kb, vx[e], kc));
                     if (sw.has(h, w)) val += fmaf(u, vx[e], v);
                     vo[e] = val;
                     if (++w == W) { w = 0; ++h; }
@@ -446,7 +455,7 @@ extern "C" int cnsn_site_fwd(const void* x, void* y, int dtype, int N, int C, in
 }
 
 extern "C" int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
-                             const int* perm, const int* content, const int* style, float lam, int relu,
+                             const int* perm, const int* content, const int* style, float lam, float cn_eps, int relu,
                              const cnsn_gate_params* g, const float* save, const cnsn_gate_grads* dg,
                              float* workspace, void* stream) {
     Window cw, sw;
@@ -463,7 +472,7 @@ extern "C" int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype,
     a.w = g->w; a.gamma = g->gamma;
     a.mu = sv + L.mu; a.sd = sv + L.sd; a.gate = sv + L.g; a.shat = sv + L.shat; a.r = sv + L.r;
     a.dw = dg->dw; a.dgamma = dg->dgamma; a.dbeta = dg->dbeta;
-    s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = 0.f; s.perm = perm;
+    s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = cn_eps; s.perm = perm;
     s.mu_c = sv + L.mu_c; s.sd_c = sv + L.sd_c; s.mu_s = sv + L.mu_s; s.sd_s = sv + L.sd_s;
     const int frc = flow::launch_site<true>(s, dtype, workspace, (cudaStream_t)stream, false);
     return frc == -100 ? CNSN_E_UNSUPPORTED : frc;

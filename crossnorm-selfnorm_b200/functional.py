@@ -143,15 +143,15 @@ class CnsnSiteFn(torch.autograd.Function):
         g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
         y, save = _lib.backend().site_fwd(x, perm, cwin, swin, lam, cn_eps, g, momentum, bn_eps, sn_eps, relu)
         ctx.save_for_backward(x, g_w, g_gamma, g_beta)
-        ctx.site = (perm, cwin, swin, lam, bool(relu), save)
+        ctx.site = (perm, cwin, swin, lam, cn_eps, bool(relu), save)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         x, g_w, g_gamma, g_beta = ctx.saved_tensors
-        perm, cwin, swin, lam, relu, save = ctx.site
+        perm, cwin, swin, lam, cn_eps, relu, save = ctx.site
         g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
-        dx, gg = _lib.backend().site_bwd(x, _dense(dy), perm, cwin, swin, lam, g, save, relu)
+        dx, gg = _lib.backend().site_bwd(x, _dense(dy), perm, cwin, swin, lam, cn_eps, g, save, relu)
         return (dx, None, None, None, None, None, None, None, None, None, None,
                 gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype))
 

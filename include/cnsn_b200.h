@@ -218,7 +218,7 @@ int cnsn_site_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
                   const cnsn_gate_params* g, float momentum, float bn_eps, float sn_eps, int relu,
                   float* save, void* stream);
 int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
-                  const int* perm, const int* content, const int* style, float lam, int relu,
+                  const int* perm, const int* content, const int* style, float lam, float cn_eps, int relu,
                   const cnsn_gate_params* g, const float* save, const cnsn_gate_grads* dg,
                   float* workspace, void* stream);
 

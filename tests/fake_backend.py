@@ -141,9 +141,9 @@ class OracleBackend:
         self.calls.pop()
         return (torch.relu(y) if relu else y), save
 
-    def site_bwd(self, x, dy, perm, cwin, swin, lam, g, save, relu=False):
+    def site_bwd(self, x, dy, perm, cwin, swin, lam, cn_eps, g, save, relu=False):
         self.calls.append("site_bwd")
-        z, _ = self.crossnorm_fwd(x, perm, None, cwin, swin, lam, 1e-5)
+        z, _ = self.crossnorm_fwd(x, perm, None, cwin, swin, lam, cn_eps)
         d = torch.where(z > 0, dy, torch.zeros_like(dy)) if relu else dy
         dz, gg, _ = self.selfnorm_bwd(z, d, g, None, True, save)
         dx = self.crossnorm_bwd(x, dz, perm, None, cwin, swin, lam, None)

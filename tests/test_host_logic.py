@@ -318,3 +318,48 @@ def test_dropin_wideresnet_matches_reference(mod):
         assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
     for (ka, ba), (kb, bb) in zip(na.named_buffers(), nb.named_buffers()):
         assert torch.allclose(ba.double(), bb.double(), atol=1e-9), ka
+
+
+@pytest.mark.parametrize("host,ctor,kw,xshape", [
+    ("models.cifar.resnext_cnsn", "CifarResNeXt",
+     dict(depth=11, cardinality=2, base_width=8, num_classes=10, active_num=2, pos="post", beta=1, crop="both",
+          cnsn_type="cnsn"), (4, 3, 32, 32)),
+    ("models.imagenet.resnet_cnsn", "ResNet",
+     # crop='neither': at 64x64 input the last stage has 2x2 planes, where the reference's box sampler never accepts
+     dict(layers=[1, 1, 1, 1], num_classes=7, active_num=2, pos="post", beta=1, crop="neither", cnsn_type="cnsn"),
+     (4, 3, 64, 64)),
+    ("models.imagenet.resnet_cnsn", "ResNet",
+     dict(layers=[1, 1, 1, 1], num_classes=7, active_num=1, pos="post", beta=1, crop="neither", cnsn_type="sn"),
+     (4, 3, 64, 64)),
+])
+def test_dropin_other_reference_hosts(mod, host, ctor, kw, xshape):
+    """The other callers SURVEY.md 8b lists -- the reference's unmodified CIFAR ResNeXt and ImageNet ResNet files --
+    with `models.cnsn` swapped for this package: same seeds -> same active sites and draws, logits, gradients and
+    buffers equal to the unmodified reference's."""
+    ref = load_reference_cnsn()
+    if ref is None:
+        pytest.skip("reference checkout not present")
+    ours = _reference_host(host, mod)
+    theirs = _reference_host(host, ref)
+    torch.manual_seed(0)
+    na = getattr(theirs, ctor)(**kw).double().train()
+    torch.manual_seed(0)
+    nb = getattr(ours, ctor)(**kw).double().train()
+    assert list(na.state_dict().keys()) == list(nb.state_dict().keys())
+    nb.load_state_dict(na.state_dict())
+    x = torch.randn(*xshape, dtype=torch.float64)
+    outs = []
+    for net in (na, nb):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        out = net(x, aug=kw["cnsn_type"] == "cnsn")      # 'sn' hosts have no feature-space CrossNorm (imagenet.py:215)
+        out.square().sum().backward()
+        outs.append(out)
+    if kw["cnsn_type"] == "cnsn":
+        assert mod._fake.calls.count("site_fwd") == kw["active_num"] == mod._fake.calls.count("site_bwd")
+    assert "selfnorm_fwd" in mod._fake.calls and "selfnorm_bwd" in mod._fake.calls
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(na.named_parameters(), nb.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+    for (ka, ba), (kb, bb) in zip(na.named_buffers(), nb.named_buffers()):
+        assert torch.allclose(ba.double(), bb.double(), atol=1e-9), ka
