@@ -11,8 +11,10 @@
 //   forward  CTA(ticket t): channel c = t / nI, instances j*I .. j*I+I-1
 //     1. cp.async.bulk the planes of x into shared memory                                   (TMA)
 //     2. (mu, sd) over the content and the style window; publish the style pair at cn[c][i]; poll cn[c][p(i)]
-//     3. z = CrossNorm(x) IN PLACE in shared memory (rounded to T, exactly what the unfused sequence stores);
-//        exact two-pass (mu_z, sd_z) of the whole plane; publish at sn[c][i]
+//     3. (mu_z, sd_z) of z = CrossNorm(x); publish at sn[c][i].  Whole-plane content window (crop 'neither' /
+//        'style'): z = ca*x + cb everywhere, so the statistics follow from the content statistics -- no pass, z is
+//        not materialised.  Cropped content window: z IN PLACE in shared memory (rounded to T, exactly what the
+//        unfused sequence stores), exact two-pass over the plane
 //     4. the channel's last ticket folds the N words (BatchNorm1d batch statistics, running statistics) and
 //        publishes the channel constants; everyone else polls them
 //     5. y = g * z (max(., 0) when the block's ReLU is fused in) out of shared memory, streamed out
@@ -20,9 +22,11 @@
 //     1. one reduction pass over (x, dy): z is affine in x per region, so three sums (over the content window:
 //        d*(x - mu_c) and d; outside it: d*x) give SelfNorm's sum dy*z AND -- dz = g*dy + b*(z - mu_z) + a being
 //        affine in (dy, x) as well -- CrossNorm's S1, S2 in closed form; neither z nor dz is materialised
-//     2. sum dy*z -> sn[c][i]; channel fold (dgamma, dbeta, dw, the two batch-norm-backward scalars)
-//     3. S1, S2 scattered to cn[c][p(i)], poll cn[c][i]; dx = affine in (dy, x) per region out of shared memory,
-//        streamed out
+//     2. CrossNorm's (S1, S2) are affine in the channel constants (k1, k2) SelfNorm's fold is about to produce:
+//        their three coefficient words go to cn[c][p(i)][0..2] and sum dy*z to sn[c][i] BEFORE anybody waits
+//     3. channel fold (dgamma, dbeta, dw, the two batch-norm-backward scalars) -- the item's only wait
+//     4. (k1, k2) known: S1, S2 of this instance and of the instance it is the style source of; dx = affine in
+//        (dy, x) per region out of shared memory, streamed out
 //
 // Training mode only (CrossNorm never fires in eval mode, models/cnsn.py:104).  Shapes outside the resident path
 // (planes that are not 16-byte multiples, channels too large for the GPU's shared memory, channel permutation,
@@ -43,7 +47,7 @@ struct SiteArgs {
     float lam, cn_eps;
     const int* perm;        // [N] style source of every sample
     float* mu_c; float* sd_c; float* mu_s; float* sd_s;     // CrossNorm save block
-    float2* pub_cn;         // [C][N] CrossNorm words, pre-filled with the sentinel
+    float2* pub_cn;         // CrossNorm words, pre-filled with the sentinel: forward [C][N], backward [C][N][3]
 };
 
 // One 16-byte vector of the CrossNorm output: ca*x + cb inside the content window, x outside, rounded to T.
@@ -66,7 +70,7 @@ __device__ __forceinline__ void cn_vec(const float (&vx)[VecOf<T>::n], float (&v
 }
 
 template <typename T, bool BWD, int TPI>
-__global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
+__global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
     constexpr int TH = kSiteT;
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
@@ -161,32 +165,41 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
             ca = lam + (1.f - lam) * A;
             cb = (1.f - lam) * (ps.x - stc.x * A);
         }
-        // ---- z = CrossNorm(x) in place (thread-private slots), SelfNorm statistics of z --------------------
-        float s0 = 0.f, s1 = 0.f;
-        if (live) {
+        // ---- SelfNorm statistics of z = CrossNorm(x) ----------------------------------------------------------
+        float own_x, own_y;
+        if (cfull) {
+            // whole-plane content window: z = ca*x + cb everywhere, so its statistics follow from the content
+            // statistics (mean ca*mu_c + cb, unbiased variance ca^2 * (sd_c^2 - eps_c)): no pass, z is not materialised
+            own_x = fmaf(ca, stc.x, cb);
+            own_y = sqrtf(fmaf(ca * ca, fmaxf(stc.y * stc.y - s.cn_eps, 0.f), a.eps));
+        } else {
+            // z in place (thread-private slots, rounded to T as the two-operator sequence stores it), exact two-pass
+            float s0 = 0.f, s1 = 0.f;
+            if (live) {
 #pragma unroll 4
-            for (int i = r; i < nv; i += TPI) {
-                float vx[V], vz[V];
-                unpack<T>(lds128(sx + 16u * i), vx);
-                cn_vec<T>(vx, vz, i, W, cw, cfull, ca, cb);
-                sts128(sx + 16u * i, pack<T>(vz));
+                for (int i = r; i < nv; i += TPI) {
+                    float vx[V], vz[V];
+                    unpack<T>(lds128(sx + 16u * i), vx);
+                    cn_vec<T>(vx, vz, i, W, cw, false, ca, cb);
+                    sts128(sx + 16u * i, pack<T>(vz));
 #pragma unroll
-                for (int e = 0; e < V; ++e) { if (e & 1) s1 += vz[e]; else s0 += vz[e]; }
+                    for (int e = 0; e < V; ++e) { if (e & 1) s1 += vz[e]; else s0 += vz[e]; }
+                }
             }
-        }
-        const float mean = team_sum<TPI>(s0 + s1, s_f[0]) * (1.f / M);
-        s0 = s1 = 0.f;
-        if (live) {
+            const float mean = team_sum<TPI>(s0 + s1, s_f[0]) * (1.f / M);
+            s0 = s1 = 0.f;
+            if (live) {
 #pragma unroll 4
-            for (int i = r; i < nv; i += TPI) {
-                float vz[V];
-                unpack<T>(lds128(sx + 16u * i), vz);
+                for (int i = r; i < nv; i += TPI) {
+                    float vz[V];
+                    unpack<T>(lds128(sx + 16u * i), vz);
 #pragma unroll
-                for (int e = 0; e < V; ++e) { const float d = vz[e] - mean; if (e & 1) s1 = fmaf(d, d, s1); else s0 = fmaf(d, d, s0); }
+                    for (int e = 0; e < V; ++e) { const float d = vz[e] - mean; if (e & 1) s1 = fmaf(d, d, s1); else s0 = fmaf(d, d, s0); }
+                }
             }
+            const float m2 = team_sum<TPI>(s0 + s1, s_f[1]);
+            own_x = mean; own_y = sqrtf(m2 / (M - 1.f) + a.eps);
         }
-        const float m2 = team_sum<TPI>(s0 + s1, s_f[1]);
-        const float own_x = mean, own_y = sqrtf(m2 / (M - 1.f) + a.eps);
         if (live && r == 0) {
             a.mu[nc] = own_x; a.sd[nc] = own_y;
             fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
@@ -204,13 +217,14 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
         const float sh = (fmaf(p_w0, own_x, p_w1 * own_y) - cm.x) * cm.y;
         const float gt = 1.f / (1.f + expf(-fmaf(p_ga, sh, p_b)));
         if (r == 0) { a.gate[nc] = gt; a.shat[nc] = sh; }
+        const float ya = cfull ? gt * ca : gt, yb = cfull ? gt * cb : 0.f;     // cfull: shared memory still holds x
 #pragma unroll 4
         for (int i = r; i < nv; i += TPI) {
             float vz[V], vo[V];
             unpack<T>(lds128(sx + 16u * i), vz);
 #pragma unroll
             for (int e = 0; e < V; ++e) {
-                const float y = fmaf(gt, vz[e], 0.f);
+                const float y = fmaf(ya, vz[e], yb);
                 vo[e] = relu ? fmaxf(y, 0.f) : y;
             }
             stg_stream(po + i, pack<T>(vo));
@@ -264,7 +278,27 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
         const float Po = cfull ? 0.f : team_sum<TPI>(o0 + o1, s_f[2]);      // cfull is uniform over the grid
         const float sxy = fmaf(ca, fmaf(muc, Tc, Ac), fmaf(cb, Tc, Po));
         const float own_x = sxy * pre_g * (1.f - pre_g), own_y = pre_s;
-        if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+        // SelfNorm's ds = p_b*(own_x*gamma - k1 - own_y*k2) is affine in the channel constants (k1, k2), hence so are
+        // dz = pre_g*d + kb*z + kc (kb = ds*KB, kc = ds*KC) and CrossNorm's sums of it over the content window:
+        //   sum dz = pre_g*Tc + ds*E1,  sum dz*(x - mu_c) = pre_g*Ac + ds*E2
+        // (sum_cw (x - mu_c) = 0, sum_cw (x - mu_c)^2 = (Mc - 1)*(sd_c^2 - eps): dz is never materialised).  So
+        // (S1, S2) = w0 + w1*k1 + w2*k2 with three words known NOW: they are handed to the style source before anybody
+        // waits, and the only wait of the item is the channel fold -- no second exchange behind it.
+        const float Mc = (float)cw.area(), Ms = (float)sw.area();
+        const float KB = p_w1 * (1.f / (M - 1.f)) / p_sd;
+        const float KC = p_w0 * (1.f / M) - KB * p_mu;
+        const float E1 = Mc * fmaf(KB, fmaf(ca, muc, cb), KC);
+        const float E2 = KB * ca * (Mc - 1.f) * (sdc * sdc - s.cn_eps);
+        const float l1 = 1.f - lam, l2 = (1.f - lam) / sdc;
+        const float base1 = pre_g * Tc, base2 = pre_g * Ac;
+        if (live && r == 0) {
+            const float D0 = p_b * own_x * p_ga, D1 = -p_b, D2 = -p_b * own_y;
+            float2* wp = s.pub_cn + ((size_t)c * N + src_n) * 3;
+            fused::ll_publish(wp, l1 * fmaf(D0, E1, base1), l2 * fmaf(D0, E2, base2));
+            fused::ll_publish(wp + 1, l1 * D1 * E1, l2 * D1 * E2);
+            fused::ll_publish(wp + 2, l1 * D2 * E1, l2 * D2 * E2);
+            fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+        }
         if (folder) {
             const float2 cst = fold_publish<true, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
             if (threadIdx.x == 0) s_chan = cst;
@@ -274,18 +308,15 @@ __global__ void __launch_bounds__(kSiteT) k_site_res(const SiteArgs s) {
         __syncthreads();
         if (!live) return;
         const float2 cm = s_chan;
-        // ---- dz = pre_g*d + kb*z + kc; CrossNorm's sums of it in closed form, pairwise exchange -----------------
         const float dsn = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
-        const float kb = dsn * p_w1 * (1.f / (M - 1.f)) / p_sd;
-        const float kc = dsn * p_w0 * (1.f / M) - kb * p_mu;
-        const float Mc = (float)cw.area(), Ms = (float)sw.area();
+        const float kb = dsn * KB, kc = dsn * KC;
         const float zx = kb * ca, zc = fmaf(kb, cb, kc);      // inside the content window: dz = pre_g*d + zx*x + zc
-        const float sum_dz = fmaf(pre_g, Tc, Mc * fmaf(zx, muc, zc));
-        const float sum_dzx = fmaf(pre_g, Ac, zx * (Mc - 1.f) * (sdc * sdc - s.cn_eps));
-        const float S1 = (1.f - lam) * sum_dz;
-        const float S2 = (1.f - lam) * sum_dzx / sdc;
-        if (r == 0) fused::ll_publish(s.pub_cn + (size_t)c * N + src_n, S1, S2);
-        const float2 ds = poll_word(s.pub_cn + (size_t)c * N + n, a.poll_ns);     // (dmu_s, dsd_s) of this instance
+        const float S1 = l1 * fmaf(dsn, E1, base1);
+        const float S2 = l2 * fmaf(dsn, E2, base2);
+        // this instance as somebody's style source: that instance's three words (published before its own wait)
+        const float2* wq = s.pub_cn + ((size_t)c * N + n) * 3;
+        const float2 q0 = poll_word(wq, a.poll_ns), q1 = poll_word(wq + 1, a.poll_ns), q2 = poll_word(wq + 2, a.poll_ns);
+        const float2 ds = make_float2(fmaf(q2.x, cm.y, fmaf(q1.x, cm.x, q0.x)), fmaf(q2.y, cm.y, fmaf(q1.y, cm.x, q0.y)));
         // CrossNorm backward inside the content window: dx = p*dz + q*x + r0; as somebody's style source: += u*x + v
         const float p = lam + (1.f - lam) * A;
         const float q = -A * S2 / ((Mc - 1.f) * sdc);
@@ -358,12 +389,13 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
     a.order = env_int("CNSN_FLOW_ORDER", 0);
     a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
     a.items = (unsigned)((unsigned long long)C * g.nI);
-    // scratch: sn words [C][N] | channel words [C] x 4 (one 32-byte sector each) | ticket | cn words [C][N]; all 0xff
+    // scratch: sn words [C][N] | channel words [C] x 4 (one 32-byte sector each) | ticket | cn words [C][N] (forward)
+    // or [C][N][3] (backward); all 0xff
     a.pub = reinterpret_cast<float2*>(scratch);
     a.chan = a.pub + (size_t)N * C;
     a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
     s.pub_cn = a.chan + 4 * (size_t)C + 1;
-    const size_t fill_bytes = (2 * (size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
+    const size_t fill_bytes = ((BWD ? 4 : 2) * (size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
     const dim3 grid(a.items), block(kSiteT);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
@@ -390,7 +422,8 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
     return launch_status();
 }
 
-static size_t site_scratch_floats(int N, int C) { return 4 * (size_t)N * C + 8 * (size_t)C + 8; }
+// sn words [C][N] | channel words [C] x 4 | ticket | cn words [C][N] x 3 (backward; forward uses one per instance)
+static size_t site_scratch_floats(int N, int C) { return 8 * (size_t)N * C + 8 * (size_t)C + 8; }
 
 struct SiteSave {             // offsets (in floats) into the save block
     size_t mu_c, sd_c, mu_s, sd_s, mu, sd, g, shat, r, scratch, total;

@@ -1,7 +1,7 @@
 """Timing of a CNSN site whose CrossNorm and SelfNorm both fire: the fused site kernels (cnsn_site_fwd/_bwd)
 against this package's two-operator sequence, through the module API (CUDA events; median of `steps`).
 
-    python tools/perf_site.py [steps]
+    python tools/perf_site.py [steps] [case indices, e.g. 0,4]
 
 Algorithmic bytes of the fused site: 2*S forward + 3*S backward; the sequence moves 4*S + 6*S."""
 import os
@@ -75,6 +75,8 @@ def cabi(x, dy, sn, crop):
     return f1, b1, f0, b0
 
 
+if len(sys.argv) > 2:                                 # optional: comma-separated case indices
+    CASES = [CASES[int(i)] for i in sys.argv[2].split(",")]
 for shape, dt, crop in CASES:
     torch.manual_seed(0)
     np.random.seed(0)
