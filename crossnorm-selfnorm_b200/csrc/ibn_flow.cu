@@ -275,7 +275,9 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         auto fn = k_ibn_res<T, BWD, TPI_>;                                                               \
         e = prepare_kernel(fn, kIbnT, dsmem, &per_sm);                                                   \
         if (e != cudaSuccess) return (int)e;                                                             \
-        if ((long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;   /* a channel must be co-resident */ \
+        /* a channel must be co-resident when its items wait for each other (training-mode batch-norm channels); */ \
+        /* instance-norm channels never wait (their folder only collects words of earlier tickets) */          \
+        if (a.half < C && a.training && (long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;    \
         a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);                                        \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \

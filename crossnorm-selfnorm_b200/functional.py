@@ -189,5 +189,6 @@ class IbnFn(torch.autograd.Function):
         x, in_w, bn_w = ctx.saved_tensors
         half, training, save = ctx.ibn
         dx, g = _lib.backend().ibn_bwd(x, _dense(dy), half, {"in_w": in_w, "bn_w": bn_w}, training, save)
-        return (dx, None, None, None, None, None, None,
-                g[0].to(in_w.dtype), g[1].to(in_w.dtype), g[2].to(bn_w.dtype), g[3].to(bn_w.dtype))
+        gi = (g[0].to(in_w.dtype), g[1].to(in_w.dtype)) if in_w is not None else (None, None)
+        gb = (g[2].to(bn_w.dtype), g[3].to(bn_w.dtype)) if bn_w is not None else (None, None)   # half == C: no BN half
+        return (dx, None, None, None, None, None, None) + gi + gb

@@ -29,7 +29,7 @@ class Bottleneck(nn.Module):
 
     def __init__(self, cin, planes, stride, shortcut, pos, beta, crop, cnsn_type, ops, fuse_post, ibn=None, ibn_host=False):
         super().__init__()
-        assert ibn in (None, "a"), "IBN-b (instance norm after the residual add) is not built"
+        assert ibn in (None, "a", "b")
         cout = planes * _EXPANSION
         self.ibn_variant = bool(ibn_host)                # wiring of resnet_ibn_cnsn.py (every block of that host)
         self.conv1 = nn.Conv2d(cin, planes, 1, bias=False)
@@ -42,12 +42,20 @@ class Bottleneck(nn.Module):
         self.bn2 = nn.BatchNorm2d(planes)
         self.conv3 = nn.Conv2d(planes, cout, 1, bias=False)
         self.bn3 = nn.BatchNorm2d(cout)
+        if ibn == "b":                                   # IBN-b: instance norm after the residual add (:62, :122-123)
+            from ..ibn import InstanceNorm2d
+            self.IN = InstanceNorm2d(cout, affine=True)
+        else:
+            self.IN = None
         self.relu = nn.ReLU(inplace=True)
         self.downsample = shortcut
         self.stride = stride
         self.pos = pos
         self.fuse_post = bool(fuse_post) and pos == "post"
-        if cnsn_type is not None:                         # None: CrossNorm lives in image space only
+        self.cnsn = None
+        if self.IN is not None and pos == "post":         # the instance norm takes the 'post' site's place (:67-68)
+            self.fuse_post = False
+        elif cnsn_type is not None:                       # None: CrossNorm lives in image space only
             assert cnsn_type in ("sn", "cn", "cnsn")
             assert pos in _POSITIONS
             cross = ops.CrossNorm(crop=crop, beta=beta) if "cn" in cnsn_type else None
@@ -69,7 +77,9 @@ class Bottleneck(nn.Module):
         if self.fuse_post:
             return self.cnsn(h, skip, True)               # relu(cnsn(h + skip)) in one kernel pair
         h = h + skip
-        if self.pos == "post":
+        if self.IN is not None:
+            h = self.IN(h)
+        elif self.pos == "post":
             h = self.cnsn(h)
         return self.relu(h)
 
@@ -80,7 +90,11 @@ class ResNet(nn.Module):
         super().__init__()
         ops = ops or _default_ops()
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
-        self.bn1 = nn.BatchNorm2d(64)
+        if ibn_cfg[0] == "b":                             # IBN-b stem (resnet_ibn_cnsn.py:143-144)
+            from ..ibn import InstanceNorm2d
+            self.bn1 = InstanceNorm2d(64, affine=True)
+        else:
+            self.bn1 = nn.BatchNorm2d(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post,
@@ -96,7 +110,10 @@ class ResNet(nn.Module):
                 if b == 0 and (s != 1 or width != planes * _EXPANSION):
                     shortcut = nn.Sequential(nn.Conv2d(width, planes * _EXPANSION, 1, s, bias=False),
                                              nn.BatchNorm2d(planes * _EXPANSION))
-                blocks.append(Bottleneck(width, planes, s, shortcut, ibn=ibn_cfg[i], **kw))
+                ibn = ibn_cfg[i]
+                if ibn == "b" and (b == 0 or b < count - 1):   # IBN-b: the last block of a stage, never its first (:204-214)
+                    ibn = None
+                blocks.append(Bottleneck(width, planes, s, shortcut, ibn=ibn, **kw))
                 width = planes * _EXPANSION
             stages.append(nn.Sequential(*blocks))
         self.layer1, self.layer2, self.layer3, self.layer4 = stages
@@ -143,3 +160,10 @@ def resnet50_ibn_a(active_num=1, pos="post", beta=1, crop="neither", cnsn_type="
     """ResNet-50-IBN-a + CNSN (models/imagenet/resnet_ibn_cnsn.py:262-275): IBN replaces bn1 in stages 1-3."""
     return ResNet([3, 4, 6, 3], active_num=active_num, pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type,
                   ibn_cfg=("a", "a", "a", None), **kw)
+
+
+def resnet50_ibn_b(active_num=1, pos="post", beta=1, crop="neither", cnsn_type="sn", **kw):
+    """ResNet-50-IBN-b + CNSN (the ibn_cfg=('b','b',None,None) variant of models/imagenet/resnet_ibn_cnsn.py):
+    instance norm in the stem and after the residual add of the last block of stages 1-2."""
+    return ResNet([3, 4, 6, 3], active_num=active_num, pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type,
+                  ibn_cfg=("b", "b", None, None), **kw)

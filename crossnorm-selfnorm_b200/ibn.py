@@ -10,7 +10,7 @@ import torch.nn as nn
 
 from .functional import IbnFn
 
-__all__ = ["IBN"]
+__all__ = ["IBN", "InstanceNorm2d"]
 
 
 class IBN(nn.Module):
@@ -27,3 +27,19 @@ class IBN(nn.Module):
         return IbnFn.apply(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps),
                            (bn.running_mean, bn.running_var, bn.num_batches_tracked),
                            self.IN.weight, self.IN.bias, bn.weight, bn.bias)
+
+
+class InstanceNorm2d(nn.InstanceNorm2d):
+    """``nn.InstanceNorm2d(C, affine=True)`` as the reference uses it for IBN-b -- after the residual add of the last
+    block of a stage and in the stem (``models/imagenet/resnet_ibn_cnsn.py:62,122-123,143-144``) -- through the same
+    kernels as ``IBN`` with every channel on the instance-norm side (``half = C``): one launch per direction.  Same
+    class hierarchy and ``state_dict`` keys (``weight``, ``bias``) as the torch module it replaces."""
+
+    def __init__(self, num_features, eps=1e-5, affine=True):
+        super().__init__(num_features, eps=eps, affine=True, track_running_stats=False)
+        assert affine, "the reference constructs InstanceNorm2d(C, affine=True)"
+
+    def forward(self, x):
+        assert x.dim() == 4 and x.size(1) == self.num_features
+        return IbnFn.apply(x, self.num_features, False, 0.1, float(self.eps), 1e-5, (None, None, None),
+                           self.weight, self.bias, None, None)

@@ -98,10 +98,12 @@ class OracleBackend:
 
     def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
         self.calls.append("ibn_fwd")
-        pp = {k: _np(p[k]) for k in ("in_w", "in_b", "bn_w", "bn_b")}
-        bufs = {"rm": _np(p["run_mean"]), "rv": _np(p["run_var"])}
+        e = np.zeros(0)                                      # half == C: no batch-norm half
+        pp = {k: (_np(p[k]) if p.get(k) is not None else e) for k in ("in_w", "in_b", "bn_w", "bn_b")}
+        bufs = {"rm": _np(p["run_mean"]) if p.get("run_mean") is not None else e,
+                "rv": _np(p["run_var"]) if p.get("run_var") is not None else e}
         y, rm, rv = IB.ibn_fwd(_np(x), half, pp, bufs, training, momentum, eps_in, eps_bn)
-        if training:
+        if training and p.get("run_mean") is not None:
             p["run_mean"].copy_(_t(rm, p["run_mean"]))
             p["run_var"].copy_(_t(rv, p["run_var"]))
             if p.get("nbt") is not None:
@@ -110,7 +112,7 @@ class OracleBackend:
 
     def ibn_bwd(self, x, dy, half, p, training, save):
         self.calls.append("ibn_bwd")
-        pp = {"in_w": _np(p["in_w"]), "bn_w": _np(p["bn_w"])}
+        pp = {"in_w": _np(p["in_w"]), "bn_w": _np(p["bn_w"]) if p.get("bn_w") is not None else np.zeros(0)}
         dx, a, b, c, d = IB.ibn_bwd(_np(x), _np(dy), half, pp, save["bufs"], training, *save["eps"])
         return _t(dx, x), tuple(_t(v, x, torch.float32) for v in (a, b, c, d))
 

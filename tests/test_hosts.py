@@ -109,6 +109,39 @@ def test_resnet_ibn_a_matches_reference_model(fake, pos, capsys):
         assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
 
 
+@pytest.mark.parametrize("pos,fuse", [("post", False), ("post", True), ("residual", False)])
+def test_resnet_ibn_b_matches_reference_model(fake, pos, fuse, capsys):
+    """ResNet-IBN-b wiring (instance norm in the stem and after the residual add of a stage's last block,
+    models/imagenet/resnet_ibn_cnsn.py:62,122-123,143-144,204-214) vs the reference file: identical state dict for
+    equal seeds, identical logits and gradients; the instance norms run through cnsn_ibn_* with half = C."""
+    from cnsn_b200.hosts import ResNet
+    from cnsn_b200.ibn import InstanceNorm2d
+    RefResNet = _reference_host("models.imagenet.resnet_ibn_cnsn", "ResNet")
+    kw = dict(num_classes=7, active_num=1, pos=pos, beta=1, crop="neither", cnsn_type="cnsn")
+    torch.manual_seed(0)
+    a = RefResNet(layers=[2, 2, 1, 1], ibn_cfg=("b", "b", None, None), **kw).double().train()
+    torch.manual_seed(0)
+    b = ResNet([2, 2, 1, 1], ibn_cfg=("b", "b", None, None), fuse_post=fuse, **kw).double().train()
+    capsys.readouterr()
+    assert isinstance(b.bn1, InstanceNorm2d) and b.layer1[0].IN is None and isinstance(b.layer1[1].IN, InstanceNorm2d)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    x = torch.randn(2, 3, 224, 224, dtype=torch.float64)      # the reference head is AvgPool2d(7): 224 x 224 input
+    outs = []
+    for net in (a, b):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        o = net(x, aug=True)
+        o.square().sum().backward()
+        outs.append(o)
+    assert fake.calls.count("ibn_fwd") == 3 and fake.calls.count("ibn_bwd") == 3     # stem + two stage tails
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+
+
 def test_resnet50_census():
     """ResNet-50 + SN ('post'): 16 SelfNorm sites with the channel counts of SURVEY.md 8 (cfg4)."""
     from cnsn_b200.hosts import resnet50

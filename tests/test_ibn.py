@@ -34,6 +34,12 @@ def _case(shape, seed):
     return x, dy, half, p, bufs
 
 
+def O_varied(shape, seed):
+    rs = np.random.RandomState(seed)
+    N, C = shape[:2]
+    return rs.standard_normal(shape) * (0.5 + rs.rand(N, C, 1, 1)) + rs.standard_normal((N, C, 1, 1))
+
+
 def _load(m, p, bufs):
     with torch.no_grad():
         m.IN.weight.copy_(torch.from_numpy(p["in_w"])); m.IN.bias.copy_(torch.from_numpy(p["in_b"]))
@@ -97,3 +103,69 @@ def test_ibn_kernel_vs_oracle(shape, dtype, training):
     assert np.allclose(m.BN.running_mean.double().cpu().numpy(), rm, atol=1e-5)
     assert np.allclose(m.BN.running_var.double().cpu().numpy(), rv, atol=1e-5, rtol=1e-5)
     assert int(m.BN.num_batches_tracked) == (1 if training else 0)
+
+
+def test_instance_norm_state_dict_and_cpu_semantics():
+    """cnsn_b200.ibn.InstanceNorm2d is an nn.InstanceNorm2d(C, affine=True) (isinstance, state dict); the oracle with
+    half = C equals torch's module (what the reference's IBN-b blocks call, resnet_ibn_cnsn.py:62,122-123)."""
+    from cnsn_b200.ibn import InstanceNorm2d
+    m = InstanceNorm2d(6, affine=True)
+    r = torch.nn.InstanceNorm2d(6, affine=True)
+    assert isinstance(m, torch.nn.InstanceNorm2d) and list(m.state_dict()) == list(r.state_dict()) == ["weight", "bias"]
+    rs = np.random.RandomState(0)
+    x, dy = rs.standard_normal((3, 6, 5, 4)), rs.standard_normal((3, 6, 5, 4))
+    p = {"in_w": rs.uniform(0.5, 1.5, 6), "in_b": rs.uniform(-0.5, 0.5, 6), "bn_w": np.zeros(0), "bn_b": np.zeros(0)}
+    bufs = {"rm": np.zeros(0), "rv": np.zeros(0)}
+    r = r.double()
+    with torch.no_grad():
+        r.weight.copy_(torch.from_numpy(p["in_w"]))
+        r.bias.copy_(torch.from_numpy(p["in_b"]))
+    xt = torch.from_numpy(x).requires_grad_(True)
+    y = r(xt)
+    y.backward(torch.from_numpy(dy))
+    yo, _, _ = B.ibn_fwd(x, 6, p, bufs, True)
+    dxo, giw, gib, _, _ = B.ibn_bwd(x, dy, 6, p, bufs, True)
+    assert np.abs(y.detach().numpy() - yo).max() < 1e-12 and np.abs(xt.grad.numpy() - dxo).max() < 1e-12
+    assert np.abs(r.weight.grad.numpy() - giw).max() < 1e-10 and np.abs(r.bias.grad.numpy() - gib).max() < 1e-10
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((8, 16, 8, 8), torch.float32), ((32, 64, 28, 28), torch.float32),
+                                         ((16, 8, 56, 56), torch.float32), ((33, 10, 12, 12), torch.float32),
+                                         ((32, 16, 16, 16), torch.bfloat16),
+                                         # the IBN-b stem plane (112 x 112) with more samples than CTAs fit the GPU at
+                                         # two planes per item: instance-norm channels need no co-residency
+                                         ((300, 2, 112, 112), torch.float32)])
+@pytest.mark.parametrize("training", [True, False])
+def test_instance_norm_kernel_vs_oracle(shape, dtype, training):
+    """IBN-b's instance norm: cnsn_ibn_fwd/_bwd with half = C (no batch-norm half) through cnsn_b200.ibn.InstanceNorm2d."""
+    import cnsn_b200
+    from cnsn_b200.ibn import InstanceNorm2d
+    C = shape[1]
+    rs = np.random.RandomState(sum(shape))
+    x = O_varied(shape, sum(shape) + 2)
+    dy = rs.standard_normal(shape)
+    if dtype != torch.float32:
+        x, dy = (torch.from_numpy(v).to(dtype).double().numpy() for v in (x, dy))
+    p = {"in_w": rs.uniform(0.5, 1.5, C).astype(np.float32).astype(np.float64),
+         "in_b": rs.uniform(-0.5, 0.5, C).astype(np.float32).astype(np.float64), "bn_w": np.zeros(0), "bn_b": np.zeros(0)}
+    bufs = {"rm": np.zeros(0), "rv": np.zeros(0)}
+    m = InstanceNorm2d(C, affine=True)
+    with torch.no_grad():
+        m.weight.copy_(torch.from_numpy(p["in_w"]))
+        m.bias.copy_(torch.from_numpy(p["in_b"]))
+    m = m.cuda().train(training)
+    xt = torch.from_numpy(x).to(device="cuda", dtype=dtype).requires_grad_(True)
+    n0 = cnsn_b200.launch_count()
+    y = m(xt)
+    y.backward(torch.from_numpy(dy).to(device="cuda", dtype=dtype))
+    torch.cuda.synchronize()
+    assert cnsn_b200.launch_count() - n0 == 2
+    yo, _, _ = B.ibn_fwd(x, C, p, bufs, training)
+    dxo, giw, gib, _, _ = B.ibn_bwd(x, dy, C, p, bufs, training)
+    atol, rtol = (1e-5, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    assert np.allclose(y.detach().double().cpu().numpy(), yo, atol=atol, rtol=rtol)
+    assert np.allclose(xt.grad.double().cpu().numpy(), dxo, atol=atol, rtol=rtol)
+    ptol = 1e-5 if dtype == torch.float32 else 1e-3
+    for a, b in ((m.weight.grad, giw), (m.bias.grad, gib)):
+        assert np.abs(a.double().cpu().numpy() - b).max() <= ptol * max(np.abs(b).max(), 1e-6)
