@@ -21,7 +21,7 @@ extern "C" const char* cnsn_error_string(int code) {
         case CNSN_E_WORKSPACE: return "cnsn: workspace too small";
         case CNSN_E_BATCH1: return "Expected more than 1 value per channel when training";
         case CNSN_E_ALIGN: return "cnsn: tensor pointer not aligned to its element size";
-        case CNSN_E_UNSUPPORTED: return "cnsn: shape not supported by this operator (IBN, fused site: planes must be multiples of 16 bytes and a channel must fit on chip)";
+        case CNSN_E_UNSUPPORTED: return "cnsn: shape not supported by this operator (fused site: planes must be multiples of 16 bytes and a channel must fit on chip)";
         default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t)code);

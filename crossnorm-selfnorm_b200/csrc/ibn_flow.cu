@@ -22,6 +22,7 @@
 #include <stdio.h>
 
 #include "flow_common.cuh"
+#include "ibn_general.cuh"
 
 namespace cnsn {
 namespace flow {
@@ -296,6 +297,17 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
 
 using namespace cnsn;
 
+static ibn_general::GArgs general_args(const flow::IArgs& a) {
+    ibn_general::GArgs g{};
+    g.x = a.x; g.dy = a.dy; g.out = a.out; g.N = a.N; g.C = a.C; g.M = a.M; g.half = a.half; g.training = a.training;
+    g.momentum = a.momentum; g.eps_in = a.eps_in; g.eps_bn = a.eps_bn;
+    g.in_w = a.in_w; g.in_b = a.in_b; g.bn_w = a.bn_w; g.bn_b = a.bn_b;
+    g.run_mean = a.run_mean; g.run_var = a.run_var; g.nbt = a.nbt;
+    g.in_mean = a.in_mean; g.in_rstd = a.in_rstd; g.bn_mean = a.bn_mean; g.bn_rstd = a.bn_rstd;
+    g.d_in_w = a.d_in_w; g.d_in_b = a.d_in_b; g.d_bn_w = a.d_bn_w; g.d_bn_b = a.d_bn_b;
+    return g;
+}
+
 // save: [in_mean N*half | in_rstd N*half | bn_mean C-half | bn_rstd C-half | pad | polled words (2*N*C + 8*C + 2)]
 static size_t ibn_stats_floats(int N, int C, int half) { return (2 * (size_t)N * half + 2 * (size_t)(C - half) + 1) & ~(size_t)1; }
 extern "C" size_t cnsn_ibn_save_floats(int N, int C, int half) { return ibn_stats_floats(N, C, half) + 2 * (size_t)N * C + 8 * (size_t)C + 8; }
@@ -316,7 +328,11 @@ extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int
     a.run_mean = p->run_mean; a.run_var = p->run_var; a.nbt = p->nbt;
     a.in_mean = save; a.in_rstd = save + (size_t)N * half;
     a.bn_mean = save + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
-    return flow::launch_ibn<false>(a, dtype, save + ibn_stats_floats(N, C, half), (cudaStream_t)stream);
+    float* scratch = save + ibn_stats_floats(N, C, half);
+    const int rc = flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream);
+    if (rc != CNSN_E_UNSUPPORTED) return rc;
+    ibn_general::GArgs g = general_args(a);          // odd / oversized planes: the three-kernel path
+    return ibn_general::ibn_general_fwd(g, dtype, scratch, (cudaStream_t)stream);
 }
 
 extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W, int half,
@@ -335,5 +351,8 @@ extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, 
     a.in_mean = sv; a.in_rstd = sv + (size_t)N * half;
     a.bn_mean = sv + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     a.d_in_w = d_in_w; a.d_in_b = d_in_b; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b;
-    return flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream);
+    const int rc = flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream);
+    if (rc != CNSN_E_UNSUPPORTED) return rc;
+    ibn_general::GArgs g = general_args(a);
+    return ibn_general::ibn_general_bwd(g, dtype, workspace, (cudaStream_t)stream);
 }

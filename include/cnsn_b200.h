@@ -40,8 +40,9 @@ enum {
     CNSN_E_WORKSPACE = -2,/* workspace too small */
     CNSN_E_BATCH1 = -3,   /* SelfNorm training with N == 1 (reference: BatchNorm1d ValueError) */
     CNSN_E_ALIGN = -4,    /* tensor base pointer not aligned to its element size */
-    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_ibn_*, cnsn_site_*: planes must
-                             be 16-byte multiples and a channel's N planes must fit the GPU's shared memory) */
+    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_site_*: planes must be 16-byte
+                             multiples and a channel's N planes must fit the GPU's shared memory; ask
+                             cnsn_site_supported() first) */
 };
 
 /* Library / ABI identification. */
@@ -229,8 +230,11 @@ int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int
  *   c <  half : y = (x - mean_nc) / sqrt(biased_var_nc + eps_in) * in_w[c] + in_b[c]          (always instance statistics)
  *   c >= half : y = (x - m_c) / sqrt(v_c + eps_bn) * bn_w[c-half] + bn_b[c-half]; training: batch statistics over
  *               (N,H,W), running_mean / running_var (unbiased) updated with `momentum`, nbt incremented; eval: running.
- * Planes must be multiples of 16 bytes (CNSN_E_BADARG otherwise).  save: cnsn_ibn_save_floats() floats, written by
- * forward, read by backward; workspace: cnsn_ibn_workspace_floats().  Parameter gradients are WRITTEN.
+ * half == C is a plain nn.InstanceNorm2d(C, affine=True) (the IBN-b blocks and stem, resnet_ibn_cnsn.py:62,122-123,
+ * 143-144; bn_* / run_* may be NULL), half == 0 a plain BatchNorm2d.  One resident kernel per direction when planes are
+ * multiples of 16 bytes and fit shared memory; every other shape takes three stream-ordered kernels per direction
+ * (same results).  save: cnsn_ibn_save_floats() floats, written by forward, read by backward; workspace:
+ * cnsn_ibn_workspace_floats().  Parameter gradients are WRITTEN.
  */
 typedef struct cnsn_ibn_params {
     const float* in_w;     /* (half)     IN.weight */

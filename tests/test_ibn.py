@@ -169,3 +169,58 @@ def test_instance_norm_kernel_vs_oracle(shape, dtype, training):
     ptol = 1e-5 if dtype == torch.float32 else 1e-3
     for a, b in ((m.weight.grad, giw), (m.bias.grad, gib)):
         assert np.abs(a.double().cpu().numpy() - b).max() <= ptol * max(np.abs(b).max(), 1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype,half", [((6, 8, 7, 7), torch.float32, 4), ((16, 8, 14, 14), torch.bfloat16, 4),
+                                              ((5, 6, 9, 14), torch.float32, 3), ((3, 4, 224, 224), torch.float32, 2),
+                                              ((6, 8, 7, 7), torch.float32, 8), ((33, 5, 7, 7), torch.float16, 2)])
+@pytest.mark.parametrize("training", [True, False])
+def test_ibn_general_path_vs_oracle(shape, dtype, half, training):
+    """Shapes outside the resident kernel -- planes that are not 16-byte multiples (7x7, 14x14 bf16, 9x14), planes
+    too large for shared memory (224x224) -- take the three-kernel path (ibn_general.cu): same results, three
+    launches per direction, no CNSN_E_UNSUPPORTED."""
+    import cnsn_b200
+    from cnsn_b200 import _lib as L
+    N, C, H, W = shape
+    rs = np.random.RandomState(sum(shape) + half)
+    x = O_varied(shape, sum(shape) + 3)
+    dy = rs.standard_normal(shape)
+    if dtype != torch.float32:
+        x, dy = (torch.from_numpy(v).to(dtype).double().numpy() for v in (x, dy))
+
+    def f32(v):
+        return v.astype(np.float32).astype(np.float64)
+
+    p = {"in_w": f32(rs.uniform(0.5, 1.5, half)), "in_b": f32(rs.uniform(-0.5, 0.5, half)),
+         "bn_w": f32(rs.uniform(0.5, 1.5, C - half)), "bn_b": f32(rs.uniform(-0.5, 0.5, C - half))}
+    bufs = {"rm": f32(rs.uniform(-1, 1, C - half)), "rv": f32(rs.uniform(0.5, 2, C - half))}
+    dev = "cuda:0"
+
+    def t(v, dt=torch.float32):
+        return torch.from_numpy(v).to(device=dev, dtype=dt)
+
+    pt = {k: t(v) for k, v in p.items()}
+    pt.update(run_mean=t(bufs["rm"]), run_var=t(bufs["rv"]), nbt=torch.zeros((), dtype=torch.int64, device=dev))
+    if half == C:
+        pt.update(bn_w=None, bn_b=None, run_mean=None, run_var=None, nbt=None)
+    xt, dyt = t(x, dtype), t(dy, dtype)
+    be = L.backend()
+    n0 = cnsn_b200.launch_count()
+    y, save = be.ibn_fwd(xt, half, pt, training, 0.1, 1e-5, 1e-5)
+    dx, g = be.ibn_bwd(xt, dyt, half, pt, training, save)
+    torch.cuda.synchronize()
+    assert cnsn_b200.launch_count() - n0 == 6
+    yo, rm, rv = B.ibn_fwd(x, half, p, bufs, training)
+    dxo, giw, gib, gbw, gbb = B.ibn_bwd(x, dy, half, p, bufs, training)
+    atol, rtol = (1e-5, 1e-5) if dtype == torch.float32 else (2e-2, 1e-2)
+    assert np.allclose(y.double().cpu().numpy(), yo, atol=atol, rtol=rtol)
+    assert np.allclose(dx.double().cpu().numpy(), dxo, atol=atol, rtol=rtol)
+    ptol = 1e-5 if dtype == torch.float32 else 1e-3
+    for a, b in zip(g, (giw, gib, gbw, gbb)):
+        if b.size:
+            assert np.abs(a.double().cpu().numpy() - b).max() <= ptol * max(np.abs(b).max(), 1e-6)
+    if half < C:
+        assert np.allclose(pt["run_mean"].double().cpu().numpy(), rm, atol=1e-5)
+        assert np.allclose(pt["run_var"].double().cpu().numpy(), rv, atol=1e-5, rtol=1e-5)
+        assert int(pt["nbt"]) == (1 if training else 0)
