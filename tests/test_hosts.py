@@ -142,6 +142,39 @@ def test_resnet_ibn_b_matches_reference_model(fake, pos, fuse, capsys):
         assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
 
 
+@pytest.mark.parametrize("pos", ["post", "pre", "residual", "identity"])
+def test_resnext_matches_reference_model(fake, pos, capsys):
+    """CIFAR ResNeXt host vs models/cifar/resnext_cnsn.py: identical state dict for equal seeds; same inputs and host
+    RNG -> same logits and gradients (including the reference's post-ReLU 'post' site and the 'identity' quirk)."""
+    from cnsn_b200.hosts import CifarResNeXt
+    Ref = _reference_host("models.cifar.resnext_cnsn", "CifarResNeXt")
+    kw = dict(depth=20, cardinality=2, base_width=16, num_classes=10, active_num=2, pos=pos, beta=1, crop="both",
+              cnsn_type="cnsn")
+    torch.manual_seed(0)
+    a = Ref(**kw).double().train()
+    torch.manual_seed(0)
+    b = CifarResNeXt(**kw).double().train()
+    capsys.readouterr()
+    sa, sb = a.state_dict(), b.state_dict()
+    assert list(sa) == list(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    x = torch.randn(4, 3, 32, 32, dtype=torch.float64)
+    outs = []
+    for net in (a, b):
+        torch.manual_seed(5)
+        np.random.seed(6)
+        o = net(x, aug=True)
+        o.square().sum().backward()
+        outs.append(o)
+    assert fake.calls.count("site_fwd") == 2 and "selfnorm_bwd" in fake.calls
+    assert torch.allclose(outs[0], outs[1], atol=1e-8)
+    for (ka, pa), (kb, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert ka == kb and (pa.grad is None) == (pb.grad is None), ka     # 'identity': a projection block drops its site
+        if pa.grad is not None:
+            assert torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
+
+
 def test_resnet50_census():
     """ResNet-50 + SN ('post'): 16 SelfNorm sites with the channel counts of SURVEY.md 8 (cfg4)."""
     from cnsn_b200.hosts import resnet50
