@@ -10,7 +10,6 @@ decides whether this step's forward activates CrossNorm sites (``net(x, aug=True
 every step, as there.
 """
 import math
-import os
 
 import numpy as np
 import torch

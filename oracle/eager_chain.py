@@ -8,7 +8,6 @@ with explicit parameter tensors, and autograd differentiates it exactly as it do
 It is validated against the live reference in tests/test_oracle_vs_reference.py (bit-identical
 outputs on CPU) and is never imported by the product package.
 """
-import numpy as np
 import torch
 import torch.nn.functional as F
 

@@ -5,7 +5,6 @@ module set with the reference's surface, executing the reference's eager ATen op
 models in the product package can be run on CPU for the baseline without the product ever depending
 on this directory.
 """
-import numpy as np
 import torch
 import torch.nn as nn
 
