@@ -203,3 +203,42 @@ def test_site_c_abi_error_codes(mod):
     perm = torch.randperm(6).to(torch.int32).to(DEV)
     with pytest.raises(RuntimeError, match="not supported"):
         be.site_fwd(torch.randn(6, 4, 7, 7, device=DEV), perm, (0, 7, 0, 7), (0, 7, 0, 7), 0.0, 1e-5, g, 0.1, 1e-5, 1e-12)
+
+
+@pytest.mark.parametrize("shape,crop", [((16, 8, 8, 8), "both"), ((12, 4, 32, 32), "neither"), ((9, 6, 20, 20), "content"),
+                                        ((8, 4, 56, 56), "style")])
+@pytest.mark.parametrize("relu", [False, True])
+def test_site_lam_blend_vs_oracle(mod, shape, crop, relu):
+    """The lam blend of cn_op_2ins_space_chan (models/cnsn.py:86-87; no caller of the reference enables it, the C
+    ABI carries it): cnsn_site_fwd/_bwd called through the backend with lam = 0.3 against the oracle's composition."""
+    import cnsn_b200._lib as L
+    N, C, H, W = shape
+    lam = 0.3
+    x = O.varied_input(shape, seed=91, dtype=np.float32)
+    dy = np.random.RandomState(92).standard_normal(shape).astype(np.float32)
+    params, bufs = H.random_sn_params(C, seed=93)
+    torch.manual_seed(95)
+    np.random.seed(96)
+    plan = O.draw_plan(shape, crop=crop, beta=1)
+    cw = plan["content_window"] or (0, H, 0, W)
+    sw = plan["style_window"] or (0, H, 0, W)
+    sn = H.make_selfnorm(mod, C, params, bufs, DEV)
+    bn = sn.g_bn
+    g = L.GateTensors(sn.g_fc.weight.detach(), bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
+                      bn.num_batches_tracked)
+    be = L.backend()
+    xt = torch.from_numpy(x).to(DEV)
+    perm = torch.from_numpy(plan["perm"]).to(torch.int32).to(DEV)
+    y, save = be.site_fwd(xt, perm, cw, sw, lam, 1e-5, g, 0.1, 1e-5, 1e-12, relu)
+    dx, gg = be.site_bwd(xt, torch.from_numpy(dy).to(DEV), perm, cw, sw, lam, 1e-5, g, save, relu)
+    y, dx = y.double().cpu().numpy(), dx.double().cpu().numpy()
+    z = O.crossnorm_fwd(x, plan, lam)
+    yo, nb = O.selfnorm_fwd(z, params, bufs, True)
+    d = np.where(y > 0, dy, 0.0) if relu else dy
+    dzo, gr = O.selfnorm_bwd(z, d, params, bufs, True)
+    dxo = O.crossnorm_bwd(x, dzo, plan, lam)
+    close32(y, np.maximum(yo, 0.0) if relu else yo, "y")
+    close32(dx, dxo, "dx")
+    for a, k in zip(gg, ("g_w", "g_gamma", "g_beta")):
+        assert H.relmax(a.double().cpu().numpy(), gr[k]) <= H.PARAM_RTOL, k
+    close32(bn.running_var.double().cpu().numpy(), nb["g_rv"], "running_var")
