@@ -212,7 +212,7 @@ def test_site_lam_blend_vs_oracle(mod, shape, crop, relu):
     """The lam blend of cn_op_2ins_space_chan (models/cnsn.py:86-87; no caller of the reference enables it, the C
     ABI carries it): cnsn_site_fwd/_bwd called through the backend with lam = 0.3 against the oracle's composition."""
     import cnsn_b200._lib as L
-    N, C, H, W = shape
+    C, hh, ww = shape[1], shape[2], shape[3]
     lam = 0.3
     x = O.varied_input(shape, seed=91, dtype=np.float32)
     dy = np.random.RandomState(92).standard_normal(shape).astype(np.float32)
@@ -220,8 +220,8 @@ def test_site_lam_blend_vs_oracle(mod, shape, crop, relu):
     torch.manual_seed(95)
     np.random.seed(96)
     plan = O.draw_plan(shape, crop=crop, beta=1)
-    cw = plan["content_window"] or (0, H, 0, W)
-    sw = plan["style_window"] or (0, H, 0, W)
+    cw = tuple(int(v) for v in (plan["content_window"] or (0, hh, 0, ww)))
+    sw = tuple(int(v) for v in (plan["style_window"] or (0, hh, 0, ww)))
     sn = H.make_selfnorm(mod, C, params, bufs, DEV)
     bn = sn.g_bn
     g = L.GateTensors(sn.g_fc.weight.detach(), bn.weight.detach(), bn.bias.detach(), bn.running_mean, bn.running_var,
