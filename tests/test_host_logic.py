@@ -363,3 +363,35 @@ def test_dropin_other_reference_hosts(mod, host, ctor, kw, xshape):
         assert ka == kb and torch.allclose(pa.grad, pb.grad, atol=1e-7, rtol=1e-6), ka
     for (ka, ba), (kb, bb) in zip(na.named_buffers(), nb.named_buffers()):
         assert torch.allclose(ba.double(), bb.double(), atol=1e-9), ka
+
+
+def test_cnsn_site_fusion_declines_what_the_kernels_do_not_cover(mod):
+    """Two-gate SelfNorm, channel permutation, eval-mode BatchNorm inside the gate, a backend that says the shape does
+    not fit: CNSN.forward runs the two operators in sequence (same results as ever), never the fused call."""
+    import functools
+    x = torch.randn(4, 3, 6, 4, dtype=torch.float64)
+
+    def calls_of(blk):
+        blk.crossnorm.active = True
+        n0 = len(mod._fake.calls)
+        blk(x)
+        assert blk.crossnorm.active is False
+        return mod._fake.calls[n0:]
+
+    two = mod.CNSN(mod.CrossNorm("neither", 1), mod.SelfNorm(3, is_two=True)).double().train()
+    assert calls_of(two) == ["crossnorm_fwd", "selfnorm_fwd"]
+    chan = mod.CNSN(mod.CrossNorm("neither", 1), mod.SelfNorm(3)).double().train()
+    chan.crossnorm.cn_op = functools.partial(mod.cn_op_2ins_space_chan, crop="neither", beta=1, chan=True)
+    assert calls_of(chan) == ["crossnorm_fwd", "selfnorm_fwd"]
+    frozen = mod.CNSN(mod.CrossNorm("neither", 1), mod.SelfNorm(3)).double().train()
+    frozen.selfnorm.g_bn.eval()                      # gate BatchNorm on running statistics
+    assert calls_of(frozen) == ["crossnorm_fwd", "selfnorm_fwd"]
+    plain = mod.CNSN(mod.CrossNorm("neither", 1), mod.SelfNorm(3)).double().train()
+    mod._fake.site_supported = lambda t: False       # e.g. 7x7 planes, 224x224 image planes
+    try:
+        assert calls_of(plain) == ["crossnorm_fwd", "selfnorm_fwd"]
+    finally:
+        del mod._fake.site_supported
+    assert calls_of(plain) == ["site_fwd"]
+    only_cn = mod.CNSN(mod.CrossNorm("neither", 1), None).train()
+    assert calls_of(only_cn) == ["crossnorm_fwd"]

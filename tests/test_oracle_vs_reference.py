@@ -98,3 +98,31 @@ def test_eager_chain_is_bit_identical_to_reference():
         yb = E.crossnorm(xb, torch.from_numpy(plan["perm"]), plan["style_window"], plan["content_window"])
         yb.backward(dy)
         assert torch.equal(ya, yb) and torch.equal(xa.grad, xb.grad), crop
+
+
+@pytest.mark.parametrize("crop", ["neither", "style", "content", "both"])
+def test_numpy_oracle_site_vs_reference_cnsn_module(crop):
+    """The reference's CNSN module with its CrossNorm active (models/cnsn.py:159-164), executed live in fp64, against
+    the oracle's composition site_fwd / site_bwd -- the checker of the fused site kernels."""
+    shape = (6, 5, 8, 12)
+    x = O.varied_input(shape, seed=7, dtype=np.float64)
+    dy = np.random.RandomState(8).standard_normal(shape)
+    params, bufs = H.random_sn_params(shape[1], seed=9)
+    sn = H.make_selfnorm(ref, shape[1], params, bufs, "cpu").double()
+    blk = ref.CNSN(ref.CrossNorm(crop=crop, beta=1), sn).train()
+    blk.crossnorm.active = True
+    torch.manual_seed(21)
+    np.random.seed(22)
+    xt = t64(x).requires_grad_(True)
+    y = blk(xt)
+    y.backward(t64(dy))
+    assert blk.crossnorm.active is False
+    torch.manual_seed(21)
+    np.random.seed(22)
+    plan = O.draw_plan(shape, crop=crop, beta=1)
+    yo, _, nb = O.site_fwd(x, plan, params, bufs)
+    dxo, gr = O.site_bwd(x, dy, plan, params, bufs)
+    assert H.maxabs(yo, y.detach().numpy()) < 1e-12 and H.maxabs(dxo, xt.grad.numpy()) < 1e-11
+    assert H.relmax(gr["g_w"], sn.g_fc.weight.grad.view(-1, 2).numpy()) < 1e-10
+    assert H.relmax(gr["g_gamma"], sn.g_bn.weight.grad.numpy()) < 1e-10
+    assert H.maxabs(nb["g_rv"], sn.g_bn.running_var.numpy()) < 1e-12
