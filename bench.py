@@ -130,6 +130,19 @@ def physical_gpu_index(local):
     return local
 
 
+def bind_to_gpu_numa(index):
+    """Opt-in (CNSN_BENCH_NUMA=1): pin this rank to the CPUs NVML reports as local to its GPU BEFORE the pinned
+    staging buffers of the e2e leg are allocated (first touch then places them on the GPU's NUMA node).  Off by
+    default: unmeasured so far."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return sorted(os.sched_getaffinity(0))
+    except Exception as e:      # pragma: no cover
+        return "unavailable: %r" % (e,)
+
+
 # ----------------------------------------------------------------------------- CPU reference arm
 def cpu_reference_selfnorm(shape, steps, warmup):
     """Eager-PyTorch chain of the reference on this box's host cores (bounded sample)."""
@@ -276,6 +289,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py (b200 arm) needs a CUDA device"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(physical_gpu_index(local)) if os.environ.get("CNSN_BENCH_NUMA") == "1" else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     if args.gpus != world and rank == 0 and world > 1:
@@ -403,6 +417,8 @@ def main():
                "d2h_bytes_per_step": 2 * S, "ms_per_step": e_ms, "steps": e2e_steps,
                "api": "cnsn_b200.cnsn.SelfNorm forward + autograd backward on pinned host tensors; "
                       "double-buffered: H2D / compute / D2H of consecutive steps overlap on three streams"}
+        if numa is not None:
+            e2e["numa_cpus"] = numa if isinstance(numa, str) else "%d cpus bound (NVML affinity of the GPU)" % len(numa)
         del bufs
         del hx, hdy, hy, hdx
 
