@@ -46,6 +46,14 @@ def test_argument_validation_without_gpu():
     assert h.cnsn_selfnorm_save_floats(4, 16, 0) == 4 * 64 + 16 + 2 * 64 + 36 * 16 + 8
     assert h.cnsn_selfnorm_save_floats(4, 16, 1) == 6 * 64 + 32 + 2 * 64 + 36 * 16 + 8
     assert h.cnsn_crossnorm_save_floats(4, 16) == 256 + 2 * 64 + 8
+    # fused site: 8 statistics blocks of N*C, r (C), exchange area (sn words, channel sectors, ticket, 3 cn words)
+    assert h.cnsn_site_workspace_floats(4, 16) == 8 * 64 + 8 * 16 + 8
+    assert h.cnsn_site_save_floats(4, 16) == 8 * 64 + 16 + h.cnsn_site_workspace_floats(4, 16)
+    assert h.cnsn_site_fwd(None, None, 0, 4, 16, 8, 8, None, None, None, 0.0, 1e-5, None, 0.1, 1e-5, 1e-12, 0, None, None) == -1
+    assert h.cnsn_site_bwd(None, None, None, 0, 4, 16, 8, 8, None, None, None, 0.0, 1e-5, 0, None, None, None, None, None) == -1
+    assert h.cnsn_site_supported(7, 4, 16, 8, 8) == 0 and h.cnsn_site_supported(0, 0, 16, 8, 8) == 0    # bad dtype / dims
+    assert h.cnsn_site_supported(0, 4, 16, 7, 7) == 0          # 7x7 fp32 planes are not 16-byte multiples
+    assert h.cnsn_ibn_fwd(None, None, 0, 4, 16, 8, 8, 8, None, 1, 0.1, 1e-5, 1e-5, None, None) == -1
 
 
 def test_error_strings_cover_every_code():
