@@ -204,7 +204,9 @@ class CNSN(nn.Module):
     def forward(self, x, residual=None, relu=False):
         """``forward(x)`` is the reference call (models/cnsn.py:159-164).  ``forward(x, residual, relu)`` computes
         relu?(CNSN(x + residual)) -- the pos='post' block tail -- fusing add and ReLU into the SelfNorm kernels
-        whenever this step's CrossNorm does not fire at the site."""
+        whenever this step's CrossNorm does not fire at the site.  When both operators fire, the pair runs as ONE
+        fused kernel per direction (``cnsn_site_fwd/_bwd``) wherever ``_site_fusable`` says so, else
+        one after the other; host RNG consumption, ``.active`` handling and results are the same either way."""
         fire = bool(self.crossnorm) and self.crossnorm.active
         if residual is None and not relu:
             if fire:
