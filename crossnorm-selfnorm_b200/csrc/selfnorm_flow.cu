@@ -844,6 +844,46 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
 
 constexpr int kResT = 128;              // threads per CTA of the shared-memory-resident kernel
 
+// EXPERIMENT, opt-in (CNSN_FLOW_I3=1), forward only, not measured yet: items of THREE planes and
+// 192 threads (64 per plane).  At the north-star plane size (12.5 KB) an SM holds 8 items x 2 planes = 16 planes with
+// the default geometry and cannot take a ninth; 6 items x 3 planes = 18 planes fit the same 228 KB.  Same kernel
+// template (it is generic in TH and TPI); only taken when the default geometry would be two planes per item.
+static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
+    constexpr int kT3 = 192, kTpi3 = 64, kI3 = kT3 / kTpi3;
+    const int N = a.N, C = a.C;
+    const size_t pbytes = (size_t)a.M * esize(dtype);
+    if (pbytes % 16 || N < kI3 || pbytes * 2 > (25u << 10) + 512 || pbytes * 4 <= (25u << 10) + 512) return -100;
+    const size_t dsmem = 128 + kI3 * pbytes;
+    const DeviceShape ds = device_shape();
+    a.nI = (N + kI3 - 1) / kI3;
+    a.D = 0;
+    a.order = env_int("CNSN_FLOW_ORDER", 0);
+    const unsigned long long items = (unsigned long long)C * a.nI;
+    if (items > 0x7fffffffull) return -100;
+    a.pub = reinterpret_cast<float2*>(scratch);
+    a.chan = a.pub + (size_t)N * C;
+    a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
+    a.done = nullptr; a.ready = nullptr; a.trace = nullptr;
+    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.items = (unsigned)items;
+    const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
+    cudaError_t e = cudaSuccess;
+    int per_sm = 0;
+    CNSN_DISPATCH_DTYPE(dtype, T, {
+        auto fn = k_sn_res<T, false, false, false, kTpi3, kT3>;
+        e = prepare_kernel(fn, kT3, dsmem, &per_sm);
+        if (e != cudaSuccess) return (int)e;
+        if ((long long)per_sm * ds.sms < 2ll * a.nI) return -100;
+        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);
+        e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
+        if (e != cudaSuccess) return (int)e;
+        fn<<<dim3((unsigned)items), dim3(kT3), dsmem, stream>>>(a);
+    });
+    if (getenv("CNSN_FLOW_DEBUG"))
+        fprintf(stderr, "[cnsn flow/res-i3] fwd tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d\n", kTpi3, kI3, a.nI, items, dsmem, per_sm);
+    return launch_status();
+}
+
 // Shared-memory-resident path.  Returns -100 when the shape does not fit (the caller uses the L2 path).
 template <bool BWD>
 static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, bool dy_from_global = false) {
@@ -852,6 +892,10 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     if (((size_t)a.M * esz) % 16 || N < 1 || C < 1) return -100;
     const bool add = !BWD && a.res != nullptr;
     const bool dyg = BWD && dy_from_global;
+    if (!BWD && !add && env_int("CNSN_FLOW_I3", 0)) {
+        const int rc3 = launch_res_i3(a, dtype, scratch, stream);
+        if (rc3 != -100) return rc3;
+    }
     const size_t inst_bytes = (size_t)a.M * esz * (((BWD && !dyg) || add) ? 2 : 1);
     const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
     int inst = 1;
