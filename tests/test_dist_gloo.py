@@ -20,7 +20,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, which="eager"):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -29,25 +29,40 @@ def _worker(rank, world, port, q):
     torch.set_num_threads(2)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from cnsn_b200.train import bench_wrn
-    from oracle import eager_modules
-    r = bench_wrn(torch.device("cpu"), world, rank, batch=4, steps=2, warmup=1, cn_prob=1.0, ops=eager_modules)
-    q.put((rank, r["param_checksum"], r["value"], r["n_gpus"], float(np.random.rand())))
+    extra = None
+    if which == "eager":
+        from oracle import eager_modules as ops
+    else:                       # the package's own modules and autograd Functions over the oracle-backed stand-in backend
+        import cnsn_b200._lib as L
+        import cnsn_b200.cnsn as ops
+        from fake_backend import OracleBackend
+        fake = OracleBackend()
+        L.set_backend_for_tests(fake)
+    r = bench_wrn(torch.device("cpu"), world, rank, batch=4, steps=2, warmup=1, cn_prob=1.0, ops=ops)
+    if which != "eager":
+        extra = (fake.calls.count("site_fwd"), fake.calls.count("site_bwd"), fake.calls.count("selfnorm_bwd"))
+    q.put((rank, r["param_checksum"], r["value"], r["n_gpus"], float(np.random.rand()), extra))
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_gloo_training_keeps_replicas_in_sync():
+@pytest.mark.parametrize("which", ["eager", "package"])
+def test_two_rank_gloo_training_keeps_replicas_in_sync(which):
+    """which='package': the product's modules (CNSN.forward with the fused site, the autograd Functions' parameter
+    gradients) under DistributedDataParallel, over the oracle-backed stand-in backend."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, which)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=500) for _ in procs)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
-    (_, c0, v0, n0, u0), (_, c1, v1, n1, u1) = res
+    (_, c0, v0, n0, u0, e0), (_, c1, v1, n1, u1, e1) = res
+    if which == "package":      # 3 steps x 2 active sites, every one through the fused call; the other sites plain SelfNorm
+        assert e0[0] == e0[1] == 6 and e1[0] == e1[1] == 6 and e0[2] > 0
     assert n0 == n1 == 2
     assert c0 == pytest.approx(c1, rel=1e-12)          # same initial weights + all-reduced grads -> identical replicas
     assert v0 == pytest.approx(v1, rel=1e-9)           # throughput is computed from the max-over-ranks time
