@@ -16,7 +16,8 @@ LIB_PATH = os.path.join(_PKG, "libcnsn_b200.so")
 
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
-ABI_VERSION = 4
+CNSN_E_TIMEOUT = -6
+ABI_VERSION = 5
 
 _DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
 
@@ -43,6 +44,8 @@ SIGNATURES = {
     "cnsn_version": (c_int, []),
     "cnsn_error_string": (c_char_p, [c_int]),
     "cnsn_launch_count": (c_ulonglong, []),
+    "cnsn_async_error": (c_int, [c_int]),
+    "cnsn_tune": (c_int, [c_char_p, c_int]),
     "cnsn_instance_stats": (c_int, [c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p]),
     "cnsn_instance_stats_bwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int,
@@ -107,6 +110,53 @@ def lib():
 
 def launch_count():
     return int(lib().cnsn_launch_count())
+
+
+def async_error(clear=True):
+    """CNSN_E_TIMEOUT state of the library (a kernel gave up a bounded wait; see include/cnsn_b200.h).  Raises
+    RuntimeError when set; ``clear`` resets it so that the process can carry on."""
+    rc = lib().cnsn_async_error(int(clear))
+    if rc:
+        raise RuntimeError("cnsn_b200 error %d: %s" % (rc, lib().cnsn_error_string(rc).decode()))
+
+
+# knob name -> {symbolic value -> int}; plain ints pass through (struct Knobs, csrc/flow_common.cuh)
+_KNOB_WORDS = {"selfnorm_impl": {"auto": 0, "v1": 1, "flow": 3}, "crossnorm_impl": {"auto": 0, "v1": 1},
+               "flow_mode": {"auto": 0, "res": 1, "l2": 2}, "flow_bwd": {"auto": 0, "res": 1, "dyg": 2, "l2": 3}}
+
+
+def tune(**knobs):
+    """MEASUREMENT / TEST HOOK: set process-wide tuning knobs of the library (``tune(reset=1)`` restores the
+    defaults).  The library never reads the environment; tools that take CNSN_* variables call ``tune_from_env``."""
+    for k, v in knobs.items():
+        if isinstance(v, str):
+            v = _KNOB_WORDS[k][v] if k in _KNOB_WORDS and v in _KNOB_WORDS[k] else int(v)
+        rc = lib().cnsn_tune(k.encode(), int(v))
+        if rc:
+            raise KeyError("cnsn_b200: unknown tuning knob %r" % k)
+
+
+class tuned:
+    """``with tuned(flow_mode="res"): ...`` -- knobs set inside, defaults restored on exit (tests, A/B tools)."""
+
+    def __init__(self, **knobs):
+        self.knobs = knobs
+
+    def __enter__(self):
+        tune(**self.knobs)
+        return self
+
+    def __exit__(self, *a):
+        tune(reset=1)
+        return False
+
+
+def tune_from_env(environ=None):
+    """For the measurement tools only: CNSN_TUNE_<KNOB>=value variables -> tune().  Returns what was set."""
+    environ = os.environ if environ is None else environ
+    got = {k[len("CNSN_TUNE_"):].lower(): v for k, v in environ.items() if k.startswith("CNSN_TUNE_")}
+    tune(**got)
+    return got
 
 
 _SIZES = {}
@@ -345,11 +395,16 @@ class CudaBackend:
         N, C, H, W = x.shape
         keep = []
         ps = self._ibn_struct(p, keep)
-        save = torch.empty(lib().cnsn_ibn_save_floats(N, C, half), dtype=torch.float32, device=x.device)
+        save = torch.empty(_size("cnsn_ibn_save_floats", N, C, half), dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         with _on(x.device):
             _check(lib().cnsn_ibn_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
                                       momentum, eps_in, eps_bn, _p(save), _stream(x)))
+        if training:                     # buffers that were not fp32-contiguous were updated in a temporary: write back
+            for name, tmp in (("run_mean", keep[4]), ("run_var", keep[5])):
+                buf = p.get(name)
+                if buf is not None and tmp is not buf:
+                    buf.copy_(tmp)
         return y, save
 
     def ibn_bwd(self, x, dy, half, p, training, save):
@@ -360,7 +415,7 @@ class CudaBackend:
         dev = x.device
         g = torch.empty(2 * C, dtype=torch.float32, device=dev)
         d_in_w, d_in_b, d_bn_w, d_bn_b = g[:half], g[half:2 * half], g[2 * half:C + half], g[C + half:]
-        ws = torch.empty(lib().cnsn_ibn_workspace_floats(N, C), dtype=torch.float32, device=dev)
+        ws = torch.empty(_size("cnsn_ibn_workspace_floats", N, C), dtype=torch.float32, device=dev)
         dx = torch.empty_like(x)
         with _on(dev):
             _check(lib().cnsn_ibn_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
@@ -412,7 +467,7 @@ class CudaBackend:
     # -- fused site: CrossNorm -> SelfNorm ---------------------------------------------------
     def site_supported(self, x):
         """True when cnsn_site_fwd/_bwd can run this shape on x's device (cached per shape)."""
-        if not x.is_cuda:
+        if not x.is_cuda or x.data_ptr() % 16:          # a misaligned slice goes through the two-operator sequence
             return False
         N, C, H, W = x.shape
         with _on(x.device):

@@ -23,6 +23,15 @@ __all__ = ["calc_ins_mean_std", "instance_norm_mix", "cn_rand_bbox", "cn_op_2ins
 _CROPS = ("neither", "style", "content", "both")
 
 
+def _bn_momentum(bn):
+    """BatchNorm's update factor for this call (``momentum=None`` means torch's cumulative average)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if not bn.training or bn.num_batches_tracked is None:
+        return 0.0
+    return 1.0 / (int(bn.num_batches_tracked) + 1)
+
+
 def _full(x):
     return (0, x.size(2), 0, x.size(3))
 
@@ -183,9 +192,9 @@ class SelfNorm(nn.Module):
         if residual is not None or relu:
             assert self.f_fc is None, "the fused block supports the single-gate SelfNorm"
             assert residual is None or residual.shape == x.shape
-            return SelfNormBlockFn.apply(x, residual, bool(relu), bn.training, float(bn.momentum), float(bn.eps), 1e-12,
+            return SelfNormBlockFn.apply(x, residual, bool(relu), bn.training, _bn_momentum(bn), float(bn.eps), 1e-12,
                                          self._bufs(bn), self.g_fc.weight, bn.weight, bn.bias)
-        args = [x, bn.training, float(bn.momentum), float(bn.eps), 1e-12,          # eps :133
+        args = [x, bn.training, _bn_momentum(bn), float(bn.eps), 1e-12,          # eps :133
                 self._bufs(bn), self._bufs(self.f_bn) if self.f_fc is not None else None,
                 self.g_fc.weight, bn.weight, bn.bias]
         if self.f_fc is not None:
@@ -253,5 +262,5 @@ class CNSN(nn.Module):
         cn.active = False
         bn = sn.g_bn
         return CnsnSiteFn.apply(x, perm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5, bool(relu),
-                                float(bn.momentum), float(bn.eps), 1e-12, SelfNorm._bufs(bn),
+                                _bn_momentum(bn), float(bn.eps), 1e-12, SelfNorm._bufs(bn),
                                 sn.g_fc.weight, bn.weight, bn.bias)

@@ -16,7 +16,7 @@
 // precedes the apply phase: that is the kernel boundary here.
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "flow_common.cuh"
 
 namespace cnsn {
 
@@ -183,11 +183,8 @@ int crossnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N
                        const float* mu_c, const float* sd_c, const float* mu_s, const float* sd_s,
                        float* scratch, cudaStream_t stream);
 }
-// CNSN_CROSSNORM_IMPL=v1 forces the two-kernel path (A/B measurements).
-static bool cn_use_flow() {
-    const char* e = getenv("CNSN_CROSSNORM_IMPL");
-    return !(e && e[0] == 'v');
-}
+// cnsn_tune("crossnorm_impl", 1) forces the two-kernel path (A/B measurements, tests).
+static bool cn_use_flow() { return knobs().crossnorm_impl != 1; }
 
 }  // namespace cnsn
 

@@ -34,7 +34,6 @@ struct CNArgs {
     const void* x; const void* dy; void* out;      // forward: dy == nullptr, out = y; backward: out = dx
     int N, C, H, W;
     int nI;                 // items per channel = ceil(N / I)
-    int order;              // 0: atomic ticket per CTA; 1: blockIdx.x
     int poll_ns;
     int pf_dist;            // L2-prefetch the item pf_dist tickets ahead (0 = off)
     unsigned items;         // total tickets
@@ -44,24 +43,18 @@ struct CNArgs {
     float* mu_c; float* sd_c; float* mu_s; float* sd_s;     // save block: written by forward, read by backward
     float2* pub;            // [C][N] polled words, pre-filled with the sentinel
     unsigned* ticket;       // starts at 0xffffffff
+    unsigned* err;          // asynchronous error word
 };
 
 template <typename T, bool BWD, int TPI>
-__global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
+__device__ __forceinline__ void cn_res_item(const CNArgs& a, const unsigned t, const unsigned par) {
     constexpr int TH = kCnT;
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
     extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
-    __shared__ unsigned s_word;
     __shared__ float s_f[4][TH / 32];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
-    if (threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;   // the counter starts at 0xffffffff
-    }
-    __syncthreads();
-    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned nI = (unsigned)a.nI;
     const unsigned c = t / nI, j = t - c * nI;
     const int N = a.N, C = a.C, H = a.H, W = a.W, M = H * W;
     const int n = (int)j * I + (int)(threadIdx.x / TPI);
@@ -76,13 +69,13 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
         const int first = (int)j * I;
         const int nlive = min(I, N - first);
         const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+            tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
         }
         // L2 prefetch for the CTA that will take this one's place (see selfnorm_flow.cu)
         const unsigned tf = t + (unsigned)a.pf_dist;
@@ -91,8 +84,8 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
             const int ff = (int)jf * I, nf = min(I, N - ff);
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
-                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+                tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
             }
         }
     }
@@ -107,7 +100,7 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
         muc = a.mu_c[nc]; sdc = a.sd_c[nc]; mus = a.mu_s[nc]; sds = a.sd_s[nc];
         sds_src = a.sd_s[(size_t)src_n * C + c];
     }
-    fused::mbar_wait(bar, 0);
+    mbar_wait(bar, par, a.err);
 
     uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + nc * M);
     if (!BWD) {
@@ -117,10 +110,10 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
         if (!same) sts = window_stats<T, TPI>(sx, W, M, sw, sfull, r, live, a.eps, s_f[2], s_f[3]);
         if (live && r == 0) {
             a.mu_c[nc] = stc.x; a.sd_c[nc] = stc.y; a.mu_s[nc] = sts.x; a.sd_s[nc] = sts.y;
-            fused::ll_publish(a.pub + (size_t)c * N + n, sts.x, sts.y);
+            ll_publish(a.pub + (size_t)c * N + n, sts.x, sts.y);
         }
         if (!live) return;
-        const float2 ps = poll_word(a.pub + (size_t)c * N + src_n, a.poll_ns);   // the team polls one address
+        const float2 ps = poll_word(a.pub + (size_t)c * N + src_n, a.poll_ns, a.err);   // the team polls one address
         const float A = ps.y / stc.y;
         const float ca = lam + (1.f - lam) * A;
         const float cb = (1.f - lam) * (ps.x - stc.x * A);
@@ -151,9 +144,9 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
         const float tsum = team_sum<TPI>(t0 + t1, s_f[1]);
         const float S1 = (1.f - lam) * tsum;
         const float S2 = (1.f - lam) * asum / sdc;
-        if (live && r == 0) fused::ll_publish(a.pub + (size_t)c * N + src_n, S1, S2);
+        if (live && r == 0) ll_publish(a.pub + (size_t)c * N + src_n, S1, S2);
         if (!live) return;
-        const float2 ds = poll_word(a.pub + (size_t)c * N + n, a.poll_ns);        // (dmu_s, dsd_s) of this instance
+        const float2 ds = poll_word(a.pub + (size_t)c * N + n, a.poll_ns, a.err);        // (dmu_s, dsd_s) of this instance
         const float Mc = (float)cw.area(), Ms = (float)sw.area();
         const float A = sds_src / sdc;
         // inside the content window: dx = p*dy + q*x + r0
@@ -188,6 +181,11 @@ __global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
     }
 }
 
+template <typename T, bool BWD, int TPI>
+__global__ void __launch_bounds__(kCnT) k_cn_res(const CNArgs a) {
+    CNSN_TICKET_LOOP(a, (cn_res_item<T, BWD, TPI>(a, t, it & 1u)))
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -197,7 +195,8 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     const int esz = (int)esize(dtype);
     if (((size_t)M * esz) % 16 || N < 1 || C < 1) return -100;
     const size_t inst_bytes = (size_t)M * esz * (BWD ? 2 : 1);
-    const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
+    const Knobs& kn = knobs();
+    const size_t target = (size_t)kn.item_kb << 10;
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
     const int tpi = kCnT / inst;
@@ -206,15 +205,14 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     const int sms = ds.sms;
     if (dsmem > (size_t)ds.smem_optin / 2) return -100;      // at least two CTAs per SM
     a.nI = (N + inst - 1) / inst;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.poll_ns = kn.poll_ns;
+    a.err = async_error_word();
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return -100;
     a.items = (unsigned)items;
     a.pub = reinterpret_cast<float2*>(scratch);              // [C][N] float2 | ticket
     a.ticket = reinterpret_cast<unsigned*>(a.pub + (size_t)N * C);
     const size_t fill_bytes = ((size_t)N * C + 1) * sizeof(float2);
-    const dim3 grid((unsigned)items), block(kCnT);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
 #define CNSN_CN_CASE(TPI_)                                                                               \
@@ -223,17 +221,18 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = prepare_kernel(fn, kCnT, dsmem, &per_sm);                                                    \
         if (e != cudaSuccess) return (int)e;                                                             \
         if ((long long)per_sm * sms < 2ll * a.nI) return -100;    /* a whole channel must be co-resident */ \
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * sms / 2;                                               \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
-        fn<<<grid, block, dsmem, stream>>>(a);                                                           \
+        e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, sms, kCnT, dsmem, stream);                         \
+        if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_CN_CASE(8) CNSN_CN_CASE(16) CNSN_CN_CASE(32) CNSN_CN_CASE(64) CNSN_CN_CASE(128)
         default: return -100;
     });
 #undef CNSN_CN_CASE
-    if (getenv("CNSN_FLOW_DEBUG"))
+    if (kn.debug)
         fprintf(stderr, "[cnsn flow/cn] %s tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d\n", BWD ? "bwd" : "fwd", tpi, inst, a.nI,
                 items, dsmem, per_sm);
     return launch_status();
@@ -246,6 +245,7 @@ int crossnorm_flow_fwd(const void* x, void* y, int dtype, int N, int C, int H, i
                        const Window& cw, const Window& sw, float lam, float eps,
                        float* mu_c, float* sd_c, float* mu_s, float* sd_s, float* scratch, cudaStream_t stream) {
     if (!aligned16(x) || !aligned16(y)) return -100;
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
     CNArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.H = H; a.W = W;
     a.cw = cw; a.sw = sw; a.lam = lam; a.eps = eps; a.perm = perm;
@@ -258,6 +258,7 @@ int crossnorm_flow_bwd(const void* x, const void* dy, void* dx, int dtype, int N
                        const float* mu_c, const float* sd_c, const float* mu_s, const float* sd_s,
                        float* scratch, cudaStream_t stream) {
     if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) return -100;
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
     CNArgs a{};
     a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.H = H; a.W = W;
     a.cw = cw; a.sw = sw; a.lam = lam; a.eps = 0.f; a.perm = perm;

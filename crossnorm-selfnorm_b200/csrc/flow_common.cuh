@@ -1,5 +1,7 @@
-// flow_common.cuh -- building blocks shared by the ticket-ordered dataflow kernels (selfnorm_flow.cu,
-// crossnorm_flow.cu): gpu-scope flags, polled 8-byte words, team / CTA reductions, shared-memory vector loads.
+// flow_common.cuh -- building blocks shared by the ticket-ordered dataflow kernels (selfnorm_flow.cu, crossnorm_flow.cu,
+// site_flow.cu, ibn_flow.cu): mbarrier + TMA bulk-copy wrappers, polled 8-byte words ("data is the flag"), the
+// asynchronous error word, team / CTA reductions, shared-memory vector loads, and the host-side launch helpers
+// (tuning knobs, per-kernel preparation, cooperative persistent launch).
 #pragma once
 
 #include <stdlib.h>
@@ -7,14 +9,116 @@
 #include <mutex>
 #include <unordered_map>
 
-#include "fused_common.cuh"
+#include "common.cuh"
 
 namespace cnsn {
+
+// ---- tuning knobs (A/B measurements and tests only) --------------------------------------------------------
+// Process-wide, set through cnsn_tune() (include/cnsn_b200.h) -- NEVER read from the environment, so an
+// inherited variable cannot change which kernel a training job runs.  0 / -1 = "default dispatch".
+struct Knobs {
+    int selfnorm_impl = 0;      // 0 auto, 1 three-kernel path, 3 dataflow kernels only
+    int crossnorm_impl = 0;     // 0 auto, 1 two-kernel path
+    int flow_mode = 0;          // SelfNorm forward: 0 auto, 1 shared-memory-resident, 2 L2 items
+    int flow_bwd = 0;           // SelfNorm backward: 0 auto, 1 resident, 2 x resident + dy through L2, 3 L2 items
+    int flow_d = 0;             // L2 items: look-ahead in channels (0 = from lookahead_mb)
+    int flow_tpi = 0;           // threads per instance override
+    int flow_batches = 6;       // L2 items: batches of kU loads a thread covers its plane in
+    int lookahead_mb = 40;      // L2 items: bytes kept between the reduce and the apply stream
+    int item_kb = 25;           // resident items: shared memory per CTA aimed at
+    int grp_kb = 20;            // channel-group items: shared memory per CTA aimed at
+    int keep = 1;               // L2 items: R loads evict-last
+    int pf = -1;                // resident items: L2 prefetch distance in tickets (-1 = half the resident CTAs)
+    int rpf = 0;                // L2 items: prefetch distance in channels
+    int poll_ns = 100;          // sleep between polls of a published word
+    int i3 = 0;                 // forward: three planes per resident item where two is the default
+    int cooperative = 1;        // resident items: cooperative launch (co-residency guaranteed by the driver)
+    int grid_cap = 0;           // resident items: cap the persistent grid (0 = every CTA the GPU holds)
+    int debug = 0;              // print the chosen geometry to stderr
+    int trace = 0;              // resident SelfNorm: per-item timestamps to $CNSN_FLOW_TRACE (synchronous, debug)
+};
+Knobs& knobs();                                  // api.cu
+
+// ---- asynchronous error word ---------------------------------------------------------------------------------
+// A wait that exceeds its bound (seconds: only a bug, a debugger or a sanitizer gets there) does NOT trap -- a trap
+// destroys the CUDA context of a training job.  The waiting thread records a code in a pinned, device-mapped host
+// word and carries on with whatever it read; the host finds the code at its next call (CNSN_E_TIMEOUT) or through
+// cnsn_async_error().  The results of that one launch are undefined, the process stays usable.
+unsigned* async_error_word();                    // api.cu: device-visible pointer, allocated on first use
+int async_error_peek();                          // api.cu: host-side read (0 = none)
+enum { kErrPollTimeout = 1, kErrTmaTimeout = 2 };
+
 namespace flow {
 
-using fused::smem_u32;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+constexpr unsigned long long kWaitBoundNs = 20ull * 1000 * 1000 * 1000;    // 20 s
+static __device__ __noinline__ void report_timeout(unsigned* err, unsigned code) {
+    if (err) atomicCAS(err, 0u, code);
+    __threadfence_system();
+}
 
-constexpr unsigned kSpin = 1u << 25;    // bounded polls (>= 64 ns each, i.e. seconds): trap instead of hanging the GPU
+// ---- mbarrier + TMA 1-D bulk copies (SASS: UBLKCP / UBLKPF / SYNCS) ---------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Waiting warps sleep explicitly: a try_wait that wakes on every TMA chunk starves the warps doing arithmetic.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity, unsigned* err) {
+    unsigned spins = 0;
+    unsigned long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(200);
+        if ((++spins & 0xfffu) == 0) {
+            const unsigned long long now = gtime();
+            if (!t0) t0 = now;
+            else if (now - t0 > kWaitBoundNs) { report_timeout(err, kErrTmaTimeout); return; }
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar,
+                                            uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(policy) : "memory");
+}
+// L2 prefetch of a future item: the HBM latency (and its tail) is paid before shared memory is tied up.
+__device__ __forceinline__ void tma_prefetch_l2(const void* src_gmem, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" :: "l"(src_gmem), "r"(bytes) : "memory");
+}
+// generic-proxy accesses to shared memory made so far are ordered before later async-proxy (TMA) writes
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ---- "data is the flag" exchange (as in low-latency collective protocols) ----------------------------------
+// A per-instance result is ONE aligned 8-byte store whose second word can never equal the sentinel, into an area
+// pre-filled with the sentinel (0xff bytes).  Readers poll the 8-byte word itself: no separate flag, no fence, one
+// L2 hop each way.  A NaN payload is canonicalised (0x7fc00000), an all-ones NaN cannot be published.
+constexpr unsigned kSentinel = 0xffffffffu;
+__device__ __forceinline__ void ll_publish(float2* slot, float a, float b) {
+    if (b != b) b = __uint_as_float(0x7fc00000u);
+    asm volatile("st.relaxed.gpu.global.v2.f32 [%0], {%1, %2};" :: "l"(slot), "f"(a), "f"(b) : "memory");
+}
+__device__ __forceinline__ float2 ll_peek(const float2* slot) {
+    float2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(slot));
+    return v;
+}
+__device__ __forceinline__ bool ll_valid(const float2& v) { return __float_as_uint(v.y) != kSentinel; }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
     unsigned v;
@@ -86,11 +190,6 @@ __device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[TH / 32]) {
     }
 }
 
-__device__ __forceinline__ unsigned long long gtime() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     uint4 r;
     asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
@@ -118,13 +217,20 @@ template <> __device__ __forceinline__ float lds_elem<__half>(uint32_t base, int
 __device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns) {
-    float2 v = fused::ll_peek(p);
+// Poll one published word until it is there.  Bounded (kWaitBoundNs): on expiry the error word is set and the
+// sentinel-valued read is returned -- no trap.
+__device__ __forceinline__ float2 poll_word(const float2* p, int sleep_ns, unsigned* err) {
+    float2 v = ll_peek(p);
     unsigned spins = 0;
-    while (!fused::ll_valid(v)) {
+    unsigned long long t0 = 0;
+    while (!ll_valid(v)) {
         __nanosleep(sleep_ns);
-        v = fused::ll_peek(p);
-        if (++spins > kSpin) __trap();
+        v = ll_peek(p);
+        if ((++spins & 0xfffu) == 0) {
+            const unsigned long long now = gtime();
+            if (!t0) t0 = now;
+            else if (now - t0 > kWaitBoundNs) { report_timeout(err, kErrPollTimeout); break; }
+        }
     }
     return v;
 }
@@ -176,9 +282,30 @@ __device__ __forceinline__ float2 window_stats(uint32_t sx, int W, int M, const 
     return make_float2(mean, sqrtf(m2 / (cnt - 1.f) + eps));
 }
 
-// host: per-(device, kernel, dynamic shared memory) launch preparation, done once: opt in to the shared-memory
-// size, prefer the maximum carve-out, ask the occupancy API how many CTAs fit an SM.  (Three driver calls that
-// would otherwise be paid on every launch; they dominate the host time of small tensors.)
+// The persistent ticket loop every shared-memory-resident kernel runs (cooperative launch, grid = the CTAs the GPU
+// holds at once): take a ticket, run the item, until the tickets run out.  The item's bulk copies complete on ONE
+// mbarrier per CTA whose phase parity alternates with the iteration; the barrier at the end of an iteration orders
+// the item's last shared-memory reads before the next item's bulk copies overwrite them.
+#define CNSN_TICKET_LOOP(ARGS, ITEM_CALL)                                                         \
+    extern __shared__ __align__(128) unsigned char dsm_loop[];                                    \
+    __shared__ unsigned s_ticket;                                                                 \
+    if (threadIdx.x == 0) {                                                                       \
+        mbar_init(reinterpret_cast<uint64_t*>(dsm_loop), 1);                                      \
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");                        \
+    }                                                                                             \
+    for (unsigned it = 0;; ++it) {                                                                \
+        if (threadIdx.x == 0) s_ticket = atomicAdd((ARGS).ticket, 1u) + 1u; /* starts at 0xffffffff */ \
+        __syncthreads();                                                                          \
+        const unsigned t = s_ticket;                                                              \
+        if (t >= (ARGS).items) break;                                                             \
+        ITEM_CALL;                                                                                \
+        fence_proxy_async_smem();                                                                 \
+        __syncthreads();                                                                          \
+    }
+
+// host: per-(device, kernel) launch preparation, done once: opt in to the device's maximum dynamic shared memory
+// (the attribute is per function and last-write-wins, so it is set ONCE to the maximum, never to one call's size),
+// prefer the maximum carve-out; the occupancy for a given dynamic size is cached per (device, kernel, size).
 struct DeviceShape { int sms = 0, smem_optin = 0; };
 static inline DeviceShape device_shape() {
     static std::mutex mu;
@@ -197,27 +324,53 @@ static inline DeviceShape device_shape() {
 template <typename K>
 static inline cudaError_t prepare_kernel(K fn, int threads, size_t dsmem, int* ctas_per_sm) {
     static std::mutex mu;
-    static std::unordered_map<unsigned long long, int> cache;     // per kernel instantiation (K is its type)
+    static std::unordered_map<unsigned long long, int> occ;       // (device, kernel, dsmem) -> CTAs per SM
+    static std::unordered_map<unsigned long long, bool> ready;    // (device, kernel) -> attributes set
     int dev = 0;
     cudaGetDevice(&dev);
-    const unsigned long long key = ((unsigned long long)dev << 56) ^ ((unsigned long long)(uintptr_t)fn * 0x9e3779b97f4a7c15ull) ^ dsmem;
+    const unsigned long long fkey = ((unsigned long long)dev << 56) ^ ((unsigned long long)(uintptr_t)fn * 0x9e3779b97f4a7c15ull);
+    const unsigned long long key = fkey ^ (dsmem * 0xc2b2ae3d27d4eb4full);
     std::lock_guard<std::mutex> lock(mu);
-    auto it = cache.find(key);
-    if (it != cache.end()) { *ctas_per_sm = it->second; return cudaSuccess; }
+    auto it = occ.find(key);
+    if (it != occ.end()) { *ctas_per_sm = it->second; return cudaSuccess; }
     cudaError_t e = cudaSuccess;
-    if (dsmem > 48 * 1024) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
-    if (e == cudaSuccess && dsmem) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fn, threads, dsmem);
-    if (e == cudaSuccess) cache[key] = *ctas_per_sm;
+    if (!ready.count(fkey)) {
+        const DeviceShape d = device_shape();
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        if (e != cudaSuccess) return e;
+        ready[fkey] = true;
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(ctas_per_sm, fn, threads, dsmem);
+    if (e == cudaSuccess) occ[key] = *ctas_per_sm;
     return e;
 }
 
-// host: integer environment knob (A/B measurements only)
-static inline int env_int(const char* name, int dflt) {
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
+// host: launch a persistent ticket kernel.  The grid is capped at the number of CTAs the GPU holds at once
+// (occupancy x SMs) and launched COOPERATIVELY: the driver then guarantees that every CTA of the grid is resident
+// at the same time whatever else shares the GPU (NCCL kernels, other streams, MPS), which is what the spin-waits
+// between the CTAs of a channel rely on.  Each CTA loops over tickets until they run out.
+template <typename K, typename A>
+static inline cudaError_t launch_persistent(K fn, const A& args, unsigned items, unsigned channel_items, int per_sm, int sms,
+                                            int threads, size_t dsmem, cudaStream_t stream) {
+    unsigned long long cap = (unsigned long long)per_sm * sms;
+    const Knobs& kn = knobs();
+    // test knob: a smaller grid (every CTA then runs many items); never below one channel's items -- a channel's
+    // items wait for each other, so all of them must be held by CTAs at the same time
+    if (kn.grid_cap > 0 && (unsigned long long)kn.grid_cap < cap) cap = kn.grid_cap < (int)channel_items ? channel_items : kn.grid_cap;
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = dsmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = kn.cooperative ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, fn, args);
 }
-
 
 }  // namespace flow
 }  // namespace cnsn

@@ -32,7 +32,7 @@ constexpr int kIbnT = 128;
 struct IArgs {
     const void* x; const void* dy; void* out;
     int N, C, M, half;
-    int nI, order, poll_ns, pf_dist, training;
+    int nI, poll_ns, pf_dist, training;
     unsigned items;
     float eps_in, eps_bn, momentum;
     const float* in_w; const float* in_b;       // [half]
@@ -44,23 +44,17 @@ struct IArgs {
     float2* pub;                                // [C][N] polled words
     float2* chan;                               // [C] x 4 (one sector per channel)
     unsigned* ticket;
+    unsigned* err;                              // asynchronous error word
 };
 
 template <typename T, bool BWD, int TPI>
-__global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
+__device__ __forceinline__ void ibn_res_item(const IArgs& a, const unsigned t, const unsigned par) {
     constexpr int TH = kIbnT, I = TH / TPI, V = VecOf<T>::n, kHold = 4;
     extern __shared__ __align__(128) unsigned char dsm[];
-    __shared__ unsigned s_word;
     __shared__ float2 s_chan;
     __shared__ float s_f[2][TH / 32];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
-    if (threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;
-    }
-    __syncthreads();
-    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned nI = (unsigned)a.nI;
     const unsigned c = t / nI, j = t - c * nI;
     const int N = a.N, C = a.C, M = a.M, half = a.half;
     const int n = (int)j * I + (int)(threadIdx.x / TPI);
@@ -74,13 +68,13 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
     if (threadIdx.x < 32) {
         const int first = (int)j * I, nlive = min(I, N - first);
         const uint64_t pol = l2_policy_evict_first();
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+            tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
         }
         const unsigned tf = t + (unsigned)a.pf_dist;
         if (a.pf_dist && tf < a.items) {
@@ -88,8 +82,8 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
             const int ff = (int)jf * I, nf = min(I, N - ff);
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
-                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+                tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
             }
         }
     }
@@ -105,7 +99,7 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
         if (is_in) { if (live) { mean = a.in_mean[(size_t)n * half + c]; rstd = a.in_rstd[(size_t)n * half + c]; } }
         else { mean = a.bn_mean[cb]; rstd = a.bn_rstd[cb]; }
     }
-    fused::mbar_wait(bar, 0);
+    mbar_wait(bar, par, a.err);
 
     // ---- per-instance reduction ------------------------------------------------------------------
     float own_x = 0.f, own_y = 0.f;                          // forward (mean, M2); backward (A, B)
@@ -149,7 +143,7 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
         }
     }
     // published when somebody will read it: the channel merge (training batch norm), the parameter gradients
-    if (live && r == 0 && (coupled || BWD)) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    if (live && r == 0 && (coupled || BWD)) ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
 
     // ---- channel constants -------------------------------------------------------------------------
     float2* flag = a.chan + 4u * c;
@@ -160,21 +154,21 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
         for (int u = 0; u < kHold; ++u) {
             const int k = threadIdx.x + u * TH;
             hold[u] = make_float2(0.f, 0.f);
-            if (k < N) hold[u] = poll_word(pb + k, 100);
+            if (k < N) hold[u] = poll_word(pb + k, 100, a.err);
         }
-        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100);
+        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100, a.err);
         float v[2] = {0.f, 0.f};
         if (!BWD) {                                          // Chan merge of N equal-sized (mean, M2) pairs
 #pragma unroll
             for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) v[0] += hold[u].x;
-            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) v[0] += fused::ll_peek(pb + k).x;
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) v[0] += ll_peek(pb + k).x;
             cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[0]), reinterpret_cast<float(*)[TH / 32]>(s_f[0]));
             const float cmean = v[0] / N;
 #pragma unroll
             for (int u = 0; u < kHold; ++u)
                 if (threadIdx.x + u * TH < N) { const float d = hold[u].x - cmean; v[1] += hold[u].y + M * d * d; }
             for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
-                const float2 p = fused::ll_peek(pb + k);
+                const float2 p = ll_peek(pb + k);
                 const float d = p.x - cmean;
                 v[1] += p.y + M * d * d;
             }
@@ -183,7 +177,7 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
             const float var_b = v[1] / cnt;
             const float crstd = 1.f / sqrtf(var_b + a.eps_bn);
             if (threadIdx.x == 0) {
-                fused::ll_publish(flag, cmean, crstd);
+                ll_publish(flag, cmean, crstd);
                 s_chan = make_float2(cmean, crstd);
                 a.bn_mean[cb] = cmean; a.bn_rstd[cb] = crstd;
                 a.run_mean[cb] = (1.f - a.momentum) * a.run_mean[cb] + a.momentum * cmean;
@@ -193,12 +187,12 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
         } else {                                             // channel sums of (A, B): dbeta, dgamma, and for batch norm the means
 #pragma unroll
             for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) { v[0] += hold[u].x; v[1] += hold[u].y; }
-            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] += p.x; v[1] += p.y; }
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = ll_peek(pb + k); v[0] += p.x; v[1] += p.y; }
             cta_sums<2, TH>(v, s_f);
             if (threadIdx.x == 0) {
                 if (coupled) {
                     const float inv = 1.f / ((float)N * (float)M);
-                    fused::ll_publish(flag, v[0] * inv, v[1] * inv);
+                    ll_publish(flag, v[0] * inv, v[1] * inv);
                     s_chan = make_float2(v[0] * inv, v[1] * inv);
                 }
                 if (is_in) { a.d_in_b[c] = v[0]; a.d_in_w[c] = v[1]; }
@@ -206,7 +200,7 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
             }
         }
     } else if (coupled && threadIdx.x == 0) {
-        s_chan = poll_word(flag, a.poll_ns);
+        s_chan = poll_word(flag, a.poll_ns, a.err);
     }
     if (coupled) __syncthreads();                            // CTA-uniform
     if (!live) return;
@@ -247,6 +241,11 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
     }
 }
 
+template <typename T, bool BWD, int TPI>
+__global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
+    CNSN_TICKET_LOOP(a, (ibn_res_item<T, BWD, TPI>(a, t, it & 1u)))
+}
+
 template <bool BWD>
 static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     const int N = a.N, C = a.C;
@@ -260,8 +259,10 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     const DeviceShape ds = device_shape();
     if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_UNSUPPORTED;
     a.nI = (N + inst - 1) / inst;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    const Knobs& kn = knobs();
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
+    a.poll_ns = kn.poll_ns;
+    a.err = async_error_word();
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return CNSN_E_UNSUPPORTED;
     a.items = (unsigned)items;
@@ -279,10 +280,11 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         /* a channel must be co-resident when its items wait for each other (training-mode batch-norm channels); */ \
         /* instance-norm channels never wait (their folder only collects words of earlier tickets) */          \
         if (a.half < C && a.training && (long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;    \
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);                                        \
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;                                            \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
-        fn<<<dim3((unsigned)items), dim3(kIbnT), dsmem, stream>>>(a);                                    \
+        e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kIbnT, dsmem, stream);                     \
+        if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_IBN_CASE(8) CNSN_IBN_CASE(16) CNSN_IBN_CASE(32) CNSN_IBN_CASE(64) CNSN_IBN_CASE(128)

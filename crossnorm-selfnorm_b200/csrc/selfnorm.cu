@@ -14,7 +14,7 @@
 
 #include <algorithm>
 
-#include "common.cuh"
+#include "flow_common.cuh"
 
 namespace cnsn {
 
@@ -288,25 +288,6 @@ struct SaveLayout {           // offsets (in floats) into the save block
     }
 };
 
-namespace fused {
-int selfnorm_fused_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
-                       const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
-                       float* mu, float* sd, float* gate, float* shat, float* r, float* scratch_floats,
-                       cudaStream_t stream);
-int selfnorm_fused_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
-                       const cnsn_gate_params* g, int training,
-                       float* mu, float* sd, float* gate, float* shat, float* r,
-                       const cnsn_gate_grads* dg, float* scratch_floats, cudaStream_t stream);
-}
-namespace cluster {
-int selfnorm_cluster_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
-                         const cnsn_gate_params* g, int training, float momentum, float bn_eps, float eps,
-                         float* mu, float* sd, float* gate, float* shat, float* r, cudaStream_t stream);
-int selfnorm_cluster_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
-                         const cnsn_gate_params* g, int training,
-                         float* mu, float* sd, float* gate, float* shat, float* r,
-                         const cnsn_gate_grads* dg, cudaStream_t stream);
-}
 namespace flow {
 size_t scratch_floats(int N, int C);
 int selfnorm_flow_fwd(const void* x, const void* res, void* z, void* y, int relu, int dtype, int N, int C, int H, int W,
@@ -318,15 +299,10 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
                       float* mu, float* sd, float* gate, float* shat, float* r,
                       const cnsn_gate_grads* dg, float* scratch, cudaStream_t stream);
 }
-// CNSN_SELFNORM_IMPL selects the path for A/B measurements: "v1" = three kernels, "cluster" = one 16-CTA
-// cluster per channel (selfnorm_cluster.cu), "flow" = ticket-ordered dataflow kernel (selfnorm_flow.cu),
-// "persistent" = the persistent fused kernels (selfnorm_fused.cu), unset = the default dispatch.
-enum { kImplAuto = 0, kImplV1 = 1, kImplCluster = 2, kImplFlow = 3, kImplPersistent = 4 };
-static int impl_choice() {
-    const char* e = getenv("CNSN_SELFNORM_IMPL");
-    if (!e) return kImplAuto;
-    return e[0] == 'v' ? kImplV1 : e[0] == 'c' ? kImplCluster : e[0] == 'f' ? kImplFlow : e[0] == 'p' ? kImplPersistent : kImplAuto;
-}
+// cnsn_tune("selfnorm_impl", v) selects the path for A/B measurements and tests: 1 = three kernels, 3 = the dataflow
+// kernels only, 0 = the default dispatch (dataflow kernels, three-kernel path for shapes they do not take).
+enum { kImplAuto = 0, kImplV1 = 1, kImplFlow = 3 };
+static int impl_choice() { return knobs().selfnorm_impl; }
 
 static bool gate_ok(const cnsn_gate_params* p) { return p && p->w && p->gamma && p->beta && p->run_mean && p->run_var; }
 
@@ -376,19 +352,6 @@ static int selfnorm_fwd_impl(const void* x, const void* res, void* z, void* y, i
         if (arc) return arc;
         x = z;
     }
-    const bool plain = !res && !relu;                // the A/B kernels know nothing of the block fusion
-    if (plain && !two && impl_choice() == kImplCluster) {
-        const int frc = cluster::selfnorm_cluster_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
-                                                      save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
-                                                      save + L.r_g, s);
-        if (frc != -100) return frc;
-    }
-    if (plain && !two && impl_choice() == kImplPersistent) {
-        const int frc = fused::selfnorm_fused_fwd(x, y, dtype, N, C, H, W, g, training, momentum, bn_eps, eps,
-                                                  save + L.mu, save + L.sd, save + L.g, save + L.shat_g,
-                                                  save + L.r_g, save + L.scratch, s);
-        if (frc != -100) return frc;         // -100: shape not eligible, use the three-kernel path
-    }
     const Window full{0, H, 0, W};
     int rc = launch_instance_stats(x, dtype, inst, H, W, full, eps, save + L.mu, save + L.sd, s);
     if (rc) return rc;
@@ -437,24 +400,11 @@ static int selfnorm_bwd_impl(const void* x, const void* dy, void* dx, int relu, 
     const size_t nc = (size_t)inst;
     float* sxy = workspace; float* st = workspace + nc; float* cb = workspace + 2 * nc; float* cc = workspace + 3 * nc;
     cudaStream_t s = (cudaStream_t)stream;
-    // Default: the dataflow kernel (3*S of HBM traffic).  The persistent and cluster kernels stay selectable for
-    // A/B measurements (CNSN_SELFNORM_IMPL=persistent|cluster|v1).
+    // Default: the dataflow kernels (3*S of HBM traffic).
     if (!two && (impl_choice() == kImplFlow || impl_choice() == kImplAuto)) {
         float* sv = const_cast<float*>(save);
         const int frc = flow::selfnorm_flow_bwd(x, dy, dx, relu, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
                                                 sv + L.g, sv + L.shat_g, sv + L.r_g, dg, workspace, s);
-        if (frc != -100) return frc;
-    }
-    if (!relu && !two && impl_choice() == kImplCluster) {
-        float* sv = const_cast<float*>(save);
-        const int frc = cluster::selfnorm_cluster_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
-                                                      sv + L.g, sv + L.shat_g, sv + L.r_g, dg, s);
-        if (frc != -100) return frc;
-    }
-    if (!relu && !two && impl_choice() == kImplPersistent) {
-        float* sv = const_cast<float*>(save);
-        const int frc = fused::selfnorm_fused_bwd(x, dy, dx, dtype, N, C, H, W, g, training, sv + L.mu, sv + L.sd,
-                                                  sv + L.g, sv + L.shat_g, sv + L.r_g, dg, workspace, s);
         if (frc != -100) return frc;
     }
     const bool vec = vec_ok2(x, dy, dtype, M) && aligned16(dx);

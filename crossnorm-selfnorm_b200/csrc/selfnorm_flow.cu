@@ -130,12 +130,10 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
     __shared__ Moments s_m[kT / 32];
 
     // ---- which item am I --------------------------------------------------------------------
-    unsigned t = blockIdx.x;
-    if (a.order == 0) {
-        if (threadIdx.x == 0) s_word = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        t = s_word;
-    }
+    if (threadIdx.x == 0) s_word = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned t = s_word;
+    __syncthreads();                                         // s_word is reused below
     const unsigned nI = (unsigned)a.nI, D = (unsigned)a.D, C = (unsigned)a.C;
     bool isA;
     unsigned c, j;
@@ -178,8 +176,8 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
         if (a.pf_dist && c + (unsigned)a.pf_dist < C && r == 0 && live) {
             const size_t off = ((size_t)n * C + c + (unsigned)a.pf_dist) * M;
             const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T);
-            fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-            if (two) fused::tma_prefetch_l2(static_cast<const T*>(BWD ? a.dy : a.res) + off, pbytes);
+            tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+            if (two) tma_prefetch_l2(static_cast<const T*>(BWD ? a.dy : a.res) + off, pbytes);
         }
         Moments acc = moments_zero();
         for (int i0 = r; i0 < nv; i0 += kStep) {
@@ -271,11 +269,16 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
         if (BWD) { p_b = a.r[c]; p_gt = a.gate[nc]; p_mu = a.mu[nc]; p_sd = a.sd[nc]; }
         else p_b = a.beta[c];
     }
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0) {                                  // the R items of c hold smaller tickets: they run or are done
         unsigned spins = 0;
+        unsigned long long t0 = 0;
         while (ld_acquire_u32(a.ready + c) == 0u) {
             __nanosleep(64);
-            if (++spins > kSpin) __trap();
+            if ((++spins & 0xfffu) == 0) {
+                const unsigned long long now = gtime();
+                if (!t0) t0 = now;
+                else if (now - t0 > kWaitBoundNs) { report_timeout(a.err, kErrPollTimeout); break; }
+            }
         }
     }
     __syncthreads();
@@ -351,7 +354,7 @@ __global__ void __launch_bounds__(kT, (BWD || ADD) ? 4 : 5) k_sn_flow(const FArg
 // resident.  Twice the instances fit on chip, at 7 L2 transactions per byte of S instead of 6 (both planes
 // resident) or 8 (k_sn_flow).  For channels whose x AND dy do not fit the GPU's shared memory.
 template <typename T, bool BWD, bool ADD, bool DYG, int TPI, int TH>
-__global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
+__device__ __forceinline__ void sn_res_item(const FArgs& a, const unsigned t, const unsigned par) {
     static_assert(!(BWD && ADD), "the fused add is a forward feature");
     static_assert(BWD || !DYG, "DYG is a backward variant");
     constexpr bool two = (BWD && !DYG) || ADD;               // a second plane per instance in shared memory: dy / res
@@ -359,17 +362,10 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
     extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
-    __shared__ unsigned s_word;
     __shared__ float2 s_chan;
     __shared__ float s_f[2][TH / 32];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
-    if (threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;   // the counter starts at 0xffffffff
-    }
-    __syncthreads();
-    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned nI = (unsigned)a.nI;
     const unsigned c = t / nI, j = t - c * nI;
     const int N = a.N, C = a.C, M = a.M;
     CNSN_FTRACE(0);                                          // 0 ticket taken
@@ -386,13 +382,13 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         const int nlive = min(I, N - first);
         const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
         const T* second = static_cast<const T*>(BWD ? a.dy : a.res);
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (two ? 2u : 1u));
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (two ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (two) fused::tma_load_1d(dst + (size_t)I * pbytes, second + off, pbytes, bar, pol);   // not for DYG
+            tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (two) tma_load_1d(dst + (size_t)I * pbytes, second + off, pbytes, bar, pol);   // not for DYG
         }
         // L2 prefetch for the CTA that will take this one's place: its TMA loads then hit L2 instead of paying
         // the HBM latency (and its tail) while its shared memory is already tied up.  Same L2 traffic.
@@ -402,8 +398,8 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
             const int ff = (int)jf * I, nf = min(I, N - ff);
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
-                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (two || DYG) fused::tma_prefetch_l2(second + off, pbytes);
+                tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (two || DYG) tma_prefetch_l2(second + off, pbytes);
             }
         }
     }
@@ -430,7 +426,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         }
     };
     if (DYG) issue_dy(r, pol_keep);
-    fused::mbar_wait(bar, 0);
+    mbar_wait(bar, par, a.err);
     CNSN_FTRACE(1);                                          // 1 planes landed
 
     // ---- reduce out of shared memory -----------------------------------------------------------
@@ -516,7 +512,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     // eval mode: the channel constants are the running statistics (forward) / vanish (backward, k1 = k2 = 0):
     // nothing to wait for -- a single pass per instance.  Backward still publishes (parameter gradients).
     const bool batch_coupled = a.training != 0;
-    if (live && r == 0 && (BWD || batch_coupled)) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    if (live && r == 0 && (BWD || batch_coupled)) ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
     CNSN_FTRACE(2);                                          // 2 reduced + published
 
     // ---- channel constants ------------------------------------------------------------------------
@@ -536,7 +532,7 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
         CNSN_FTRACE(3);                                      // 3 (folder) channel folded
         if (threadIdx.x == 0) s_chan = cst;
     } else if (threadIdx.x == 0) {
-        s_chan = poll_word(flag, a.poll_ns);
+        s_chan = poll_word(flag, a.poll_ns, a.err);
     }
     __syncthreads();
     CNSN_FTRACE(4);                                          // 4 channel constants known
@@ -601,6 +597,11 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
     CNSN_FTRACE(5);                                          // 5 applied
 }
 
+template <typename T, bool BWD, bool ADD, bool DYG, int TPI, int TH>
+__global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
+    CNSN_TICKET_LOOP(a, (sn_res_item<T, BWD, ADD, DYG, TPI, TH>(a, t, it & 1u)))
+}
+
 // =============================================================================================
 // Channel-group variant of the shared-memory-resident kernel, for planes that are NOT a multiple of 16 bytes
 // (7x7 fp32 = 196 B, 14x14 bf16 = 392 B, 7x7 bf16 = 98 B: the last two stages of ResNet-50).  kk adjacent
@@ -613,23 +614,16 @@ __global__ void __launch_bounds__(TH) k_sn_res(const FArgs a) {
 constexpr int kGrpT = 128;
 
 template <typename T, bool BWD, bool ADD, int TPI>
-__global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
+__device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, const unsigned par) {
     static_assert(!(BWD && ADD), "the fused add is a forward feature");
     constexpr int TH = kGrpT, P = kGrpT / TPI;
     constexpr int V = VecOf<T>::n;
     constexpr bool two = BWD || ADD;
     extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I super-planes of x | I of dy / res]
-    __shared__ unsigned s_word;
     __shared__ float4 s_coef[P];                             // per instance: out = .x*dy + .y*x + .z
     __shared__ float s_f[2][TH / 32];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
-    if (threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;
-    }
-    __syncthreads();
-    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned nI = (unsigned)a.nI;
     const unsigned g = t / nI, j = t - g * nI;
     const int N = a.N, C = a.C, M = a.M, kk = a.kk, I = P / kk;
     const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T), sp = (unsigned)kk * pbytes;
@@ -639,13 +633,13 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
     if (threadIdx.x < 32) {                                  // lane q fetches sample q's run of kk planes
         const uint64_t pol = l2_policy_evict_first();
         const T* second = static_cast<const T*>(BWD ? a.dy : a.res);
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * sp * (two ? 2u : 1u));
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nlive * sp * (two ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + (size_t)g * kk) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * sp;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, sp, bar, pol);
-            if (two) fused::tma_load_1d(dst + soff2, second + off, sp, bar, pol);
+            tma_load_1d(dst, static_cast<const T*>(a.x) + off, sp, bar, pol);
+            if (two) tma_load_1d(dst + soff2, second + off, sp, bar, pol);
         }
         const unsigned tf = t + (unsigned)a.pf_dist;
         if (a.pf_dist && tf < a.items) {
@@ -653,8 +647,8 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
             const int ff = (int)jf * I, nf = min(I, N - ff);
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + (size_t)gf * kk) * M;
-                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, sp);
-                if (two) fused::tma_prefetch_l2(second + off, sp);
+                tma_prefetch_l2(static_cast<const T*>(a.x) + off, sp);
+                if (two) tma_prefetch_l2(second + off, sp);
             }
         }
     }
@@ -678,7 +672,7 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
     } else {
         p_b = a.beta[c];
     }
-    fused::mbar_wait(bar, 0);
+    mbar_wait(bar, par, a.err);
     const int vps = (int)(sp / 16u), nvec = nlive * vps;     // 128-bit vectors per super-plane / in the item
     if (ADD) {                                               // z = x + res over the item, in place and written out
         for (int vi = threadIdx.x; vi < nvec; vi += TH) {
@@ -717,7 +711,7 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
         own_x = mean; own_y = sqrtf(m2 / (M - 1.f) + a.eps);
         if (live && r == 0) { a.mu[nc] = own_x; a.sd[nc] = own_y; }
     }
-    if (live && r == 0 && (BWD || batch_coupled)) fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    if (live && r == 0 && (BWD || batch_coupled)) ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
     // ---- channel constants ------------------------------------------------------------------------
     if (BWD || batch_coupled) {                              // channel k of the group: folded by ticket nI-1-(k mod nI)
         for (int k = (int)(nI - 1u - j); k < kk; k += (int)nI) {
@@ -731,7 +725,7 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
     }
     float2 cm;
     if (batch_coupled) {
-        cm = poll_word(a.chan + 4u * c, a.poll_ns);          // 4 lanes per address; the folder's own words are there
+        cm = poll_word(a.chan + 4u * c, a.poll_ns, a.err);          // 4 lanes per address; the folder's own words are there
     } else if (BWD) {
         cm = make_float2(0.f, 0.f);
     } else {
@@ -777,6 +771,11 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
     }
 }
 
+template <typename T, bool BWD, bool ADD, int TPI>
+__global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
+    CNSN_TICKET_LOOP(a, (sn_grp_item<T, BWD, ADD, TPI>(a, t, it & 1u)))
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -786,7 +785,7 @@ __global__ void __launch_bounds__(kGrpT) k_sn_grp(const FArgs a) {
 // (256,256,56,56) fp32: TPI 64 (4 batches of 4 loads) is the optimum; 6 batches is the rule that reproduces the
 // measured optimum on the other shapes as well (profiles/README.md).
 static int pick_tpi(int nv) {
-    const int batches = env_int("CNSN_FLOW_BATCHES", 6);
+    const int batches = knobs().flow_batches;
     int tpi = 8;
     while (tpi < kT && tpi * kUReg * batches < nv) tpi <<= 1;
     return tpi;
@@ -800,20 +799,21 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     if (N < 1 || C < 1) return -100;
     const int nv = a.M * esz / 16;
     int tpi = pick_tpi(nv);
-    if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kT && (v & (v - 1)) == 0) tpi = v; }
+    const Knobs& kn = knobs();
+    if (const int v = kn.flow_tpi) { if (v >= 8 && v <= kT && (v & (v - 1)) == 0) tpi = v; }
     const int I = kT / tpi;
     a.nI = (N + I - 1) / I;
     // Look-ahead: enough channels to cover the R items in flight plus the fold latency, bounded by L2.
     const size_t chan_bytes = (size_t)N * a.M * esz * (BWD ? 2 : 1);
-    int D = (int)(((size_t)env_int("CNSN_FLOW_LOOKAHEAD_MB", 40) << 20) / (chan_bytes ? chan_bytes : 1));
+    int D = (int)(((size_t)kn.lookahead_mb << 20) / (chan_bytes ? chan_bytes : 1));
     if (D < 2) D = 2;
-    if (const int v = env_int("CNSN_FLOW_D", 0)) D = v;
+    if (const int v = kn.flow_d) D = v;
     if (D > C) D = C;
     if (D < 1) D = 1;
     a.D = D;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
-    a.keep = env_int("CNSN_FLOW_KEEP", 1);
-    a.pf_dist = env_int("CNSN_FLOW_RPF", 0);               // R items: L2 prefetch distance in channels (0 = off)
+    a.keep = kn.keep;
+    a.pf_dist = kn.rpf;                                    // R items: L2 prefetch distance in channels (0 = off)
+    a.err = async_error_word();
     const unsigned long long items = 2ull * C * a.nI;
     if (items > 0x7fffffffull) return -100;
     // scratch: pub [C][N] float2 | chan [C] float2 | done [C] | ready [C] | ticket
@@ -835,16 +835,16 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
         default: return -100;
     });
 #undef CNSN_FLOW_CASE
-    if (getenv("CNSN_FLOW_DEBUG"))
-        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu order=%d add=%d relu=%d\n", BWD ? "bwd" : "fwd", tpi, I,
-                a.nI, D, items, a.order, a.res != nullptr, a.relu);
+    if (kn.debug)
+        fprintf(stderr, "[cnsn flow] %s tpi=%d I=%d nI=%d D=%d items=%llu add=%d relu=%d\n", BWD ? "bwd" : "fwd", tpi, I,
+                a.nI, D, items, a.res != nullptr, a.relu);
     return launch_status();
 }
 
 
 constexpr int kResT = 128;              // threads per CTA of the shared-memory-resident kernel
 
-// EXPERIMENT, opt-in (CNSN_FLOW_I3=1), forward only, not measured yet: items of THREE planes and
+// EXPERIMENT, opt-in (cnsn_tune("i3", 1)), forward only: items of THREE planes and
 // 192 threads (64 per plane).  At the north-star plane size (12.5 KB) an SM holds 8 items x 2 planes = 16 planes with
 // the default geometry and cannot take a ninth; 6 items x 3 planes = 18 planes fit the same 228 KB.  Same kernel
 // template (it is generic in TH and TPI); only taken when the default geometry would be two planes per item.
@@ -857,15 +857,16 @@ static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t strea
     const DeviceShape ds = device_shape();
     a.nI = (N + kI3 - 1) / kI3;
     a.D = 0;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
+    const Knobs& kn = knobs();
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return -100;
     a.pub = reinterpret_cast<float2*>(scratch);
     a.chan = a.pub + (size_t)N * C;
     a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
     a.done = nullptr; a.ready = nullptr; a.trace = nullptr;
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.poll_ns = kn.poll_ns;
     a.items = (unsigned)items;
+    a.err = async_error_word();
     const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
@@ -874,12 +875,13 @@ static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t strea
         e = prepare_kernel(fn, kT3, dsmem, &per_sm);
         if (e != cudaSuccess) return (int)e;
         if ((long long)per_sm * ds.sms < 2ll * a.nI) return -100;
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
         if (e != cudaSuccess) return (int)e;
-        fn<<<dim3((unsigned)items), dim3(kT3), dsmem, stream>>>(a);
+        e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kT3, dsmem, stream);
+        if (e != cudaSuccess) return (int)e;
     });
-    if (getenv("CNSN_FLOW_DEBUG"))
+    if (kn.debug)
         fprintf(stderr, "[cnsn flow/res-i3] fwd tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d\n", kTpi3, kI3, a.nI, items, dsmem, per_sm);
     return launch_status();
 }
@@ -892,15 +894,16 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     if (((size_t)a.M * esz) % 16 || N < 1 || C < 1) return -100;
     const bool add = !BWD && a.res != nullptr;
     const bool dyg = BWD && dy_from_global;
-    if (!BWD && !add && env_int("CNSN_FLOW_I3", 0)) {
+    const Knobs& kn = knobs();
+    if (!BWD && !add && kn.i3) {
         const int rc3 = launch_res_i3(a, dtype, scratch, stream);
         if (rc3 != -100) return rc3;
     }
     const size_t inst_bytes = (size_t)a.M * esz * (((BWD && !dyg) || add) ? 2 : 1);
-    const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
+    const size_t target = (size_t)kn.item_kb << 10;
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
-    if (const int v = env_int("CNSN_FLOW_TPI", 0)) { if (v >= 8 && v <= kResT && (v & (v - 1)) == 0) inst = kResT / v; }
+    if (const int v = kn.flow_tpi) { if (v >= 8 && v <= kResT && (v & (v - 1)) == 0) inst = kResT / v; }
     const int tpi = kResT / inst;
     const size_t dsmem = 128 + (size_t)inst * inst_bytes;
     const DeviceShape ds = device_shape();
@@ -908,7 +911,6 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     if (dsmem > (size_t)ds.smem_optin / 2) return -100;      // at least two CTAs per SM
     a.nI = (N + inst - 1) / inst;
     a.D = 0;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return -100;
     // scratch: pub [C][N] float2 | channel words [C] x 4 float2 (one 32-byte sector each) | ticket.  Everything is
@@ -918,13 +920,13 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
     a.done = nullptr;
     a.ready = nullptr;
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.poll_ns = kn.poll_ns;
     a.items = (unsigned)items;
+    a.err = async_error_word();
     const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
-    const dim3 grid((unsigned)items), block(kResT);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
-    const char* trace_path = getenv("CNSN_FLOW_TRACE");      // debug: per-item timestamps (synchronous)
+    const char* trace_path = kn.trace ? getenv("CNSN_FLOW_TRACE") : nullptr;   // debug: per-item timestamps (synchronous)
     const size_t trace_bytes = (size_t)items * 8 * sizeof(unsigned long long);
     a.trace = nullptr;
     if (trace_path && cudaMalloc(&a.trace, trace_bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, trace_bytes, stream);
@@ -936,10 +938,11 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
         if (e != cudaSuccess) return (int)e;                                                             \
         /* the channel being completed must be resident as a whole (deadlock freedom), with room to spare */ \
         if ((long long)per_sm * sms < 2ll * a.nI) return -100;                                           \
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * sms / 2;                                               \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
-        fn<<<grid, block, dsmem, stream>>>(a);                                                           \
+        e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, sms, kResT, dsmem, stream);                        \
+        if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
         CNSN_RES_CASE(8) CNSN_RES_CASE(16) CNSN_RES_CASE(32) CNSN_RES_CASE(64) CNSN_RES_CASE(128)
@@ -959,9 +962,9 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
         free(h);
         cudaFree(a.trace);
     }
-    if (getenv("CNSN_FLOW_DEBUG"))
-        fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu order=%d smem=%zu ctas/sm=%d dyg=%d\n", BWD ? "bwd" : "fwd",
-                tpi, inst, a.nI, items, a.order, dsmem, per_sm, (int)dyg);
+    if (kn.debug)
+        fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d dyg=%d\n", BWD ? "bwd" : "fwd",
+                tpi, inst, a.nI, items, dsmem, per_sm, (int)dyg);
     return launch_status();
 }
 
@@ -978,7 +981,8 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (!kk) return -100;
     const bool add = !BWD && a.res != nullptr;
     const size_t ib = pb * ((BWD || add) ? 2 : 1);               // bytes per instance in shared memory
-    const size_t want = (size_t)env_int("CNSN_FLOW_GRP_KB", 20) << 10;      // item size aimed at
+    const Knobs& kn = knobs();
+    const size_t want = (size_t)kn.grp_kb << 10;                  // item size aimed at
     const int tpi = (32 * ib >= want || kk > 32) ? 4 : (64 * ib >= want || kk > 64) ? 2 : 1;
     const int I = (kGrpT / tpi) / kk;
     if (I < 1) return -100;
@@ -988,8 +992,8 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     a.kk = kk;
     a.nI = (N + I - 1) / I;
     a.D = 0;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    a.poll_ns = kn.poll_ns;
+    a.err = async_error_word();
     const unsigned long long items = (unsigned long long)(C / kk) * a.nI;
     if (items > 0x7fffffffull) return -100;
     a.items = (unsigned)items;
@@ -1007,12 +1011,13 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = prepare_kernel(fn, kGrpT, dsmem, &per_sm);
         if (e != cudaSuccess) return (int)e;
         if ((long long)per_sm * ds.sms < 2ll * a.nI) return -100;
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * ds.sms / 2);
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
         if (e != cudaSuccess) return (int)e;
-        fn<<<dim3((unsigned)items), dim3(kGrpT), dsmem, stream>>>(a);
+        e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kGrpT, dsmem, stream);
+        if (e != cudaSuccess) return (int)e;
     });
-    if (getenv("CNSN_FLOW_DEBUG"))
+    if (kn.debug)
         fprintf(stderr, "[cnsn flow/grp] %s kk=%d tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d add=%d\n", BWD ? "bwd" : "fwd", kk,
                 tpi, I, a.nI, items, dsmem, per_sm, (int)add);
     return launch_status();
@@ -1020,9 +1025,9 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
 
 // Which kernel: the shared-memory-resident one when a channel (all N planes, x [and dy]) is a small enough part
 // of the GPU's shared memory -- measured cross-over on B200 (profiles/README.md): 1/8 of 148 x 200 KB forward,
-// 1/16 backward (the L2-resident backward is the stronger alternative).  CNSN_FLOW_MODE=res|l2 forces one.
+// 1/16 backward (the L2-resident backward is the stronger alternative).  cnsn_tune("flow_mode", 1|2) forces one.
 static bool use_resident(size_t chan_bytes, bool bwd) {
-    if (const char* e = getenv("CNSN_FLOW_MODE")) return e[0] == 'r';
+    if (const int m = knobs().flow_mode) return m == 1;
     const size_t on_chip = (size_t)device_shape().sms * 200 * 1024;
     return chan_bytes * (bwd ? 16 : 8) <= on_chip;
 }
@@ -1035,6 +1040,7 @@ int selfnorm_flow_fwd(const void* x, const void* res, void* z, void* y, int relu
                       float* mu, float* sd, float* gate, float* shat, float* r, float* scratch,
                       cudaStream_t stream) {
     if (!aligned16(x) || !aligned16(y) || (res && (!aligned16(res) || !aligned16(z)))) return -100;
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
     FArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W;
     a.res = res; a.zout = res ? z : nullptr; a.relu = relu;
@@ -1055,6 +1061,7 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
                       float* mu, float* sd, float* gate, float* shat, float* r,
                       const cnsn_gate_grads* dg, float* scratch, cudaStream_t stream) {
     if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) return -100;
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
     FArgs a{};
     a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.M = H * W;
     a.relu = relu;
@@ -1065,12 +1072,11 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
     // backward: both planes resident when the channel is small, L2 items otherwise.  The third variant -- x
     // resident, dy streamed through L2 (DYG) -- measured slower than both on B200 (0.50-0.61 ms against 0.476 /
     // 0.511 at the north-star shape: two more L2 round trips per item outweigh the doubled capacity); it stays
-    // selectable.  CNSN_FLOW_BWD=res|dyg|l2 forces one (A/B measurements).
+    // selectable.  cnsn_tune("flow_bwd", 1|2|3) forces one (A/B measurements).
     const size_t chan_x = (size_t)N * H * W * esize(dtype);
     if ((((size_t)H * W * esize(dtype)) % 16) != 0) return launch_grp<true>(a, dtype, scratch, stream);
     int mode = use_resident(2 * chan_x, true) ? 0 : 2;
-    if (const char* e = getenv("CNSN_FLOW_BWD")) mode = e[0] == 'r' ? 0 : e[0] == 'd' ? 1 : 2;
-    else if (const char* m = getenv("CNSN_FLOW_MODE")) mode = m[0] == 'r' ? 0 : 2;
+    if (const int b = knobs().flow_bwd) mode = b - 1;          // 1 resident, 2 x resident + dy through L2, 3 L2 items
     if (mode < 2) {
         const int rc = launch_res<true>(a, dtype, scratch, stream, mode == 1);
         if (rc != -100) return rc;

@@ -15,7 +15,6 @@ struct FArgs {
     int nI;                 // items per channel and phase = ceil(N / I)
     int D;                  // look-ahead in channels (1..C)
     int training;
-    int order;              // 0: atomic ticket per CTA; 1: blockIdx.x (relies on in-order CTA dispatch)
     int keep;               // L2 policy of the R loads: 0 default, 1 evict_last (default: the A items re-read them)
     float momentum, bn_eps, eps;
     const float* w; const float* gamma; const float* beta;
@@ -31,6 +30,7 @@ struct FArgs {
     int kk;                 // channel-group kernel: adjacent channels per group
     int pf_dist;            // resident kernel: L2-prefetch the item pf_dist tickets ahead (0 = off)
     unsigned items;         // resident kernel: total tickets
+    unsigned* err;          // asynchronous error word (pinned host memory), see flow_common.cuh
     unsigned long long* trace;   // debug only (CNSN_FLOW_TRACE): [items][8] globaltimer stamps, else NULL
 };
 
@@ -49,9 +49,9 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
     for (int u = 0; u < kHold; ++u) {
         const int k = threadIdx.x + u * TH;
         hold[u] = make_float2(0.f, 0.f);
-        if (k < N) hold[u] = poll_word(pb + k, 100);
+        if (k < N) hold[u] = poll_word(pb + k, 100, a.err);
     }
-    for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100);   // N > kHold*TH: re-read below
+    for (int k = threadIdx.x + kHold * TH; k < N; k += TH) poll_word(pb + k, 100, a.err);   // N > kHold*TH: re-read below
     float v[2] = {0.f, 0.f};
     float2 cst;
     if (!BWD) {
@@ -59,7 +59,7 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
         if (a.training) {
 #pragma unroll
             for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) v[0] += fmaf(p_w0, hold[u].x, p_w1 * hold[u].y);
-            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] += fmaf(p_w0, p.x, p_w1 * p.y); }
+            for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = ll_peek(pb + k); v[0] += fmaf(p_w0, p.x, p_w1 * p.y); }
             cta_sums<1, TH>(*reinterpret_cast<float(*)[1]>(&v[0]), reinterpret_cast<float(*)[TH / 32]>(s_f[0]));
             m = v[0] / N;
             v[1] = 0.f;
@@ -67,7 +67,7 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
             for (int u = 0; u < kHold; ++u)
                 if (threadIdx.x + u * TH < N) { const float d = fmaf(p_w0, hold[u].x, p_w1 * hold[u].y) - m; v[1] = fmaf(d, d, v[1]); }
             for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
-                const float2 p = fused::ll_peek(pb + k);
+                const float2 p = ll_peek(pb + k);
                 const float d = fmaf(p_w0, p.x, p_w1 * p.y) - m;
                 v[1] = fmaf(d, d, v[1]);
             }
@@ -78,7 +78,7 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
         const float rstd = 1.f / sqrtf(q + a.bn_eps);
         cst = make_float2(m, rstd);
         if (threadIdx.x == 0) {
-            fused::ll_publish(flag, cst.x, cst.y);       // the channel is ready: 8 bytes, no fence
+            ll_publish(flag, cst.x, cst.y);       // the channel is ready: 8 bytes, no fence
                         a.r[c] = rstd;
             if (a.training) {
                 a.run_mean[c] = (1.f - a.momentum) * p_rm + a.momentum * m;
@@ -89,13 +89,13 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
     } else {
 #pragma unroll
         for (int u = 0; u < kHold; ++u) if (threadIdx.x + u * TH < N) { v[0] = fmaf(hold[u].x, hold[u].y, v[0]); v[1] += hold[u].x; }
-        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = fused::ll_peek(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
+        for (int k = threadIdx.x + kHold * TH; k < N; k += TH) { const float2 p = ll_peek(pb + k); v[0] = fmaf(p.x, p.y, v[0]); v[1] += p.x; }
         cta_sums<2, TH>(v, s_f);
         const float dgam = v[0], dbet = v[1];
         const float k1 = a.training ? p_ga * dbet * invN : 0.f, k2 = a.training ? p_ga * dgam * invN : 0.f;
         cst = make_float2(k1, k2);
         if (threadIdx.x == 0) {
-            fused::ll_publish(flag, cst.x, cst.y);
+            ll_publish(flag, cst.x, cst.y);
                         a.dgamma[c] = dgam; a.dbeta[c] = dbet;
         }
         // off the critical path: dw = (sum ds*mu, sum ds*sd)
@@ -110,7 +110,7 @@ __device__ __forceinline__ float2 fold_publish(const FArgs& a, unsigned c, float
             }
         }
         for (int k = threadIdx.x + kHold * TH; k < N; k += TH) {
-            const float2 p = fused::ll_peek(pb + k);
+            const float2 p = ll_peek(pb + k);
             const size_t i = (size_t)k * C + c;
             const float ds = p_b * (p.x * p_ga - k1 - p.y * k2);
             v[0] = fmaf(ds, a.mu[i], v[0]); v[1] = fmaf(ds, a.sd[i], v[1]);

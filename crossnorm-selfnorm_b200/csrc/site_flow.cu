@@ -70,23 +70,16 @@ __device__ __forceinline__ void cn_vec(const float (&vx)[VecOf<T>::n], float (&v
 }
 
 template <typename T, bool BWD, int TPI>
-__global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
+__device__ __forceinline__ void site_res_item(const SiteArgs& s, const unsigned t, const unsigned par) {
     constexpr int TH = kSiteT;
     constexpr int I = TH / TPI;
     constexpr int V = VecOf<T>::n;
     const FArgs& a = s.sn;
     extern __shared__ __align__(128) unsigned char dsm[];    // [mbarrier | I planes of x | I planes of dy]
-    __shared__ unsigned s_word;
     __shared__ float2 s_chan;
     __shared__ float s_f[4][TH / 32];
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
-    if (threadIdx.x == 0) {
-        fused::mbar_init(bar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        s_word = a.order == 0 ? atomicAdd(a.ticket, 1u) + 1u : blockIdx.x;   // the counter starts at 0xffffffff
-    }
-    __syncthreads();
-    const unsigned t = s_word, nI = (unsigned)a.nI;
+    const unsigned nI = (unsigned)a.nI;
     const unsigned c = t / nI, j = t - c * nI;
     const int N = a.N, C = a.C, H = s.H, W = s.W, M = a.M;
     const int n = (int)j * I + (int)(threadIdx.x / TPI);
@@ -101,13 +94,13 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         const int first = (int)j * I;
         const int nlive = min(I, N - first);
         const uint64_t pol = l2_policy_evict_first();        // read once: do not keep it in L2
-        if (threadIdx.x == 0) fused::mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (unsigned)nlive * pbytes * (BWD ? 2u : 1u));
         __syncwarp();
         for (int q = threadIdx.x; q < nlive; q += 32) {
             const size_t off = ((size_t)(first + q) * C + c) * M;
             unsigned char* dst = dsm + 128 + (size_t)q * pbytes;
-            fused::tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
-            if (BWD) fused::tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
+            tma_load_1d(dst, static_cast<const T*>(a.x) + off, pbytes, bar, pol);
+            if (BWD) tma_load_1d(dst + (size_t)I * pbytes, static_cast<const T*>(a.dy) + off, pbytes, bar, pol);
         }
         // L2 prefetch for the CTA that will take this one's place (see selfnorm_flow.cu)
         const unsigned tf = t + (unsigned)a.pf_dist;
@@ -116,8 +109,8 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
             const int ff = (int)jf * I, nf = min(I, N - ff);
             for (int q = threadIdx.x; q < nf; q += 32) {
                 const size_t off = ((size_t)(ff + q) * C + cf) * M;
-                fused::tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
-                if (BWD) fused::tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
+                tma_prefetch_l2(static_cast<const T*>(a.x) + off, pbytes);
+                if (BWD) tma_prefetch_l2(static_cast<const T*>(a.dy) + off, pbytes);
             }
         }
     }
@@ -145,7 +138,7 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         p_b = a.beta[c];
         if (folder && threadIdx.x == 0) { p_rm = a.run_mean[c]; p_rv = a.run_var[c]; }
     }
-    fused::mbar_wait(bar, 0);
+    mbar_wait(bar, par, a.err);
 
     float2* flag = a.chan + 4u * c;                          // one 32-byte sector per channel
     uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + nc * M);
@@ -156,11 +149,11 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         if (!same) sts = window_stats<T, TPI>(sx, W, M, sw, sfull, r, live, s.cn_eps, s_f[2], s_f[3]);
         if (live && r == 0) {
             s.mu_c[nc] = stc.x; s.sd_c[nc] = stc.y; s.mu_s[nc] = sts.x; s.sd_s[nc] = sts.y;
-            fused::ll_publish(s.pub_cn + (size_t)c * N + n, sts.x, sts.y);
+            ll_publish(s.pub_cn + (size_t)c * N + n, sts.x, sts.y);
         }
         float ca = 1.f, cb = 0.f;
         if (live) {
-            const float2 ps = poll_word(s.pub_cn + (size_t)c * N + src_n, a.poll_ns);   // the team polls one address
+            const float2 ps = poll_word(s.pub_cn + (size_t)c * N + src_n, a.poll_ns, a.err);   // the team polls one address
             const float A = ps.y / stc.y;
             ca = lam + (1.f - lam) * A;
             cb = (1.f - lam) * (ps.x - stc.x * A);
@@ -202,14 +195,14 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         }
         if (live && r == 0) {
             a.mu[nc] = own_x; a.sd[nc] = own_y;
-            fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+            ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
         }
         // ---- channel constants ---------------------------------------------------------------------------
         if (folder) {
             const float2 cst = fold_publish<false, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
             if (threadIdx.x == 0) s_chan = cst;
         } else if (threadIdx.x == 0) {
-            s_chan = poll_word(flag, a.poll_ns);
+            s_chan = poll_word(flag, a.poll_ns, a.err);
         }
         __syncthreads();
         if (!live) return;
@@ -294,16 +287,16 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         if (live && r == 0) {
             const float D0 = p_b * own_x * p_ga, D1 = -p_b, D2 = -p_b * own_y;
             float2* wp = s.pub_cn + ((size_t)c * N + src_n) * 3;
-            fused::ll_publish(wp, l1 * fmaf(D0, E1, base1), l2 * fmaf(D0, E2, base2));
-            fused::ll_publish(wp + 1, l1 * D1 * E1, l2 * D1 * E2);
-            fused::ll_publish(wp + 2, l1 * D2 * E1, l2 * D2 * E2);
-            fused::ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+            ll_publish(wp, l1 * fmaf(D0, E1, base1), l2 * fmaf(D0, E2, base2));
+            ll_publish(wp + 1, l1 * D1 * E1, l2 * D1 * E2);
+            ll_publish(wp + 2, l1 * D2 * E1, l2 * D2 * E2);
+            ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
         }
         if (folder) {
             const float2 cst = fold_publish<true, TH>(a, c, flag, p_w0, p_w1, p_ga, p_b, p_rm, p_rv, s_f);
             if (threadIdx.x == 0) s_chan = cst;
         } else if (threadIdx.x == 0) {
-            s_chan = poll_word(flag, a.poll_ns);
+            s_chan = poll_word(flag, a.poll_ns, a.err);
         }
         __syncthreads();
         if (!live) return;
@@ -315,7 +308,7 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
         const float S2 = l2 * fmaf(dsn, E2, base2);
         // this instance as somebody's style source: that instance's three words (published before its own wait)
         const float2* wq = s.pub_cn + ((size_t)c * N + n) * 3;
-        const float2 q0 = poll_word(wq, a.poll_ns), q1 = poll_word(wq + 1, a.poll_ns), q2 = poll_word(wq + 2, a.poll_ns);
+        const float2 q0 = poll_word(wq, a.poll_ns, a.err), q1 = poll_word(wq + 1, a.poll_ns, a.err), q2 = poll_word(wq + 2, a.poll_ns, a.err);
         const float2 ds = make_float2(fmaf(q2.x, cm.y, fmaf(q1.x, cm.x, q0.x)), fmaf(q2.y, cm.y, fmaf(q1.y, cm.x, q0.y)));
         // CrossNorm backward inside the content window: dx = p*dz + q*x + r0; as somebody's style source: += u*x + v
         const float p = lam + (1.f - lam) * A;
@@ -355,6 +348,11 @@ __global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
     }
 }
 
+template <typename T, bool BWD, int TPI>
+__global__ void __launch_bounds__(kSiteT, 8) k_site_res(const SiteArgs s) {
+    CNSN_TICKET_LOOP(s.sn, (site_res_item<T, BWD, TPI>(s, t, it & 1u)))
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -365,7 +363,7 @@ static bool site_shape(int dtype, int N, int C, int M, bool bwd, SiteShape& g) {
     const int esz = (int)esize(dtype);
     if (((size_t)M * esz) % 16 || N < 2 || C < 1 || M < 2) return false;
     const size_t inst_bytes = (size_t)M * esz * (bwd ? 2 : 1);
-    const size_t target = (size_t)env_int("CNSN_FLOW_ITEM_KB", 25) << 10;
+    const size_t target = (size_t)knobs().item_kb << 10;
     int inst = 1;
     while (inst < 16 && (size_t)(2 * inst) * inst_bytes <= target + 512 && 2 * inst <= N) inst <<= 1;
     g.inst = inst;
@@ -386,8 +384,9 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
     if (!site_shape(dtype, N, C, a.M, BWD, g)) return -100;
     const int sms = device_shape().sms;
     a.nI = g.nI;
-    a.order = env_int("CNSN_FLOW_ORDER", 0);
-    a.poll_ns = env_int("CNSN_FLOW_POLL_NS", 100);
+    const Knobs& kn = knobs();
+    a.poll_ns = kn.poll_ns;
+    if (!dry_run) a.err = async_error_word();
     a.items = (unsigned)((unsigned long long)C * g.nI);
     // scratch: sn words [C][N] | channel words [C] x 4 (one 32-byte sector each) | ticket | cn words [C][N] (forward)
     // or [C][N][3] (backward); all 0xff
@@ -396,7 +395,6 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
     a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
     s.pub_cn = a.chan + 4 * (size_t)C + 1;
     const size_t fill_bytes = ((BWD ? 4 : 2) * (size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
-    const dim3 grid(a.items), block(kSiteT);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
 #define CNSN_SITE_CASE(TPI_)                                                                             \
@@ -406,17 +404,18 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
         if (e != cudaSuccess) return (int)e;                                                             \
         if ((long long)per_sm * sms < 2ll * g.nI) return -100;    /* a whole channel must be co-resident */ \
         if (dry_run) return 0;                                                                           \
-        a.pf_dist = env_int("CNSN_FLOW_PF", per_sm * sms / 2);                                             \
+        a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * sms / 2;                                               \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
-        fn<<<grid, block, g.dsmem, stream>>>(s);                                                         \
+        e = launch_persistent(fn, s, a.items, (unsigned)a.nI, per_sm, sms, kSiteT, g.dsmem, stream);                     \
+        if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (g.tpi) {
         CNSN_SITE_CASE(8) CNSN_SITE_CASE(16) CNSN_SITE_CASE(32) CNSN_SITE_CASE(64) CNSN_SITE_CASE(128)
         default: return -100;
     });
 #undef CNSN_SITE_CASE
-    if (getenv("CNSN_FLOW_DEBUG"))
+    if (kn.debug)
         fprintf(stderr, "[cnsn flow/site] %s tpi=%d I=%d nI=%d items=%u smem=%zu ctas/sm=%d\n", BWD ? "bwd" : "fwd", g.tpi, g.inst,
                 g.nI, a.items, g.dsmem, per_sm);
     return launch_status();
@@ -455,6 +454,7 @@ static int site_check(const void* x, const void* out, int dtype, int N, int C, i
     if (check_window(cw, H, W) || check_window(sw, H, W)) return CNSN_E_BADARG;
     if (N < 2) return CNSN_E_BATCH1;                 // BatchNorm1d raises ValueError in the reference
     if (!aligned16(x) || !aligned16(out)) return CNSN_E_UNSUPPORTED;
+    if (async_error_peek()) return CNSN_E_TIMEOUT;
     return 0;
 }
 

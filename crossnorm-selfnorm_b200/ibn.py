@@ -10,6 +10,16 @@ import torch.nn as nn
 
 from .functional import IbnFn
 
+
+def bn_momentum(bn):
+    """The exponential-average factor torch's batch norm uses for this call: ``momentum``, or -- ``momentum=None`` --
+    the cumulative average 1 / (num_batches_tracked + 1) (a host read of the counter: rare configuration)."""
+    if bn.momentum is not None:
+        return float(bn.momentum)
+    if not bn.training or bn.num_batches_tracked is None:
+        return 0.0
+    return 1.0 / (int(bn.num_batches_tracked) + 1)
+
 __all__ = ["IBN", "InstanceNorm2d"]
 
 
@@ -23,7 +33,7 @@ class IBN(nn.Module):
     def forward(self, x):
         assert x.dim() == 4
         bn = self.BN
-        momentum = 0.1 if bn.momentum is None else float(bn.momentum)
+        momentum = bn_momentum(bn)
         return IbnFn.apply(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps),
                            (bn.running_mean, bn.running_var, bn.num_batches_tracked),
                            self.IN.weight, self.IN.bias, bn.weight, bn.bias)

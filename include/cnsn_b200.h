@@ -13,8 +13,9 @@
  *     .contiguous() itself at models/cnsn.py:14,16); element type given by `dtype`;
  *   - per-instance statistics, parameters, gradients of parameters and workspaces are fp32;
  *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous and stream-ordered;
- *   - the library never allocates: workspaces / save areas are caller-owned, sizes come from
- *     the *_floats() helpers; it keeps no mutable state besides the launch counter;
+ *   - the library never allocates device memory: workspaces / save areas are caller-owned, sizes come
+ *     from the *_floats() helpers; its only state is the launch counter, the tuning knobs of cnsn_tune()
+ *     and one 64-byte pinned host word for asynchronous errors (cnsn_async_error);
  *   - return value: 0 on success, a positive cudaError_t, or a negative CNSN_E_* code;
  *     cnsn_error_string() renders either.
  *   - windows are half-open [h0,h1) x [w0,w1) in NCHW rows/cols.  NOTE the reference names
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CNSN_ABI_VERSION 4
+#define CNSN_ABI_VERSION 5
 
 enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
 
@@ -40,9 +41,11 @@ enum {
     CNSN_E_WORKSPACE = -2,/* workspace too small */
     CNSN_E_BATCH1 = -3,   /* SelfNorm training with N == 1 (reference: BatchNorm1d ValueError) */
     CNSN_E_ALIGN = -4,    /* tensor base pointer not aligned to its element size */
-    CNSN_E_UNSUPPORTED = -5 /* shape outside what this operator's kernels handle (cnsn_site_*: planes must be 16-byte
+    CNSN_E_UNSUPPORTED = -5,/* shape outside what this operator's kernels handle (cnsn_site_*: planes must be 16-byte
                              multiples and a channel's N planes must fit the GPU's shared memory; ask
                              cnsn_site_supported() first) */
+    CNSN_E_TIMEOUT = -6   /* an EARLIER kernel of this process gave up a bounded wait (peer CTA / bulk copy); its results
+                             are undefined.  Reported by the next call and by cnsn_async_error(); never a device trap */
 };
 
 /* Library / ABI identification. */
@@ -50,6 +53,19 @@ int cnsn_version(void);
 const char* cnsn_error_string(int code);
 /* Number of CUDA kernels this library has launched in this process (monotonic, atomic). */
 unsigned long long cnsn_launch_count(void);
+/*
+ * Asynchronous error state.  The dataflow kernels wait for peer CTAs with bounded polls; a wait that expires
+ * (seconds -- a debugger, a sanitizer or a bug) records a code in a pinned word instead of trapping, so the CUDA
+ * context survives.  Returns CNSN_OK or CNSN_E_TIMEOUT; `clear` != 0 resets the state.  Every dataflow entry point
+ * also checks it and refuses to launch (CNSN_E_TIMEOUT) until it has been cleared.
+ */
+int cnsn_async_error(int clear);
+/*
+ * Measurement / test hook, not part of the drop-in surface: set one process-wide tuning knob by name ("reset"
+ * restores the defaults).  The library never reads environment variables; the names are those of struct Knobs in
+ * csrc/flow_common.cuh.  Returns CNSN_E_BADARG for an unknown name.
+ */
+int cnsn_tune(const char* name, int value);
 
 /*
  * Per-(n,c) mean and std = sqrt(unbiased_var + eps) over the window.

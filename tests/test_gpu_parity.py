@@ -12,6 +12,8 @@ import torch
 import helpers as H
 from oracle import cnsn_oracle as O
 
+import cnsn_b200._lib as L
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
@@ -206,7 +208,7 @@ def test_crossnorm_vs_oracle_f32(mod, shape, crop, chan, lam, impl, monkeypatch)
     shared-memory-resident dataflow kernel where it applies: no channel permutation, 16-byte planes) and through
     the two-kernel path (forced)."""
     if impl != "auto":
-        monkeypatch.setenv("CNSN_CROSSNORM_IMPL", impl)
+        L.tune(crossnorm_impl=impl)
     x = O.varied_input(shape, seed=11, dtype=np.float32)
     dy = np.random.RandomState(12).standard_normal(shape).astype(np.float32)
     y, dx = H.run_crossnorm(mod, x, dy, DEV, crop, chan, lam, 21, 22)
@@ -221,7 +223,7 @@ def test_crossnorm_vs_oracle_f32(mod, shape, crop, chan, lam, impl, monkeypatch)
 def test_crossnorm_cfg2_bf16(mod, impl, monkeypatch):
     """BASELINE config 2: CrossNorm (2-instance swap, no crop) on (128,64,32,32) bf16."""
     if impl != "auto":
-        monkeypatch.setenv("CNSN_CROSSNORM_IMPL", impl)
+        L.tune(crossnorm_impl=impl)
     shape = (128, 64, 32, 32)
     x = torch.randn(shape, generator=torch.Generator().manual_seed(0)).to(torch.bfloat16).float().numpy()
     dy = torch.randn(shape, generator=torch.Generator().manual_seed(1)).to(torch.bfloat16).float().numpy()
@@ -237,21 +239,26 @@ def test_crossnorm_cfg2_bf16(mod, impl, monkeypatch):
                                               ((256, 128, 8, 8), torch.float32, "content"), ((128, 64, 32, 32), torch.float16, "style"),
                                               ((48, 3, 224, 224), torch.float32, "both")])
 def test_crossnorm_large_flow_vs_two_kernel(mod, shape, dtype, crop, monkeypatch):
-    """Training-size tensors (the WideResNet sites, image-space CrossNorm): the dataflow kernel against the
-    two-kernel path on identical inputs and identical RNG draws (both are oracle-checked at small sizes above)."""
+    """Training-size tensors (the WideResNet sites, image-space CrossNorm): the dataflow kernel against the ORACLE on
+    a channel subset (CrossNorm without channel permutation couples only instances of the same channel, so the oracle
+    restricted to a few channels is exact for them), and against the two-kernel path on the whole tensor."""
     g = torch.Generator().manual_seed(5)
     x = (torch.randn(shape, generator=g) * (0.5 + torch.rand(shape[0], shape[1], 1, 1, generator=g)) + torch.randn(shape[0], shape[1], 1, 1, generator=g))
     x = x.to(dtype).float().numpy()
     dy = torch.randn(shape, generator=g).to(dtype).float().numpy()
     y0, dx0 = H.run_crossnorm(mod, x, dy, DEV, crop, False, None, 7, 8, dtype)
-    monkeypatch.setenv("CNSN_CROSSNORM_IMPL", "v1")
+    chk = close32 if dtype == torch.float32 else close16
+    torch.manual_seed(7)
+    np.random.seed(8)
+    plan = O.draw_plan(shape, crop=crop, beta=1, chan=False)
+    cs = sorted({0, shape[1] // 2, shape[1] - 1})
+    for c in cs:
+        chk(y0[:, c:c + 1], O.crossnorm_fwd(x[:, c:c + 1], plan), "y (oracle, channel %d)" % c)
+        chk(dx0[:, c:c + 1], O.crossnorm_bwd(x[:, c:c + 1], dy[:, c:c + 1], plan), "dx (oracle, channel %d)" % c)
+    L.tune(crossnorm_impl="v1")
     y1, dx1 = H.run_crossnorm(mod, x, dy, DEV, crop, False, None, 7, 8, dtype)
-    if dtype == torch.float32:
-        close32(y0, y1, "y")
-        close32(dx0, dx1, "dx")
-    else:
-        close16(y0, y1, "y")
-        close16(dx0, dx1, "dx")
+    chk(y0, y1, "y")
+    chk(dx0, dx1, "dx")
 
 
 # ------------------------------------------------------------------ properties (size independent)
@@ -299,13 +306,14 @@ def test_selfnorm_permutation_equivariance(mod):
     assert torch.allclose(m1(x)[p], m2(x[p]), atol=1e-6)
 
 
-@pytest.mark.parametrize("impl", ["auto", "persistent"])
-def test_selfnorm_north_star_shape_properties(mod, impl, monkeypatch):
-    """Full-size (256,256,56,56) fp32: too big for the numpy oracle in seconds, so check
-    size-independent properties: y/x is constant per instance and equals the saved gate; linearity
-    of backward in dy; and a strided subset of instances against the oracle restricted to 2 channels."""
-    if impl != "auto":
-        monkeypatch.setenv("CNSN_SELFNORM_IMPL", impl)
+@pytest.mark.parametrize("fwd_mode,bwd_mode", [("auto", "auto"), ("l2", "res")])
+def test_selfnorm_north_star_shape_properties(mod, fwd_mode, bwd_mode):
+    """Full-size (256,256,56,56) fp32 -- too big for the numpy oracle in seconds, so: the oracle restricted to a
+    channel subset (the gate couples only instances of the SAME channel) for y, dx, dW, dgamma, dbeta AND the running
+    buffers -- the channel fold with N = 256 and 64-128 items per channel is a geometry no small test reaches --
+    plus size-independent properties (linearity of backward in dy).  Default dispatch (resident forward, L2-item
+    backward) and the other pairing (L2-item forward, resident backward)."""
+    L.tune(flow_mode=fwd_mode, flow_bwd=bwd_mode)
     N, C, Hh, Ww = 256, 256, 56, 56
     g = torch.Generator(device=DEV).manual_seed(0)
     x = torch.randn(N, C, Hh, Ww, device=DEV, generator=g) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, device=DEV, generator=g)) \
@@ -315,9 +323,9 @@ def test_selfnorm_north_star_shape_properties(mod, impl, monkeypatch):
     x.requires_grad_(True)
     y = m(x)
     dy = torch.randn(N, C, Hh, Ww, device=DEV, generator=g)
-    (dx,) = torch.autograd.grad(y, x, dy)
-    # oracle on channels {3, 200}: the gate couples only instances of the SAME channel
-    for c in (3, 200):
+    (dx, dw, dgam, dbet) = torch.autograd.grad(y, (x, m.g_fc.weight, m.g_bn.weight, m.g_bn.bias), dy)
+    assert int(m.g_bn.num_batches_tracked) == 1
+    for c in (0, 3, 200, 255):
         xs = x.detach()[:, c:c + 1].cpu().numpy()
         dys = dy[:, c:c + 1].cpu().numpy()
         ps = {k: v[c:c + 1] for k, v in params.items()}
@@ -325,13 +333,18 @@ def test_selfnorm_north_star_shape_properties(mod, impl, monkeypatch):
         o = H.oracle_selfnorm(xs, dys, ps, bs, True)
         close32(y.detach()[:, c:c + 1].cpu().numpy(), o["y"], "y")
         close32(dx[:, c:c + 1].cpu().numpy(), o["dx"], "dx")
+        assert H.relmax(dw[c:c + 1].cpu().numpy(), o["dg_w"]) <= H.PARAM_RTOL, ("dW", c)
+        assert H.relmax(dgam[c:c + 1].cpu().numpy(), o["dg_gamma"]) <= H.PARAM_RTOL, ("dgamma", c)
+        assert H.relmax(dbet[c:c + 1].cpu().numpy(), o["dg_beta"]) <= H.PARAM_RTOL, ("dbeta", c)
+        close32(m.g_bn.running_mean[c:c + 1].cpu().numpy(), o["g_rm_after"], "running_mean")
+        close32(m.g_bn.running_var[c:c + 1].cpu().numpy(), o["g_rv_after"], "running_var")
     # linearity of the backward map in dy
     y2 = m(x)
     (dx2,) = torch.autograd.grad(y2, x, 2.0 * dy)
     assert torch.allclose(dx2, 2.0 * dx, rtol=1e-4, atol=1e-5)
 
 
-# ------------------------------------------------------------------ fused persistent kernel (tensors >= 8 MB)
+# ------------------------------------------------------------------ every SelfNorm code path (tensors >= 8 MB among them)
 FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.float32), ((256, 64, 14, 14), torch.float32),
                 ((256, 256, 7, 7), torch.float32), ((512, 32, 16, 16), torch.float32), ((96, 24, 28, 28), torch.float32),
                 ((256, 16, 56, 56), torch.bfloat16), ((300, 20, 20, 20), torch.float32), ((40, 6, 224, 224), torch.float32),
@@ -369,45 +382,26 @@ def test_selfnorm_edge_shapes_default_dispatch(mod, shape, dtype):
 
 @pytest.mark.parametrize("shape,dtype", FUSED_SHAPES)
 @pytest.mark.parametrize("training", [True, False])
-def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training, monkeypatch):
-    """Every SelfNorm code path -- the default dispatch (dataflow kernel), the three-kernel path, the persistent
-    two-stream kernels (forced), the cluster kernels, the dataflow kernel in ticket and blockIdx order -- against
-    the oracle on identical inputs."""
+def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training):
+    """Every SelfNorm code path -- the default dispatch, the three-kernel path, the dataflow kernels with L2 items
+    (look-ahead 1 as well), with shared-memory-resident items, with x resident and dy through L2 -- against the oracle
+    on identical inputs."""
     x = O.varied_input(shape, seed=sum(shape), dtype=np.float32, relu=True)
     dy = np.random.RandomState(1).standard_normal(shape).astype(np.float32)
     if dtype != torch.float32:
         x = torch.from_numpy(x).to(dtype).float().numpy()
         dy = torch.from_numpy(dy).to(dtype).float().numpy()
     params, bufs = H.random_sn_params(shape[1], seed=3)
-    r = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)          # default dispatch
-    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "v1")                                     # three-kernel path
-    v1 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_SELFNORM_IMPL")
-    monkeypatch.setenv("CNSN_FUSED_FORCE", "1")                                        # persistent two-stream fwd + bwd
-    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "persistent")
-    fz = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_FUSED_FORCE")
-    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "cluster")                                # 16-CTA cluster per channel (falls
-    cl = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)         # back where it does not apply)
-    monkeypatch.setenv("CNSN_SELFNORM_IMPL", "flow")                                   # ticket-ordered dataflow kernel
-    fl = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.setenv("CNSN_FLOW_ORDER", "1")                                         # blockIdx order, look-ahead 1
-    monkeypatch.setenv("CNSN_FLOW_D", "1")
-    fl2 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_FLOW_ORDER")
-    monkeypatch.delenv("CNSN_FLOW_D")
-    monkeypatch.setenv("CNSN_FLOW_MODE", "l2")                                         # L2-resident second read (registers)
-    fl3 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.setenv("CNSN_FLOW_MODE", "res")                                        # shared-memory-resident planes
-    fl5 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_FLOW_MODE")
-    monkeypatch.setenv("CNSN_FLOW_BWD", "dyg")                                         # backward: x resident, dy through L2
-    fl4 = H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype)
-    monkeypatch.delenv("CNSN_FLOW_BWD")
-    monkeypatch.delenv("CNSN_SELFNORM_IMPL")
+    runs = []
+    for knobs in ({}, {"selfnorm_impl": "v1"}, {"selfnorm_impl": "flow"}, {"selfnorm_impl": "flow", "flow_mode": "l2", "flow_bwd": "l2"},
+                  {"selfnorm_impl": "flow", "flow_mode": "l2", "flow_bwd": "l2", "flow_d": 1},
+                  {"selfnorm_impl": "flow", "flow_mode": "res", "flow_bwd": "res"}, {"selfnorm_impl": "flow", "flow_bwd": "dyg"},
+                  {"cooperative": 0}, {"grid_cap": 24}):
+        with L.tuned(**knobs):
+            runs.append(H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype))
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
     chk = close32 if dtype == torch.float32 else close16
-    for res in (r, v1, fz, cl, fl, fl2, fl3, fl4, fl5):
+    for res in runs:
         chk(res["y"], o["y"], "y")
         chk(res["dx"], o["dx"], "dx")
         for k in ("dg_w", "dg_gamma", "dg_beta"):

@@ -4,7 +4,7 @@ CUDA events around the batch (so host time per call is hidden as long as it is b
     python tools/perf_cabi.py selfnorm|block|crossnorm N,C,H,W f32|bf16 [crop] [reps]
 `block` = cnsn_selfnorm_block_fwd/_bwd: relu(SelfNorm(x + res)), algorithmic bytes 4*S forward (x, res in; z, y out),
 3*S backward; the last line of its output times the unfused sequence (torch add, SelfNorm, torch relu) for context.
-Environment knobs (CNSN_SELFNORM_IMPL, CNSN_CROSSNORM_IMPL, CNSN_FLOW_*) are read by the library per call.
+Tuning knobs: CNSN_TUNE_<KNOB>=value in the environment of THIS tool (it forwards them through cnsn_tune; the library itself never reads the environment).
 """
 import ctypes
 import os
@@ -16,6 +16,8 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 from cnsn_b200 import _lib as L  # noqa: E402
+
+L.tune_from_env()                  # CNSN_TUNE_<KNOB>=value -> cnsn_tune
 
 op = sys.argv[1]
 shape = tuple(int(v) for v in sys.argv[2].split(","))
@@ -106,7 +108,7 @@ def timeit(fn):
 fwd()
 tf, hf = timeit(fwd)
 tb, hb = timeit(bwd)
-tag = " ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("CNSN_") or k == "PERF_EVAL")
+tag = " ".join("%s=%s" % (k, v) for k, v in sorted(os.environ.items()) if k.startswith("CNSN_TUNE_") or k == "PERF_EVAL")
 kf = 4 if op == "block" else 2
 print("%s %s %s crop=%s [%s] | fwd %.1f us (host %.1f) %.0f GB/s | bwd %.1f us (host %.1f) %.0f GB/s | fwd+bwd %.0f GB/s" % (
     op, shape, str(dt).split(".")[-1], crop, tag or "-", tf, hf, kf * S / tf / 1e3, tb, hb, 3 * S / tb / 1e3, (kf + 3) * S / (tf + tb) / 1e3))

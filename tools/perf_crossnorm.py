@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import cnsn_b200.cnsn as M  # noqa: E402
+import cnsn_b200._lib as _L  # noqa: E402
+
+_L.tune_from_env()                 # CNSN_TUNE_<KNOB>=value -> cnsn_tune
 from oracle import eager_chain as E  # noqa: E402
 
 shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "128,64,32,32").split(","))

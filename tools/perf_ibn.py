@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import torch.nn as nn  # noqa: E402
 from cnsn_b200.ibn import IBN  # noqa: E402
+import cnsn_b200._lib as _L  # noqa: E402
+
+_L.tune_from_env()
 
 
 class ReferenceIBN(nn.Module):

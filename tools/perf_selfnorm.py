@@ -1,7 +1,7 @@
 """Quick A/B timing of SelfNorm forward / backward (CUDA events, inputs larger than L2 by default).
 
     python tools/perf_selfnorm.py [N,C,H,W] [f32|bf16] [steps]
-Environment knobs are read by the library per call: CNSN_SELFNORM_IMPL=v1|persistent|cluster|flow, CNSN_FUSED_FORCE=1, CNSN_FUSED_CTAS=<n>.
+Tuning knobs: CNSN_TUNE_<KNOB>=value in this tool's environment (forwarded through cnsn_tune), e.g. CNSN_TUNE_FLOW_MODE=res CNSN_TUNE_I3=1.
 """
 import os
 import sys
@@ -10,6 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import cnsn_b200.cnsn as M  # noqa: E402
+import cnsn_b200._lib as _L  # noqa: E402
+
+_L.tune_from_env()                 # CNSN_TUNE_<KNOB>=value -> cnsn_tune
 
 shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,256,56,56").split(","))
 dt = torch.bfloat16 if len(sys.argv) > 2 and sys.argv[2] == "bf16" else torch.float32
@@ -37,6 +40,6 @@ torch.cuda.synchronize()
 f = sorted(e[0].elapsed_time(e[1]) for e in ev)
 b = sorted(e[1].elapsed_time(e[2]) for e in ev)
 fm, bm = f[len(f) // 2], b[len(b) // 2]
-tag = "%simpl=%s ctas=%s" % ("EVAL " if os.environ.get("PERF_EVAL") else "", os.environ.get("CNSN_SELFNORM_IMPL", "auto"), os.environ.get("CNSN_FUSED_CTAS", "all"))
+tag = "%s%s" % ("EVAL " if os.environ.get("PERF_EVAL") else "", " ".join("%s=%s" % (k[10:].lower(), v) for k, v in sorted(os.environ.items()) if k.startswith("CNSN_TUNE_")) or "defaults")
 print("%s %s %s | fwd %.3f ms (min %.3f) %.0f GB/s | bwd %.3f ms (min %.3f) %.0f GB/s | fwd+bwd %.0f GB/s" % (
     shape, str(dt).split(".")[-1], tag, fm, f[0], 2 * S / fm / 1e6, bm, b[0], 3 * S / bm / 1e6, 5 * S / (fm + bm) / 1e6))

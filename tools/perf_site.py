@@ -12,6 +12,9 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 import cnsn_b200.cnsn as M  # noqa: E402
+import cnsn_b200._lib as _L  # noqa: E402
+
+_L.tune_from_env()                 # CNSN_TUNE_<KNOB>=value -> cnsn_tune
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 dev = "cuda:0"

@@ -2,8 +2,8 @@
 
     python tools/sweep_selfnorm.py N,C,H,W f32|bf16 steps "K1=V1 K2=V2" "K1=V3" ...
 
-Each quoted argument is one configuration: environment variables the library reads per call
-(CNSN_SELFNORM_IMPL, CNSN_SELFNORM_BWD, CNSN_FLOW_D, CNSN_FLOW_ORDER, CNSN_FLOW_KEEP, ...).  "-" = defaults.
+Each quoted argument is one configuration: tuning knobs of the library (cnsn_tune; struct Knobs in
+csrc/flow_common.cuh), e.g. "flow_mode=res i3=1" or "flow_bwd=dyg".  "-" = defaults.
 """
 import os
 import sys
@@ -12,6 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import cnsn_b200.cnsn as M  # noqa: E402
+import cnsn_b200._lib as L  # noqa: E402
 
 shape = tuple(int(v) for v in sys.argv[1].split(","))
 dt = torch.bfloat16 if sys.argv[2] == "bf16" else torch.float32
@@ -28,8 +29,8 @@ S = x.numel() * x.element_size()
 ref = None
 for cfg in configs:
     kv = dict(p.split("=", 1) for p in cfg.split()) if cfg != "-" else {}
-    for k, v in kv.items():
-        os.environ[k] = v
+    L.tune(reset=1)
+    L.tune(**kv)
     try:
         ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
         for i in range(3):
@@ -59,5 +60,4 @@ for cfg in configs:
         print("%s [%s] FAILED: %r" % (shape, cfg, e), flush=True)
         break
     finally:
-        for k in kv:
-            os.environ.pop(k, None)
+        L.tune(reset=1)

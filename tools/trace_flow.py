@@ -1,4 +1,4 @@
-"""Per-item timeline of the shared-memory-resident SelfNorm kernel (debug build knob CNSN_FLOW_TRACE).
+"""Per-item timeline of the shared-memory-resident SelfNorm kernel (debug knob: cnsn_tune("trace", 1) + $CNSN_FLOW_TRACE = output path).
 
     python tools/trace_flow.py [N,C,H,W] [fwd|bwd] [out.bin]
 Prints median / p90 of every phase of an item's life and the per-channel critical path.
@@ -13,12 +13,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 import cnsn_b200.cnsn as M  # noqa: E402
+import cnsn_b200._lib as L  # noqa: E402
 
 shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,256,56,56").split(","))
 bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
 out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "flow_trace.bin")
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
-os.environ.setdefault("CNSN_FLOW_MODE", "res")
+L.tune(flow_mode="res", flow_bwd="res")
+L.tune_from_env()
 x = torch.randn(shape, device="cuda:0").requires_grad_(True)
 dy = torch.randn(shape, device="cuda:0")
 sn = M.SelfNorm(shape[1]).cuda().train()
@@ -28,12 +30,14 @@ torch.cuda.synchronize()
 if bwd:
     y = sn(x)
     os.environ["CNSN_FLOW_TRACE"] = out
+    L.tune(trace=1)
     torch.autograd.grad(y, x, dy)
 else:
     os.environ["CNSN_FLOW_TRACE"] = out
+    L.tune(trace=1)
     sn(x)
 torch.cuda.synchronize()
-del os.environ["CNSN_FLOW_TRACE"]
+L.tune(trace=0)
 raw = open(out, "rb").read()
 items, nI, per_sm, isb = struct.unpack("4i", raw[:16])
 t = np.frombuffer(raw[16:], dtype=np.uint64).reshape(items, 8).astype(np.float64)
