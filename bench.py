@@ -14,9 +14,11 @@ One "step" = one forward + one backward pass of the hot path over one synthetic 
   e2e        the same metric through the nn.Module API with HOST (pinned) buffers: per step
              H2D of x and dy, forward, backward, D2H of y and dx inside the timed region
              (double-buffered over three streams, as a data loader would feed it)
+  sustained  the same step back to back for >= 1 s with clock sampling (the timed region proper is ~16 ms)
   cpu_baseline / --impl reference
-             the eager-PyTorch op chain of the reference (oracle/eager_chain.py, bit-identical
-             to models/cnsn.py on CPU) timed on this box's host cores on a bounded sample
+             the reference's OWN models/cnsn.py (oracle/_ref, copied at build time by oracle/build_ref.py; the
+             bit-identical eager port oracle/eager_modules.py when that copy is absent) on this box's host
+             cores, SAME shape; --impl reference honours --steps / --warmup (same config, same steps)
   crossnorm  secondary: CrossNorm fwd+bwd through cn_op_2ins_space_chan (BASELINE config 2, a WideResNet
              site with crops, a north-star-sized tensor)
   site       secondary: a CNSN site with both operators firing, fused site kernels vs the two-operator sequence
@@ -40,7 +42,6 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 NORTH_STAR = (256, 256, 56, 56)
-CPU_SAMPLE_N = 32                     # bounded CPU sample: N=32 of 256 instances per channel
 
 
 def parse():
@@ -53,6 +54,7 @@ def parse():
     ap.add_argument("--dtype", default="f32", choices=["f32", "bf16"])
     ap.add_argument("--no-train", action="store_true", help="skip the secondary WRN-40-2 measurement")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 1 s back-to-back run")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-crossnorm", action="store_true", help="skip the secondary CrossNorm measurements")
     ap.add_argument("--train-batch", type=int, default=512)
@@ -143,56 +145,110 @@ def bind_to_gpu_numa(index):
         return "unavailable: %r" % (e,)
 
 
+def workload_config(shape, dtype, world):
+    """The `config` object of the JSON line -- identical in both arms (the reference arm runs the SAME workload)."""
+    N, C, H, W = shape
+    S = N * C * H * W * (4 if dtype == "f32" else 2)
+    return {"workload": "SelfNorm fwd+bwd train-mode, NCHW %s (%d,%d,%d,%d) per GPU, S=%d bytes; "
+                        "independent per-GPU batches, no data-path collective" % (dtype, N, C, H, W, S),
+            "l2": "inputs (x, dy: %.0f MB each) larger than the 126 MB L2; no flush needed" % (S / 1e6),
+            "parallelism": "replicated shards x%d" % world}
+
+
+METRIC = "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)"
+
+
 # ----------------------------------------------------------------------------- CPU reference arm
+def reference_ops():
+    """(module, kind, what): the reference's OWN models/cnsn.py from oracle/_ref (copied there at build time by
+    oracle/build_ref.py; travels to the GPU box) -> kind "reference"; else the bit-identical eager-PyTorch port."""
+    from oracle import build_ref
+    mod = build_ref.load("models.cnsn")
+    if mod is not None:
+        return mod, "reference", "the reference's own models/cnsn.py (oracle/_ref, unmodified)"
+    from oracle import eager_modules
+    return eager_modules, "port", "eager-PyTorch port of models/cnsn.py (oracle/eager_modules.py; oracle/_ref absent)"
+
+
 def cpu_reference_selfnorm(shape, steps, warmup):
-    """Eager-PyTorch chain of the reference on this box's host cores (bounded sample)."""
+    """The reference SelfNorm module (models/cnsn.py:113-150), forward + autograd backward, on this box's host cores
+    with every thread torch can use, on the SAME shape as the GPU arm.  Returns the cpu_baseline object + timings."""
     import torch
-    from oracle import eager_chain as E
+    ops, kind, what = reference_ops()
     cores = len(os.sched_getaffinity(0))
     torch.set_num_threads(cores)
     N, C, H, W = shape
-    sample = (min(N, CPU_SAMPLE_N), C, H, W)
-    times = E.time_selfnorm_fwd_bwd(sample, steps, warmup, threads=cores)
-    S = sample[0] * C * H * W * 4
+    gen = torch.Generator().manual_seed(1234)
+    x = (torch.randn(shape, generator=gen) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, generator=gen))
+         + torch.randn(N, C, 1, 1, generator=gen)).requires_grad_(True)
+    dy = torch.randn(shape, generator=gen)
+    sn = ops.SelfNorm(C).train()
+    times = []
+    for i in range(warmup + steps):
+        x.grad = None
+        sn.zero_grad(set_to_none=True)
+        t0 = time.perf_counter()
+        y = sn(x)
+        y.backward(dy)
+        t1 = time.perf_counter()
+        if i >= warmup:
+            times.append(t1 - t0)
+        del y
+    S = N * C * H * W * 4
     t = sum(times) / len(times)
-    return {"value": 5 * S / t / 1e9, "unit": "GB/s", "cores": cores, "kind": "port",
-            "sample": "SelfNorm fwd+bwd fp32 on (%d,%d,%d,%d) = N %d of %d, %d steps after %d warm-up, mean; "
-                      "eager-PyTorch op chain of models/cnsn.py (oracle/eager_chain.py)" % (*sample, sample[0], N, steps, warmup),
+    return {"value": 5 * S / t / 1e9, "unit": "GB/s", "cores": cores, "kind": kind,
+            "sample": "SelfNorm fwd+bwd fp32 on the full (%d,%d,%d,%d) tensor, %d steps after %d warm-up, mean wall clock; %s, "
+                      "torch.set_num_threads(%d)" % (N, C, H, W, steps, warmup, what, cores),
             "ms_per_step": t * 1e3, "best_ms": min(times) * 1e3}
 
 
 def run_reference_arm(args, shape):
+    """`--impl reference`: the reference's CPU implementation of the path on the box's host cores, SAME config, metric,
+    unit, --steps and --warmup as the GPU arm.  Rank 0 alone runs; the other ranks exit at once."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 8))
-    warm = max(1, min(args.warmup, 2))
-    cb = cpu_reference_selfnorm(shape, steps, warm)
+    cb = cpu_reference_selfnorm(shape, args.steps, args.warmup)
     train = None
     if not args.no_train:
-        try:                                     # secondary: the same training step with the eager-PyTorch CNSN on CPU
+        try:                                     # secondary: the same training steps with the reference CNSN on CPU
             import torch
-            from cnsn_b200.train import bench_wrn
-            from oracle import eager_modules
-            train = bench_wrn(torch.device("cpu"), 1, 0, batch=64, steps=2, warmup=1, ops=eager_modules)
-            train["sample"] = "batch 64 (of 512), 2 steps after 1 warm-up, CPU, eager-PyTorch CNSN (oracle/eager_modules.py)"
-            from cnsn_b200.train import bench_resnet50_cpu
-            train["resnet50"] = bench_resnet50_cpu(eager_modules, batch=16, steps=1, warmup=1)
+            from cnsn_b200.train import bench_resnet50_cpu, bench_wrn
+            ops, kind, what = reference_ops()
+            train = bench_wrn(torch.device("cpu"), 1, 0, batch=64, steps=2, warmup=1, ops=ops)
+            train["sample"] = "batch 64 (of 512), 2 steps after 1 warm-up, CPU, CNSN operators: %s" % what
+            train["resnet50"] = bench_resnet50_cpu(ops, batch=16, steps=1, warmup=1)
         except Exception as e:
             train = {"error": repr(e)[:300]}
     line = {
-        "impl": "reference", "metric": "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)",
-        "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+        "impl": "reference", "metric": METRIC,
+        "value": cb["value"], "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SelfNorm fwd+bwd train-mode, NCHW fp32 (%d,%d,%d,%d); CPU arm runs a bounded "
-                               "sample of it (see cpu_baseline.sample)" % shape},
+        "config": workload_config(shape, "f32", max(1, args.gpus)),
         "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": cb["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "train_summary": train_summary(train),
         "train": train,
     }
     print(json.dumps(line), flush=True)
+
+
+def train_summary(train):
+    """The training-step numbers (BASELINE.json `metric`: WRN-40-2 images/s at 1/2/4/8 GPUs) in compact form, printed
+    right after `value` so that a truncated record still carries them."""
+    if not isinstance(train, dict) or "value" not in train:
+        return None
+    out = {"wrn_img_s": round(train["value"], 1), "wrn_ms": round(train["ms_per_step"], 3), "n_gpus": train.get("n_gpus")}
+    for key, short in (("resnet50", "r50"), ("resnet50_jsd", "jsd")):
+        t = train.get(key)
+        if isinstance(t, dict) and "value" in t:
+            out[short + "_img_s"] = round(t["value"], 1)
+            out[short + "_ms"] = round(t["ms_per_step"], 2)
+    if "graph" in train:
+        out["wrn_graph"] = train["graph"]
+    return out
 
 
 def bench_crossnorm(torch, M, dev, steps=30):
@@ -358,6 +414,23 @@ def main():
         except Exception:
             traffic = None
 
+    # ---- the same step back to back for >= 1 s: what the clocks do under sustained load (the 20-step timed region above
+    # lasts ~16 ms -- two or three clock samples)
+    sustained = None
+    if not args.no_sustained:
+        n_s = max(args.steps, int(1.2 / (ms_step * 1e-3)))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        with ClockSampler(physical_gpu_index(local), period=0.02) as clk_s:
+            s0.record()
+            for _ in range(n_s):
+                step()
+            s1.record()
+            torch.cuda.synchronize()
+        s_ms = s0.elapsed_time(s1) / n_s
+        sustained = {"value": 5 * S / (s_ms * 1e-3) / 1e9, "unit": "GB/s per GPU", "ms_per_step": s_ms, "steps": n_s,
+                     "seconds": s_ms * n_s * 1e-3, "frac_of_peak": 5 * S / (s_ms * 1e-3) / 1e9 / peak, "clocks": clk_s.summary()}
+
     # ---- e2e: module API with HOST pinned buffers, copies inside the timed region
     e2e = None
     if not args.no_e2e:
@@ -460,19 +533,17 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_reference_selfnorm(shape, 6, 1)
+        cpu = cpu_reference_selfnorm(shape, 4, 1)           # bounded: 5 passes of the full tensor, a few seconds
         cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     if rank == 0:
         line = {
-            "metric": "CNSN fwd+bwd GB/s (SelfNorm, algorithmic 5*S bytes per step)",
-            "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC,
+            "value": value, "unit": "GB/s", "train_summary": train_summary(train),
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": "SelfNorm fwd+bwd train-mode, NCHW %s (%d,%d,%d,%d) per GPU, S=%d bytes; "
-                                   "independent per-GPU batches, no data-path collective" % (args.dtype, *shape, S),
-                       "l2": "inputs (x, dy: %.0f MB each) larger than the 126 MB L2; no flush needed" % (S / 1e6),
-                       "parallelism": "replicated shards x%d" % world},
+            "config": workload_config(shape, args.dtype, world),
             "roofline": {"bound": "hbm", "achieved": bwd_gbs, "peak": peak, "unit": "GB/s", "frac": bwd_gbs / peak,
                          "traffic": traffic, "kernel": "cnsn_selfnorm_bwd (3*S algorithmic bytes per call)",
                          "peak_source": peak_src,
@@ -483,6 +554,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches,
             "cpu_baseline": cpu,
+            "sustained": sustained,
             "crossnorm": crossnorm,
             "site": site,
             "train": train,

@@ -31,7 +31,7 @@ struct Knobs {
     int pf = -1;                // resident items: L2 prefetch distance in tickets (-1 = half the resident CTAs)
     int rpf = 0;                // L2 items: prefetch distance in channels
     int poll_ns = 100;          // sleep between polls of a published word
-    int i3 = 0;                 // forward: three planes per resident item where two is the default
+    int i3 = 1;                 // forward: three planes per resident item (192 threads) where two would be the geometry
     int cooperative = 1;        // resident items: cooperative launch (co-residency guaranteed by the driver)
     int grid_cap = 0;           // resident items: cap the persistent grid (0 = every CTA the GPU holds)
     int debug = 0;              // print the chosen geometry to stderr
@@ -336,7 +336,11 @@ static inline cudaError_t prepare_kernel(K fn, int threads, size_t dsmem, int* c
     cudaError_t e = cudaSuccess;
     if (!ready.count(fkey)) {
         const DeviceShape d = device_shape();
-        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin);
+        cudaFuncAttributes fa{};
+        e = cudaFuncGetAttributes(&fa, fn);
+        if (e != cudaSuccess) return e;
+        // static + dynamic shared memory together are bounded by the opt-in limit
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, d.smem_optin - (int)fa.sharedSizeBytes);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) return e;
         ready[fkey] = true;

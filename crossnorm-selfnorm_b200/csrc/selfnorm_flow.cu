@@ -844,10 +844,11 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
 
 constexpr int kResT = 128;              // threads per CTA of the shared-memory-resident kernel
 
-// EXPERIMENT, opt-in (cnsn_tune("i3", 1)), forward only: items of THREE planes and
-// 192 threads (64 per plane).  At the north-star plane size (12.5 KB) an SM holds 8 items x 2 planes = 16 planes with
-// the default geometry and cannot take a ninth; 6 items x 3 planes = 18 planes fit the same 228 KB.  Same kernel
-// template (it is generic in TH and TPI); only taken when the default geometry would be two planes per item.
+// Forward items of THREE planes and 192 threads (64 per plane) where the generic geometry would be two planes per
+// 128-thread item: at the north-star plane size (12.5 KB) an SM holds 8 items x 2 planes = 16 planes and cannot take a
+// ninth item; 6 items x 3 planes = 18 planes fit the same 228 KB -- 12.5 % more bytes on chip per SM, measured 0.322 ->
+// 0.312 ms at (256,256,56,56) fp32 (gpurun_out/r2a_sweep.log).  Same kernel template (it is generic in TH and TPI).
+// cnsn_tune("i3", 0) selects the two-plane geometry (A/B, tests).
 static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     constexpr int kT3 = 192, kTpi3 = 64, kI3 = kT3 / kTpi3;
     const int N = a.N, C = a.C;

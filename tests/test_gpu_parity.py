@@ -306,7 +306,7 @@ def test_selfnorm_permutation_equivariance(mod):
     assert torch.allclose(m1(x)[p], m2(x[p]), atol=1e-6)
 
 
-@pytest.mark.parametrize("fwd_mode,bwd_mode", [("auto", "auto"), ("l2", "res")])
+@pytest.mark.parametrize("fwd_mode,bwd_mode", [("auto", "auto"), ("l2", "res"), ("res", "l2")])
 def test_selfnorm_north_star_shape_properties(mod, fwd_mode, bwd_mode):
     """Full-size (256,256,56,56) fp32 -- too big for the numpy oracle in seconds, so: the oracle restricted to a
     channel subset (the gate couples only instances of the SAME channel) for y, dx, dW, dgamma, dbeta AND the running
@@ -333,9 +333,12 @@ def test_selfnorm_north_star_shape_properties(mod, fwd_mode, bwd_mode):
         o = H.oracle_selfnorm(xs, dys, ps, bs, True)
         close32(y.detach()[:, c:c + 1].cpu().numpy(), o["y"], "y")
         close32(dx[:, c:c + 1].cpu().numpy(), o["dx"], "dx")
-        assert H.relmax(dw[c:c + 1].cpu().numpy(), o["dg_w"]) <= H.PARAM_RTOL, ("dW", c)
-        assert H.relmax(dgam[c:c + 1].cpu().numpy(), o["dg_gamma"]) <= H.PARAM_RTOL, ("dgamma", c)
-        assert H.relmax(dbet[c:c + 1].cpu().numpy(), o["dg_beta"]) <= H.PARAM_RTOL, ("dbeta", c)
+        # parameter gradients: 1e-5 relative to max |grad| of the WHOLE parameter tensor, as everywhere else (a single
+        # channel's dW is a sum of 256 terms of magnitude ~20 that cancels to ~1: judged against itself it would
+        # measure fp32 cancellation, which the reference's own fp32 autograd has as well)
+        for name, got, want in (("dW", dw, o["dg_w"]), ("dgamma", dgam, o["dg_gamma"]), ("dbeta", dbet, o["dg_beta"])):
+            err = np.abs(got[c:c + 1].double().cpu().numpy().reshape(-1) - np.asarray(want, np.float64).reshape(-1)).max()
+            assert err <= H.PARAM_RTOL * float(got.abs().max()), (name, c, err, float(got.abs().max()))
         close32(m.g_bn.running_mean[c:c + 1].cpu().numpy(), o["g_rm_after"], "running_mean")
         close32(m.g_bn.running_var[c:c + 1].cpu().numpy(), o["g_rv_after"], "running_var")
     # linearity of the backward map in dy
@@ -396,7 +399,7 @@ def test_selfnorm_fused_vs_oracle_and_v1(mod, shape, dtype, training):
     for knobs in ({}, {"selfnorm_impl": "v1"}, {"selfnorm_impl": "flow"}, {"selfnorm_impl": "flow", "flow_mode": "l2", "flow_bwd": "l2"},
                   {"selfnorm_impl": "flow", "flow_mode": "l2", "flow_bwd": "l2", "flow_d": 1},
                   {"selfnorm_impl": "flow", "flow_mode": "res", "flow_bwd": "res"}, {"selfnorm_impl": "flow", "flow_bwd": "dyg"},
-                  {"cooperative": 0}, {"grid_cap": 24}):
+                  {"cooperative": 0}, {"grid_cap": 24}, {"i3": 0}, {"i3": 0, "grid_cap": 16}):
         with L.tuned(**knobs):
             runs.append(H.run_selfnorm(mod, x, dy, params, bufs, DEV, False, training, dtype))
     o = H.oracle_selfnorm(x, dy, params, bufs, training)
