@@ -13,6 +13,7 @@ import torch
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libcnsn_b200.so")
+EXT_PATH = os.path.join(_PKG, "_cnsn_torch.so")
 
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
@@ -65,6 +66,7 @@ SIGNATURES = {
                                         c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
+    "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),
     "cnsn_ibn_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_float, c_float, c_float,
                              c_void_p, c_void_p]),
     "cnsn_ibn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_void_p,
@@ -390,6 +392,14 @@ class CudaBackend:
         vals.append(_p(p.get("nbt")).value)
         return IbnParams(*vals)
 
+    def ibn_resident(self, x, half, training):
+        """True when both directions of this shape run as the one-launch resident kernel (cached per shape)."""
+        if not x.is_cuda or x.data_ptr() % 16:
+            return False
+        N, C, H, W = x.shape
+        with _on(x.device):
+            return bool(_size("cnsn_ibn_resident", _dtype_code(x), N, C, H, W, int(half), int(training)))
+
     def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
         _require_cuda(x)
         N, C, H, W = x.shape
@@ -509,6 +519,46 @@ class CudaBackend:
 
 
 _backend = None
+_ext = None
+_ext_error = None
+_binding = "ext"          # "ext": C++ autograd nodes (_cnsn_torch.so) where they apply; "ctypes": always the ctypes binding
+
+
+def ext():
+    """The C++ host binding (_cnsn_torch.so: one autograd node per operator above the same C ABI), loaded once; None
+    when it has not been built or cannot be imported -- the ctypes binding then serves every call (same kernels)."""
+    global _ext, _ext_error
+    if _ext is None and _ext_error is None:
+        try:
+            lib()                                    # libcnsn_b200.so first (the binding links it)
+            import importlib.machinery
+            import importlib.util
+            loader = importlib.machinery.ExtensionFileLoader("_cnsn_torch", EXT_PATH)
+            spec = importlib.util.spec_from_file_location("_cnsn_torch", EXT_PATH, loader=loader)
+            mod = importlib.util.module_from_spec(spec)
+            loader.exec_module(mod)
+            if mod.abi_version() != ABI_VERSION:
+                raise RuntimeError("ABI mismatch (binding %d, library %d)" % (ABI_VERSION, mod.abi_version()))
+            _ext = mod
+        except Exception as e:      # noqa: BLE001
+            _ext_error = e
+    return _ext
+
+
+def set_binding(name):
+    """"ext" (default) or "ctypes" -- tests and A/B measurements."""
+    global _binding
+    assert name in ("ext", "ctypes")
+    old, _binding = _binding, name
+    return old
+
+
+def fast_binding():
+    """The C++ binding when it is to be used: built, selected, and the tensor-level backend is the real one (the CPU
+    test-suite installs a stand-in backend behind the Python autograd functions)."""
+    if _binding != "ext" or (_backend is not None and not isinstance(_backend, CudaBackend)):
+        return None
+    return ext()
 
 
 def backend():

@@ -55,19 +55,35 @@ def instance_norm_mix(content_feat, style_feat):
 
 def cn_rand_bbox(size, beta, bbx_thres):
     """Sample a crop box; same draws, same order, same return convention as models/cnsn.py:32-55:
-    (bbx1, bby1, bbx2, bby2) with bbx* indexing dim 2 and bby* dim 3.  (The reference's ``np.int``
-    is spelled ``int`` here; NumPy >= 1.24 removed the alias.)"""
-    d2, d3 = size[2], size[3]
+    (bbx1, bby1, bbx2, bby2) with bbx* indexing dim 2 and bby* dim 3.  (The reference's ``np.int`` is spelled ``int``
+    here -- NumPy >= 1.24 removed the alias -- and its ``np.clip`` on scalars is plain min / max: same integers.)"""
+    d2, d3 = int(size[2]), int(size[3])
     while True:
         ratio = np.random.beta(beta, beta)
         side = np.sqrt(ratio)
         ext2, ext3 = int(d2 * side), int(d3 * side)
-        c2 = np.random.randint(d2)
-        c3 = np.random.randint(d3)
-        bbx1, bbx2 = np.clip(c2 - ext2 // 2, 0, d2), np.clip(c2 + ext2 // 2, 0, d2)
-        bby1, bby2 = np.clip(c3 - ext3 // 2, 0, d3), np.clip(c3 + ext3 // 2, 0, d3)
+        c2 = int(np.random.randint(d2))
+        c3 = int(np.random.randint(d3))
+        bbx1, bbx2 = min(max(c2 - ext2 // 2, 0), d2), min(max(c2 + ext2 // 2, 0), d2)
+        bby1, bby2 = min(max(c3 - ext3 // 2, 0), d3), min(max(c3 + ext3 // 2, 0), d3)
         if float(bbx2 - bbx1) * (bby2 - bby1) / (d2 * d3) > bbx_thres:
             return bbx1, bby1, bbx2, bby2
+
+
+def _draw_windows(x, crop, beta, bbx_thres):
+    """The numpy draws of one cn_op_2ins_space_chan call in the reference's order (style box :64-66, then content box
+    :74-77), as (content, style) windows (h0, h1, w0, w1)."""
+    assert crop in _CROPS                                   # :61
+    assert x.dim() == 4
+    H, W = x.size(2), x.size(3)
+    swin = cwin = (0, H, 0, W)
+    if crop in ('style', 'both'):
+        a1, b1, a2, b2 = cn_rand_bbox(x.size(), beta=beta, bbx_thres=bbx_thres)
+        swin = (a1, a2, b1, b2)
+    if crop in ('content', 'both'):
+        a1, b1, a2, b2 = cn_rand_bbox(x.size(), beta=beta, bbx_thres=bbx_thres)
+        cwin = (a1, a2, b1, b2)
+    return cwin, swin
 
 
 class _PinnedRing:
@@ -120,6 +136,12 @@ def cn_op_2ins_space_chan(x, crop='neither', beta=1, bbx_thres=0.1, lam=None, ch
     device work (two statistics sets, permuted restyle, copy-through outside the content box) is one
     fused CUDA forward and one fused backward.
     """
+    ext = _lib.fast_binding() if (x.is_cuda and not chan) else None
+    if ext is not None:
+        # C++ node: torch.randperm(N) (:62) is drawn inside it on the same CPU generator; torch and numpy streams are
+        # independent, so drawing the boxes first changes nothing
+        cwin, swin = _draw_windows(x, crop, beta, bbx_thres)
+        return ext.crossnorm(x, cwin, swin, 0.0 if lam is None else float(lam), 1e-5)
     perm_d, cperm_d, cwin, swin = _draw_plan(x, crop, beta, bbx_thres, chan)
     return CrossNormFn.apply(x, perm_d, cperm_d, cwin, swin, 0.0 if lam is None else float(lam), 1e-5)
 
@@ -189,6 +211,11 @@ class SelfNorm(nn.Module):
         relu?(SelfNorm(x + residual)) for pos='post' sites (one gate only)."""
         assert x.dim() == 4
         bn = self.g_bn
+        if self.f_fc is None and x.is_cuda and self.g_fc.weight.dtype is torch.float32 and bn.weight is not None:
+            ext = _lib.fast_binding()
+            if ext is not None:                       # C++ autograd node: one call per direction
+                return ext.selfnorm(x, residual, bool(relu), self.g_fc.weight, bn.weight, bn.bias, bn.running_mean,
+                                    bn.running_var, bn.num_batches_tracked, bn.training, _bn_momentum(bn), float(bn.eps), 1e-12)
         if residual is not None or relu:
             assert self.f_fc is None, "the fused block supports the single-gate SelfNorm"
             assert residual is None or residual.shape == x.shape
@@ -257,6 +284,14 @@ class CNSN(nn.Module):
         ``crossnorm(x)`` (same RNG consumption), and the one-shot ``active`` flag is consumed (models/cnsn.py:108)."""
         cn, sn = self.crossnorm, self.selfnorm
         kw = cn.cn_op.keywords
+        bn = sn.g_bn
+        ext = _lib.fast_binding() if sn.g_fc.weight.dtype is torch.float32 else None
+        if ext is not None:
+            cwin, swin = _draw_windows(x, kw.get("crop", "neither"), kw.get("beta", 1), kw.get("bbx_thres", 0.1))
+            lam = kw.get("lam")
+            cn.active = False
+            return ext.site(x, cwin, swin, 0.0 if lam is None else float(lam), 1e-5, bool(relu), sn.g_fc.weight, bn.weight,
+                            bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked, _bn_momentum(bn), float(bn.eps), 1e-12)
         perm_d, _, cwin, swin = _draw_plan(x, kw.get("crop", "neither"), kw.get("beta", 1), kw.get("bbx_thres", 0.1), False)
         lam = kw.get("lam")
         cn.active = False

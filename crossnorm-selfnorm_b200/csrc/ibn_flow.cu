@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kIbnT) k_ibn_res(const IArgs a) {
 }
 
 template <bool BWD>
-static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) {
+static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream, bool dry_run = false) {
     const int N = a.N, C = a.C;
     const int esz = (int)esize(dtype);
     if (((size_t)a.M * esz) % 16) return CNSN_E_UNSUPPORTED;      // no general path for this operator (documented)
@@ -260,9 +260,11 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_UNSUPPORTED;
     a.nI = (N + inst - 1) / inst;
     const Knobs& kn = knobs();
-    if (async_error_peek()) return CNSN_E_TIMEOUT;
+    if (!dry_run) {
+        if (async_error_peek()) return CNSN_E_TIMEOUT;
+        a.err = async_error_word();
+    }
     a.poll_ns = kn.poll_ns;
-    a.err = async_error_word();
     const unsigned long long items = (unsigned long long)C * a.nI;
     if (items > 0x7fffffffull) return CNSN_E_UNSUPPORTED;
     a.items = (unsigned)items;
@@ -280,6 +282,7 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         /* a channel must be co-resident when its items wait for each other (training-mode batch-norm channels); */ \
         /* instance-norm channels never wait (their folder only collects words of earlier tickets) */          \
         if (a.half < C && a.training && (long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;    \
+        if (dry_run) return 0;                                                                           \
         a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;                                            \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
@@ -315,13 +318,22 @@ static size_t ibn_stats_floats(int N, int C, int half) { return (2 * (size_t)N *
 extern "C" size_t cnsn_ibn_save_floats(int N, int C, int half) { return ibn_stats_floats(N, C, half) + 2 * (size_t)N * C + 8 * (size_t)C + 8; }
 extern "C" size_t cnsn_ibn_workspace_floats(int N, int C) { return 2 * (size_t)N * C + 8 * (size_t)C + 8; }
 
+extern "C" int cnsn_ibn_resident(int dtype, int N, int C, int H, int W, int half, int training) {
+    if (check_dims(N, C, H, W) || half < 0 || half > C || dtype < CNSN_F32 || dtype > CNSN_F16) return 0;
+    flow::IArgs a{};
+    a.N = N; a.C = C; a.M = H * W; a.half = half; a.training = training;
+    if (flow::launch_ibn<false>(a, dtype, nullptr, nullptr, true) != 0) return 0;
+    return flow::launch_ibn<true>(a, dtype, nullptr, nullptr, true) == 0 ? 1 : 0;
+}
+
 extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, int half,
                             const cnsn_ibn_params* p, int training, float momentum, float eps_in, float eps_bn,
                             float* save, void* stream) {
     if (!x || !y || !p || !save || check_dims(N, C, H, W) || half < 0 || half > C) return CNSN_E_BADARG;
     if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
     if ((half > 0 && (!p->in_w || !p->in_b)) || (half < C && (!p->bn_w || !p->bn_b || !p->run_mean || !p->run_var))) return CNSN_E_BADARG;
-    if (!aligned16(x) || !aligned16(y)) return CNSN_E_ALIGN;
+    if (reinterpret_cast<uintptr_t>(x) % esize(dtype) || reinterpret_cast<uintptr_t>(y) % esize(dtype)) return CNSN_E_ALIGN;
+    const bool vec = aligned16(x) && aligned16(y);   // 16-byte base pointers: resident kernel; else the element-wise general path
     if (training && half < C && (long long)N * H * W < 2) return CNSN_E_BATCH1;
     flow::IArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W; a.half = half;
@@ -331,9 +343,9 @@ extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int
     a.in_mean = save; a.in_rstd = save + (size_t)N * half;
     a.bn_mean = save + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     float* scratch = save + ibn_stats_floats(N, C, half);
-    const int rc = flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream);
+    const int rc = vec ? flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
     if (rc != CNSN_E_UNSUPPORTED) return rc;
-    ibn_general::GArgs g = general_args(a);          // odd / oversized planes: the three-kernel path
+    ibn_general::GArgs g = general_args(a);          // odd / oversized planes, misaligned slices: the three-kernel path
     return ibn_general::ibn_general_fwd(g, dtype, scratch, (cudaStream_t)stream);
 }
 
@@ -344,7 +356,9 @@ extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, 
     if (!x || !dy || !dx || !p || !save || !workspace || check_dims(N, C, H, W) || half < 0 || half > C) return CNSN_E_BADARG;
     if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
     if ((half > 0 && (!p->in_w || !d_in_w || !d_in_b)) || (half < C && (!p->bn_w || !d_bn_w || !d_bn_b))) return CNSN_E_BADARG;
-    if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) return CNSN_E_ALIGN;
+    if (reinterpret_cast<uintptr_t>(x) % esize(dtype) || reinterpret_cast<uintptr_t>(dy) % esize(dtype) ||
+        reinterpret_cast<uintptr_t>(dx) % esize(dtype)) return CNSN_E_ALIGN;
+    const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx);
     flow::IArgs a{};
     a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.M = H * W; a.half = half;
     a.training = training;
@@ -353,7 +367,7 @@ extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, 
     a.in_mean = sv; a.in_rstd = sv + (size_t)N * half;
     a.bn_mean = sv + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     a.d_in_w = d_in_w; a.d_in_b = d_in_b; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b;
-    const int rc = flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream);
+    const int rc = vec ? flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
     if (rc != CNSN_E_UNSUPPORTED) return rc;
     ibn_general::GArgs g = general_args(a);
     return ibn_general::ibn_general_bwd(g, dtype, workspace, (cudaStream_t)stream);

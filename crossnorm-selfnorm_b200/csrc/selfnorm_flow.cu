@@ -876,6 +876,12 @@ static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t strea
         e = prepare_kernel(fn, kT3, dsmem, &per_sm);
         if (e != cudaSuccess) return (int)e;
         if ((long long)per_sm * ds.sms < 2ll * a.nI) return -100;
+        // only where it really puts more planes on an SM than the two-plane geometry does (12.5 KB planes: 6 x 3 = 18
+        // against 8 x 2 = 16; 12.8 KB bf16 80x80 planes: 5 x 3 = 15 against 8 x 2 = 16 -- measured slower, r2b_sweep.log)
+        int per_sm2 = 0;
+        e = prepare_kernel(k_sn_res<T, false, false, false, 64, 128>, 128, 128 + 2 * pbytes, &per_sm2);
+        if (e != cudaSuccess) return (int)e;
+        if (3 * per_sm <= 2 * per_sm2) return -100;
         a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
         if (e != cudaSuccess) return (int)e;

@@ -15,6 +15,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from ._norm import batchnorm2d_for
+
 _POSITIONS = ("residual", "pre", "post", "identity")
 _EXPANSION = 4
 
@@ -27,8 +29,10 @@ def _default_ops():
 class Bottleneck(nn.Module):
     """1x1 reduce, 3x3 (carries the stride), 1x1 expand, additive shortcut, ReLU; one optional CNSN site."""
 
-    def __init__(self, cin, planes, stride, shortcut, pos, beta, crop, cnsn_type, ops, fuse_post, ibn=None, ibn_host=False):
+    def __init__(self, cin, planes, stride, shortcut, pos, beta, crop, cnsn_type, ops, fuse_post, ibn=None, ibn_host=False,
+                 fast_bn=True):
         super().__init__()
+        BN = batchnorm2d_for(ops, fast_bn)
         assert ibn in (None, "a", "b")
         cout = planes * _EXPANSION
         self.ibn_variant = bool(ibn_host)                # wiring of resnet_ibn_cnsn.py (every block of that host)
@@ -37,11 +41,11 @@ class Bottleneck(nn.Module):
             from ..ibn import IBN
             self.bn1 = IBN(planes)
         else:
-            self.bn1 = nn.BatchNorm2d(planes)
+            self.bn1 = BN(planes)
         self.conv2 = nn.Conv2d(planes, planes, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(planes)
+        self.bn2 = BN(planes)
         self.conv3 = nn.Conv2d(planes, cout, 1, bias=False)
-        self.bn3 = nn.BatchNorm2d(cout)
+        self.bn3 = BN(cout)
         if ibn == "b":                                   # IBN-b: instance norm after the residual add (:62, :122-123)
             from ..ibn import InstanceNorm2d
             self.IN = InstanceNorm2d(cout, affine=True)
@@ -86,19 +90,20 @@ class Bottleneck(nn.Module):
 
 class ResNet(nn.Module):
     def __init__(self, layers, num_classes=1000, active_num=1, pos=None, beta=None, crop=None, cnsn_type=None,
-                 ops=None, fuse_post=False, zero_init_residual=False, ibn_cfg=(None, None, None, None)):
+                 ops=None, fuse_post=False, zero_init_residual=False, ibn_cfg=(None, None, None, None), fast_bn=True):
         super().__init__()
         ops = ops or _default_ops()
+        BN = batchnorm2d_for(ops, fast_bn)
         self.conv1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False)
         if ibn_cfg[0] == "b":                             # IBN-b stem (resnet_ibn_cnsn.py:143-144)
             from ..ibn import InstanceNorm2d
             self.bn1 = InstanceNorm2d(64, affine=True)
         else:
-            self.bn1 = nn.BatchNorm2d(64)
+            self.bn1 = BN(64)
         self.relu = nn.ReLU(inplace=True)
         self.maxpool = nn.MaxPool2d(3, 2, 1)
         kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post,
-                  ibn_host=any(v is not None for v in ibn_cfg))
+                  ibn_host=any(v is not None for v in ibn_cfg), fast_bn=fast_bn)
         width = 64
         stages = []
         for i, (planes, count) in enumerate(zip((64, 128, 256, 512), layers)):
@@ -109,7 +114,7 @@ class ResNet(nn.Module):
                 shortcut = None
                 if b == 0 and (s != 1 or width != planes * _EXPANSION):
                     shortcut = nn.Sequential(nn.Conv2d(width, planes * _EXPANSION, 1, s, bias=False),
-                                             nn.BatchNorm2d(planes * _EXPANSION))
+                                             BN(planes * _EXPANSION))
                 ibn = ibn_cfg[i]
                 if ibn == "b" and (b == 0 or b < count - 1):   # IBN-b: the last block of a stage, never its first (:204-214)
                     ibn = None

@@ -13,6 +13,8 @@ import numpy as np
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ._norm import batchnorm2d_for
+
 _POSITIONS = ("residual", "identity", "pre", "post")
 _EXPANSION = 4
 
@@ -25,14 +27,15 @@ def _default_ops():
 class _Bottleneck(nn.Module):
     def __init__(self, cin, planes, cardinality, base_width, pos, beta, crop, cnsn_type, ops, stride=1, downsample=None):
         super().__init__()
+        BN = batchnorm2d_for(ops)
         width = int(math.floor(planes * (base_width / 64.0))) * cardinality
         cout = planes * _EXPANSION
         self.conv_reduce = nn.Conv2d(cin, width, 1, 1, 0, bias=False)
-        self.bn_reduce = nn.BatchNorm2d(width)
+        self.bn_reduce = BN(width)
         self.conv_conv = nn.Conv2d(width, width, 3, stride, 1, groups=cardinality, bias=False)
-        self.bn = nn.BatchNorm2d(width)
+        self.bn = BN(width)
         self.conv_expand = nn.Conv2d(width, cout, 1, 1, 0, bias=False)
-        self.bn_expand = nn.BatchNorm2d(cout)
+        self.bn_expand = BN(cout)
         self.downsample = downsample
         assert cnsn_type in ("sn", "cn", "cnsn") and pos in _POSITIONS
         cross = ops.CrossNorm(crop=crop, beta=beta) if "cn" in cnsn_type else None
@@ -66,7 +69,7 @@ class CifarResNeXt(nn.Module):
         per_stage = (depth - 2) // 9
         self.cardinality, self.base_width, self.num_classes = cardinality, base_width, num_classes
         self.conv_1_3x3 = nn.Conv2d(3, 64, 3, 1, 1, bias=False)
-        self.bn_1 = nn.BatchNorm2d(64)
+        self.bn_1 = batchnorm2d_for(ops)(64)
         kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops)
         width = 64
         stages = []
@@ -74,7 +77,7 @@ class CifarResNeXt(nn.Module):
             shortcut = None
             if stride != 1 or width != planes * _EXPANSION:
                 shortcut = nn.Sequential(nn.Conv2d(width, planes * _EXPANSION, 1, stride, bias=False),
-                                         nn.BatchNorm2d(planes * _EXPANSION))
+                                         batchnorm2d_for(ops)(planes * _EXPANSION))
             blocks = [_Bottleneck(width, planes, cardinality, base_width, stride=stride, downsample=shortcut, **kw)]
             width = planes * _EXPANSION
             blocks += [_Bottleneck(width, planes, cardinality, base_width, **kw) for _ in range(1, per_stage)]

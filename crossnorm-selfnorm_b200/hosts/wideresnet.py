@@ -17,6 +17,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from ._norm import batchnorm2d_for
+
 _POSITIONS = ("residual", "identity", "pre", "post")
 
 
@@ -28,18 +30,19 @@ def _default_ops():
 class _PreActBlock(nn.Module):
     """BN-ReLU-conv3x3-BN-ReLU-conv3x3 with an additive shortcut and one CNSN site."""
 
-    def __init__(self, cin, cout, stride, pos, beta, crop, cnsn_type, drop_rate, ops, fuse_post=False):
+    def __init__(self, cin, cout, stride, pos, beta, crop, cnsn_type, drop_rate, ops, fuse_post=False, fast_bn=True):
         super().__init__()
+        BN = batchnorm2d_for(ops, fast_bn)
         self.fuse_post = bool(fuse_post) and pos == "post"
         assert cnsn_type in ("sn", "cn", "cnsn")
         assert pos in _POSITIONS
         self.pos, self.drop_rate, self.same = pos, drop_rate, cin == cout
         # attribute names and creation order follow the reference block so that parameter names and
         # the RNG draws of default initialisers line up
-        self.bn1 = nn.BatchNorm2d(cin)
+        self.bn1 = BN(cin)
         self.relu1 = nn.ReLU(inplace=True)
         self.conv1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
-        self.bn2 = nn.BatchNorm2d(cout)
+        self.bn2 = BN(cout)
         self.relu2 = nn.ReLU(inplace=True)
         self.conv2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False)
         self.conv_shortcut = None if self.same else nn.Conv2d(cin, cout, 1, stride, 0, bias=False)
@@ -85,18 +88,19 @@ class _Stage(nn.Module):
 
 class WideResNet(nn.Module):
     def __init__(self, depth, num_classes, widen_factor=1, drop_rate=0.0, active_num=None, pos=None, beta=None,
-                 crop=None, cnsn_type=None, ops=None, verbose=False, fuse_post=False):
+                 crop=None, cnsn_type=None, ops=None, verbose=False, fuse_post=False, fast_bn=True):
         super().__init__()
         ops = ops or _default_ops()
         assert (depth - 4) % 6 == 0
         per_stage = (depth - 4) // 6
         widths = [16, 16 * widen_factor, 32 * widen_factor, 64 * widen_factor]
-        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, drop_rate=drop_rate, ops=ops, fuse_post=fuse_post)
+        kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, drop_rate=drop_rate, ops=ops, fuse_post=fuse_post,
+                  fast_bn=fast_bn)
         self.conv1 = nn.Conv2d(3, widths[0], 3, 1, 1, bias=False)
         self.block1 = _Stage(per_stage, widths[0], widths[1], 1, **kw)
         self.block2 = _Stage(per_stage, widths[1], widths[2], 2, **kw)
         self.block3 = _Stage(per_stage, widths[2], widths[3], 2, **kw)
-        self.bn1 = nn.BatchNorm2d(widths[3])
+        self.bn1 = batchnorm2d_for(ops, fast_bn)(widths[3])
         self.relu = nn.ReLU(inplace=True)
         self.fc = nn.Linear(widths[3], num_classes)
         self.n_channels = widths[3]

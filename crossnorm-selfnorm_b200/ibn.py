@@ -6,8 +6,10 @@ buffers, so ``state_dict()`` keys match (``...bn1.IN.weight``, ``...bn1.BN.runni
 reference checkpoints load; the sub-modules are never called -- one CUDA kernel per direction handles both halves in
 place, without the reference's split / contiguous / cat copies.
 """
+import torch
 import torch.nn as nn
 
+from . import _lib
 from .functional import IbnFn
 
 
@@ -20,7 +22,7 @@ def bn_momentum(bn):
         return 0.0
     return 1.0 / (int(bn.num_batches_tracked) + 1)
 
-__all__ = ["IBN", "InstanceNorm2d"]
+__all__ = ["IBN", "InstanceNorm2d", "BatchNorm2d"]
 
 
 class IBN(nn.Module):
@@ -34,6 +36,10 @@ class IBN(nn.Module):
         assert x.dim() == 4
         bn = self.BN
         momentum = bn_momentum(bn)
+        ext = _lib.fast_binding() if (x.is_cuda and bn.weight.dtype is torch.float32) else None
+        if ext is not None:                           # C++ autograd node
+            return ext.ibn(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps), bn.running_mean,
+                           bn.running_var, bn.num_batches_tracked, self.IN.weight, self.IN.bias, bn.weight, bn.bias)
         return IbnFn.apply(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps),
                            (bn.running_mean, bn.running_var, bn.num_batches_tracked),
                            self.IN.weight, self.IN.bias, bn.weight, bn.bias)
@@ -51,5 +57,36 @@ class InstanceNorm2d(nn.InstanceNorm2d):
 
     def forward(self, x):
         assert x.dim() == 4 and x.size(1) == self.num_features
+        ext = _lib.fast_binding() if (x.is_cuda and self.weight.dtype is torch.float32) else None
+        if ext is not None:
+            return ext.ibn(x, self.num_features, False, 0.1, float(self.eps), 1e-5, None, None, None, self.weight, self.bias,
+                           None, None)
         return IbnFn.apply(x, self.num_features, False, 0.1, float(self.eps), 1e-5, (None, None, None),
                            self.weight, self.bias, None, None)
+
+
+class BatchNorm2d(nn.BatchNorm2d):
+    """``nn.BatchNorm2d`` of the host blocks (models/cifar/wideresnet_cnsn.py:51-57, models/imagenet/resnet_cnsn.py:60-75)
+    through the IBN kernels with every channel on the batch-norm side (``half = 0``): one shared-memory-resident launch
+    per direction -- x crosses HBM once forward, x and dy once backward -- instead of cuDNN's one-CTA-per-channel kernels,
+    which take 55 % of a WideResNet-40-2 step on B200 (32-128 channels on 148 SMs; profiles/README.md).  Same class
+    hierarchy, parameters, buffers and ``state_dict`` keys as the torch module; same arithmetic (batch statistics when
+    training, biased variance to normalise, unbiased into ``running_var``, ``momentum=None`` = cumulative average).
+    Anything the resident kernels do not take (CPU tensors, planes that are not 16-byte multiples or do not fit shared
+    memory, ``affine=False`` / no running statistics) goes to the torch implementation."""
+
+    def forward(self, x):
+        if (x.is_cuda and x.dim() == 4 and self.affine and self.track_running_stats and self.weight.dtype is torch.float32
+                and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+            training = self.training
+            be = _lib.backend()
+            if getattr(be, "name", "") == "cuda" and be.ibn_resident(x, 0, training):
+                momentum = bn_momentum(self)
+                ext = _lib.fast_binding()
+                if ext is not None:
+                    return ext.ibn(x, 0, training, momentum, 1e-5, float(self.eps), self.running_mean, self.running_var,
+                                   self.num_batches_tracked, None, None, self.weight, self.bias)
+                return IbnFn.apply(x, 0, training, momentum, 1e-5, float(self.eps),
+                                   (self.running_mean, self.running_var, self.num_batches_tracked),
+                                   None, None, self.weight, self.bias)
+        return super().forward(x)

@@ -46,18 +46,102 @@ def train_step(net, images, targets, opt, sched, cn_prob):
     return float(loss.detach())
 
 
-def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False):
-    """images/s of WideResNet-40-2 + CNSN training on synthetic CIFAR-shaped data (fp32, batch per GPU)."""
+class GraphedStep:
+    """The ``train_cn`` step (cifar.py:117-145) with the launch-bound part taken off the host: forward, loss and
+    backward of the step WITHOUT CrossNorm -- 1 - cn_prob = 75 % of the steps of BASELINE config 3 -- are captured once
+    into a CUDA graph and replayed; steps whose coin activates CrossNorm sites run eagerly (CrossNorm draws a fresh
+    permutation and crop boxes on the host every call, models/cnsn.py:62-77, and which sites fire changes per step,
+    wideresnet_cnsn.py:199-203).  Same arithmetic either way: the graph replays the very kernels the eager step
+    launches.  Gradients live in ONE flat buffer (every ``p.grad`` is a view of it), so the data-parallel exchange is
+    a single NCCL all-reduce (sum, then / world) of that buffer after backward -- what DistributedDataParallel's bucket does,
+    without its per-step host work; running statistics stay per replica (the reference's DataParallel behaviour).
+    The per-step ``float(loss)`` host read of the reference stays."""
+
+    def __init__(self, net, images, targets, world=1, capture=True):
+        self.net, self.world = net, world
+        self.params = [p for p in net.parameters() if p.requires_grad]
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=self.params[0].dtype, device=images.device)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.x, self.y = images.clone(), targets.clone()
+        self.graph = None
+        if capture and images.is_cuda:
+            self._capture()
+
+    def _forward_backward(self, aug):
+        self.flat.zero_()
+        logits = self.net(self.x, aug=aug)
+        loss = F.cross_entropy(logits, self.y)
+        loss.backward()                                   # accumulates into the views of the (zeroed) flat buffer
+        return loss
+
+    def _capture(self):
+        # warm-up on a side stream (cuDNN plans, caching-allocator blocks, the library's per-kernel preparation), with
+        # the buffers the forward updates put back afterwards: capture must not change the training state
+        bufs = [b for b in self.net.buffers()]
+        saved = [b.clone() for b in bufs]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._forward_backward(False)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._forward_backward(False)
+        with torch.no_grad():
+            for b, v in zip(bufs, saved):
+                b.copy_(v)
+        torch.cuda.synchronize()
+
+    def step(self, images, targets, opt, sched, cn_prob):
+        aug = bool(np.random.rand(1) < cn_prob)           # cifar.py:127
+        if images is not self.x:
+            self.x.copy_(images, non_blocking=True)
+            self.y.copy_(targets, non_blocking=True)
+        if aug or self.graph is None:
+            loss = self._forward_backward(aug)
+        else:
+            self.graph.replay()
+            loss = self.loss
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.flat)                    # sum, then the mean DistributedDataParallel would deliver
+            self.flat.div_(self.world)
+        opt.step()
+        if sched is not None:
+            sched.step()
+        return float(loss.detach())
+
+
+def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False, graph=None):
+    """images/s of WideResNet-40-2 + CNSN training on synthetic CIFAR-shaped data (fp32, batch per GPU).
+    graph (default: on CUDA with this package's operators): GraphedStep -- CUDA graph for the steps without CrossNorm,
+    one flat-buffer gradient all-reduce; otherwise the plain eager step (DistributedDataParallel when world > 1)."""
     import torch.distributed as dist
-    torch.manual_seed(1 + rank)
-    np.random.seed(1 + rank)                  # each rank draws its own perms / boxes / coins
+    if dev.type == "cuda":
+        torch.backends.cudnn.benchmark = True  # cifar.py:396
+    torch.manual_seed(1 + rank)               # parameters are broadcast below; permutations differ per rank
+    # ONE numpy stream for all ranks: the per-step coin (cifar.py:127) is drawn once per step for the whole batch in
+    # the reference (a single process drives every replica), so every rank takes the same aug / no-aug decision --
+    # and no rank waits in the gradient exchange for another rank's slower CrossNorm step
+    np.random.seed(1)
     net = wrn40_2(ops=ops, fuse_post=fuse_post).to(dev).train()
+    if graph is None:
+        graph = dev.type == "cuda" and ops is None
     model = net
     if world > 1:
+        with torch.no_grad():
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t, 0)
+    if world > 1 and not graph:
         # broadcast_buffers=False: SelfNorm / BatchNorm running statistics stay per replica, as under the
         # reference's DataParallel; only gradients are exchanged
         model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index] if dev.type == "cuda" else None,
-                                                    broadcast_buffers=False)
+                                                    broadcast_buffers=False, gradient_as_bucket_view=True)
     opt, sched = make_optimizer(model, total_steps=steps + warmup)
     x = torch.randn(batch, 3, 32, 32, device=dev)
     y = torch.randint(0, 10, (batch,), device=dev)
@@ -66,8 +150,15 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
     if is_cuda:
         from . import _lib
         launches0 = _lib.launch_count()
+    gs = GraphedStep(net, x, y, world) if graph else None
+
+    def one_step():
+        if gs is not None:
+            return gs.step(gs.x, gs.y, opt, sched, cn_prob)
+        return train_step(model, x, y, opt, sched, cn_prob)
+
     for _ in range(warmup):
-        train_step(model, x, y, opt, sched, cn_prob)
+        one_step()
     if is_cuda:
         if world > 1:
             dist.barrier()
@@ -81,7 +172,7 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
         w0 = time.perf_counter()
     loss = 0.0
     for _ in range(steps):
-        loss = train_step(model, x, y, opt, sched, cn_prob)
+        loss = one_step()
     if is_cuda:
         t1.record()
         if world > 1:
@@ -103,7 +194,9 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
            "batch_per_gpu": batch, "n_gpus": world, "dtype": "f32 (TF32 convolutions: %s)" % torch.backends.cudnn.allow_tf32,
            "config": "depth 40, widen 2, cnsn_type=cnsn, pos=post, crop=both, beta=1, active_num=2, cn_prob=%g, "
                      "SGD nesterov lr 0.1 wd 5e-4, cosine LR, synthetic 32x32, fuse_post=%s" % (cn_prob, bool(fuse_post)),
-           "final_loss": loss, "params": sum(p.numel() for p in net.parameters())}
+           "final_loss": loss, "params": sum(p.numel() for p in net.parameters()),
+           "graph": ("CUDA graph for the steps without CrossNorm (%d %% of them), eager otherwise; one flat-buffer gradient "
+                     "all-reduce" % round(100 * (1 - cn_prob))) if gs is not None and gs.graph is not None else "eager"}
     if launches0 is not None:
         from . import _lib
         out["cnsn_kernel_launches"] = _lib.launch_count() - launches0
@@ -132,8 +225,9 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
     from .hosts.resnet import resnet50
     if ops is None:
         from . import cnsn as ops
+    torch.backends.cudnn.benchmark = True      # imagenet.py:534
     torch.manual_seed(1 + rank)
-    np.random.seed(1 + rank)
+    np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
     net = resnet50(fuse_post=fuse_post, ops=ops).to(dev).train()
     model = net
     if world > 1:
@@ -193,8 +287,9 @@ def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0
     from . import _lib, cnsn as ops
     from .hosts.resnet import resnet50
     from .losses import jsd_consistency
+    torch.backends.cudnn.benchmark = True      # imagenet.py:534
     torch.manual_seed(1 + rank)
-    np.random.seed(1 + rank)
+    np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
     net = resnet50(fuse_post=fuse_post).to(dev).train()
     model = net
     if world > 1:

@@ -248,8 +248,8 @@ int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int
  *               (N,H,W), running_mean / running_var (unbiased) updated with `momentum`, nbt incremented; eval: running.
  * half == C is a plain nn.InstanceNorm2d(C, affine=True) (the IBN-b blocks and stem, resnet_ibn_cnsn.py:62,122-123,
  * 143-144; bn_* / run_* may be NULL), half == 0 a plain BatchNorm2d.  One resident kernel per direction when planes are
- * multiples of 16 bytes and fit shared memory; every other shape takes three stream-ordered kernels per direction
- * (same results).  save: cnsn_ibn_save_floats() floats, written by forward, read by backward; workspace:
+ * multiples of 16 bytes and fit shared memory; every other shape -- and base pointers that are not 16-byte aligned --
+ * takes three stream-ordered kernels per direction (same results).  save: cnsn_ibn_save_floats() floats, written by forward, read by backward; workspace:
  * cnsn_ibn_workspace_floats().  Parameter gradients are WRITTEN.
  */
 typedef struct cnsn_ibn_params {
@@ -264,6 +264,10 @@ typedef struct cnsn_ibn_params {
 
 size_t cnsn_ibn_save_floats(int N, int C, int half);
 size_t cnsn_ibn_workspace_floats(int N, int C);
+/* 1 when BOTH directions of this shape run as the one-launch shared-memory-resident kernel on the current device (what
+ * a host model asks before it routes an nn.BatchNorm2d -- half == 0 -- through these entry points instead of cuDNN), else 0
+ * (the entry points then take the three-kernel general path: correct, not tuned). */
+int cnsn_ibn_resident(int dtype, int N, int C, int H, int W, int half, int training);
 int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, int half,
                  const cnsn_ibn_params* p, int training, float momentum, float eps_in, float eps_bn,
                  float* save, void* stream);

@@ -1,0 +1,53 @@
+"""train.GraphedStep on a GPU: the CUDA-graph replay of the WideResNet-40-2 step without CrossNorm must be the same
+training step as the eager one -- same loss, same parameters and buffers after several optimizer steps in which graph
+replays and eager CrossNorm steps alternate -- and capturing must not disturb the training state."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+def _run(capture, steps=8, cn_prob=0.4):
+    from cnsn_b200.train import GraphedStep, make_optimizer, wrn40_2
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = wrn40_2(fuse_post=True).to(DEV).train()
+    opt, sched = make_optimizer(net, total_steps=steps)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 3, 32, 32, generator=g).to(DEV)
+    y = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    before = {k: v.clone() for k, v in net.state_dict().items()}
+    gs = GraphedStep(net, x, y, 1, capture=capture)
+    assert (gs.graph is not None) == capture
+    for k, v in net.state_dict().items():                 # capture (and its warm-up passes) left the state alone
+        assert torch.equal(v, before[k]), k
+    torch.manual_seed(2)
+    np.random.seed(3)                                     # the coins: a mix of CrossNorm (eager) and plain (graph) steps
+    losses = [gs.step(gs.x, gs.y, opt, sched, cn_prob) for _ in range(steps)]
+    return losses, {k: v.clone() for k, v in net.state_dict().items()}
+
+
+def test_graph_replay_is_the_eager_step():
+    saved = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    try:
+        le, se = _run(False)
+        lg, sg = _run(True)
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = saved
+    np.random.seed(3)
+    coins = [bool(np.random.rand(1) < 0.4) for _ in range(8)]
+    assert any(coins) and not all(coins)                  # both kinds of step occurred (the draws above consume more
+    assert le[0] == lg[0]                                 # numbers in CrossNorm steps; the first coin is the same)
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (le, lg)
+    worst = 0.0
+    for k in se:
+        if se[k].dtype.is_floating_point:
+            d = float((se[k] - sg[k]).abs().max() / se[k].abs().max().clamp_min(1e-12))
+            worst = max(worst, d)
+        else:
+            assert torch.equal(se[k], sg[k]), k
+    assert worst <= 2e-3, worst

@@ -224,3 +224,62 @@ def test_ibn_general_path_vs_oracle(shape, dtype, half, training):
         assert np.allclose(pt["run_mean"].double().cpu().numpy(), rm, atol=1e-5)
         assert np.allclose(pt["run_var"].double().cpu().numpy(), rv, atol=1e-5, rtol=1e-5)
         assert int(pt["nbt"]) == (1 if training else 0)
+
+
+# ------------------------------------------------------------------ BatchNorm2d drop-in (half == 0)
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((64, 16, 32, 32), torch.float32), ((128, 32, 32, 32), torch.float32), ((96, 64, 16, 16), torch.float32),
+                                         ((64, 128, 8, 8), torch.float32), ((16, 64, 56, 56), torch.float32), ((32, 8, 32, 32), torch.bfloat16),
+                                         ((8, 16, 7, 7), torch.float32)])
+@pytest.mark.parametrize("training", [True, False])
+def test_batchnorm2d_dropin_matches_torch(shape, dtype, training):
+    """cnsn_b200.ibn.BatchNorm2d (the host blocks' nn.BatchNorm2d through cnsn_ibn_* with half = 0) against torch's own
+    nn.BatchNorm2d in fp64 on the same GPU: y, dx, dweight, dbias, running statistics, num_batches_tracked; identical
+    state dict.  (8,16,7,7): planes that are not 16-byte multiples -- the drop-in hands those to torch.)"""
+    import torch.nn as nn
+    from cnsn_b200.ibn import BatchNorm2d
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(0)
+    C = shape[1]
+    x0 = (torch.randn(shape, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g)) + torch.randn(1, C, 1, 1, generator=g)).to(dtype)
+    dy0 = torch.randn(shape, generator=g).to(dtype)
+    ref = nn.BatchNorm2d(C).to(dev).double().train(training)
+    ours = BatchNorm2d(C).to(dev).train(training)
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref.bias.copy_(torch.randn(C, generator=g))
+        ref.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ours.load_state_dict({k: (v.float() if v.dtype.is_floating_point else v) for k, v in ref.state_dict().items()})
+    assert list(ours.state_dict()) == list(ref.state_dict())
+    res = []
+    for m, dt in ((ref, torch.float64), (ours, dtype)):
+        x = x0.to(dev).to(dt).requires_grad_(True)
+        y = m(x)
+        y.backward(dy0.to(dev).to(dt))
+        res.append((y.detach().double(), x.grad.double(), m.weight.grad.double(), m.bias.grad.double(),
+                    m.running_mean.double(), m.running_var.double()))
+        assert int(m.num_batches_tracked) == (1 if training else 0)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for name, a, b in zip(("y", "dx", "dweight", "dbias", "running_mean", "running_var"), res[0], res[1]):
+        err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-12))
+        assert err <= tol, (name, err)
+
+
+@pytest.mark.gpu
+def test_batchnorm2d_dropin_momentum_none_and_fallbacks():
+    """momentum=None (cumulative average) follows torch; affine=False and CPU tensors take the torch implementation."""
+    import torch.nn as nn
+    from cnsn_b200.ibn import BatchNorm2d
+    dev = "cuda:0"
+    x = torch.randn(32, 8, 16, 16, device=dev)
+    a, b = nn.BatchNorm2d(8, momentum=None).to(dev).train(), BatchNorm2d(8, momentum=None).to(dev).train()
+    for _ in range(3):
+        ya, yb = a(x), b(x)
+        x = x * 1.1 + 0.05
+    assert torch.allclose(ya, yb, atol=1e-5) and torch.allclose(a.running_mean, b.running_mean, atol=1e-6)
+    assert torch.allclose(a.running_var, b.running_var, atol=1e-5) and int(b.num_batches_tracked) == 3
+    c = BatchNorm2d(8, affine=False).to(dev).train()
+    assert torch.allclose(c(x), nn.functional.batch_norm(x, None, None, training=True), atol=1e-5)
+    d = BatchNorm2d(8).train()
+    assert d(torch.randn(4, 8, 5, 5)).shape == (4, 8, 5, 5)
