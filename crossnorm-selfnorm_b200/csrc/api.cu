@@ -56,7 +56,7 @@ extern "C" int cnsn_tune(const char* name, int value) {
     CNSN_KNOB(selfnorm_impl) CNSN_KNOB(crossnorm_impl) CNSN_KNOB(flow_mode) CNSN_KNOB(flow_bwd) CNSN_KNOB(flow_d)
     CNSN_KNOB(flow_tpi) CNSN_KNOB(flow_batches) CNSN_KNOB(lookahead_mb) CNSN_KNOB(item_kb) CNSN_KNOB(grp_kb)
     CNSN_KNOB(keep) CNSN_KNOB(pf) CNSN_KNOB(rpf) CNSN_KNOB(poll_ns) CNSN_KNOB(i3) CNSN_KNOB(cooperative)
-    CNSN_KNOB(grid_cap) CNSN_KNOB(debug) CNSN_KNOB(trace)
+    CNSN_KNOB(grid_cap) CNSN_KNOB(debug) CNSN_KNOB(trace) CNSN_KNOB(tm) CNSN_KNOB(tm_items)
 #undef CNSN_KNOB
     return CNSN_E_BADARG;
 }

@@ -32,6 +32,8 @@ struct Knobs {
     int rpf = 0;                // L2 items: prefetch distance in channels
     int poll_ns = 100;          // sleep between polls of a published word
     int i3 = 1;                 // forward: three planes per resident item (192 threads) where two would be the geometry
+    int tm = 1;                 // SelfNorm: the shared-memory + tensor-memory pipeline (selfnorm_tmem.cu) where it applies
+    int tm_items = 16;          // ... which needs at least this many items per SM to fill its two stages (tests: 0)
     int cooperative = 1;        // resident items: cooperative launch (co-residency guaranteed by the driver)
     int grid_cap = 0;           // resident items: cap the persistent grid (0 = every CTA the GPU holds)
     int debug = 0;              // print the chosen geometry to stderr
@@ -169,18 +171,30 @@ __device__ __forceinline__ Moments team_merge(Moments a, Moments* sm) {
     for (int i = 1; i < WPT; ++i) r = merge(r, sm[w0 + i]);
     return r;
 }
-// Sums over the whole CTA of TH threads (channel fold by the last R item).
-template <int K, int TH>
+// Who synchronises with whom: the whole CTA (default), or one 128-thread group of a fat CTA (named barrier; the
+// tensor-memory kernel runs four independent groups per CTA, selfnorm_tmem.cu).
+struct CtaSync {
+    __device__ __forceinline__ static int tid() { return threadIdx.x; }
+    __device__ __forceinline__ static void sync() { __syncthreads(); }
+};
+struct Group128Sync {
+    __device__ __forceinline__ static int tid() { return threadIdx.x & 127; }
+    __device__ __forceinline__ static void sync() {
+        asm volatile("bar.sync %0, 128;" :: "r"((threadIdx.x >> 7) + 1) : "memory");     // barrier 0 stays the CTA's
+    }
+};
+// Sums over the TH threads that synchronise through S (channel fold by the last item of a channel).
+template <int K, int TH, typename S = CtaSync>
 __device__ __forceinline__ void cta_sums(float (&v)[K], float (*sm)[TH / 32]) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warp = S::tid() >> 5, lane = S::tid() & 31;
 #pragma unroll
     for (int k = 0; k < K; ++k) v[k] = warp_sum(v[k]);
-    __syncthreads();
+    S::sync();
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < K; ++k) sm[k][warp] = v[k];
     }
-    __syncthreads();
+    S::sync();
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         float s = 0.f;

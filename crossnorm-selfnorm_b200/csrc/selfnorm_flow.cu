@@ -1056,6 +1056,10 @@ int selfnorm_flow_fwd(const void* x, const void* res, void* z, void* y, int relu
     a.w = g->w; a.gamma = g->gamma; a.beta = g->beta; a.run_mean = g->run_mean; a.run_var = g->run_var; a.nbt = g->nbt;
     a.mu = mu; a.sd = sd; a.gate = gate; a.shat = shat; a.r = r;
     if (odd) return launch_grp<false>(a, dtype, scratch, stream);
+    if (knobs().flow_mode == 0) {                            // default dispatch: shared + tensor memory pipeline first
+        const int rc = selfnorm_tmem_fwd(a, dtype, scratch, stream);
+        if (rc != -100) return rc;
+    }
     if (use_resident((size_t)N * H * W * esize(dtype) * (res ? 2 : 1), false)) {
         const int rc = launch_res<false>(a, dtype, scratch, stream);
         if (rc != -100) return rc;
@@ -1082,6 +1086,10 @@ int selfnorm_flow_bwd(const void* x, const void* dy, void* dx, int relu, int dty
     // selectable.  cnsn_tune("flow_bwd", 1|2|3) forces one (A/B measurements).
     const size_t chan_x = (size_t)N * H * W * esize(dtype);
     if ((((size_t)H * W * esize(dtype)) % 16) != 0) return launch_grp<true>(a, dtype, scratch, stream);
+    if (knobs().flow_bwd == 0 && knobs().flow_mode == 0) {
+        const int rc = selfnorm_tmem_bwd(a, dtype, scratch, stream);
+        if (rc != -100) return rc;
+    }
     int mode = use_resident(2 * chan_x, true) ? 0 : 2;
     if (const int b = knobs().flow_bwd) mode = b - 1;          // 1 resident, 2 x resident + dy through L2, 3 L2 items
     if (mode < 2) {

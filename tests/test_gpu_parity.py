@@ -306,14 +306,18 @@ def test_selfnorm_permutation_equivariance(mod):
     assert torch.allclose(m1(x)[p], m2(x[p]), atol=1e-6)
 
 
-@pytest.mark.parametrize("fwd_mode,bwd_mode", [("auto", "auto"), ("l2", "res"), ("res", "l2")])
+@pytest.mark.parametrize("fwd_mode,bwd_mode", [("auto", "auto"), ("l2", "res"), ("res", "l2"), ("tm0", "tm0")])
 def test_selfnorm_north_star_shape_properties(mod, fwd_mode, bwd_mode):
     """Full-size (256,256,56,56) fp32 -- too big for the numpy oracle in seconds, so: the oracle restricted to a
     channel subset (the gate couples only instances of the SAME channel) for y, dx, dW, dgamma, dbeta AND the running
     buffers -- the channel fold with N = 256 and 64-128 items per channel is a geometry no small test reaches --
-    plus size-independent properties (linearity of backward in dy).  Default dispatch (resident forward, L2-item
-    backward) and the other pairing (L2-item forward, resident backward)."""
-    L.tune(flow_mode=fwd_mode, flow_bwd=bwd_mode)
+    plus size-independent properties (linearity of backward in dy).  Default dispatch (the shared + tensor memory
+    pipeline in both directions), and the other kernels forced: L2-item forward / resident backward, resident forward /
+    L2-item backward, and the default with the tensor-memory pipeline off."""
+    if fwd_mode == "tm0":                                  # the pre-tensor-memory default: resident forward, L2-item backward
+        L.tune(tm=0)
+    else:
+        L.tune(flow_mode=fwd_mode, flow_bwd=bwd_mode)
     N, C, Hh, Ww = 256, 256, 56, 56
     g = torch.Generator(device=DEV).manual_seed(0)
     x = torch.randn(N, C, Hh, Ww, device=DEV, generator=g) * (0.5 + 1.5 * torch.rand(N, C, 1, 1, device=DEV, generator=g)) \
@@ -352,6 +356,52 @@ FUSED_SHAPES = [((256, 8, 56, 56), torch.float32), ((64, 32, 32, 32), torch.floa
                 ((256, 256, 7, 7), torch.float32), ((512, 32, 16, 16), torch.float32), ((96, 24, 28, 28), torch.float32),
                 ((256, 16, 56, 56), torch.bfloat16), ((300, 20, 20, 20), torch.float32), ((40, 6, 224, 224), torch.float32),
                 ((64, 16, 14, 14), torch.bfloat16), ((40, 24, 7, 7), torch.bfloat16), ((37, 12, 7, 7), torch.float32)]
+
+
+TMEM_SHAPES = [((37, 3, 40, 40), torch.float32), ((20, 2, 48, 48), torch.float32), ((16, 3, 52, 52), torch.float32),
+               ((19, 5, 56, 56), torch.float32), ((9, 2, 64, 64), torch.float32), ((33, 3, 56, 56), torch.bfloat16),
+               ((17, 2, 72, 72), torch.bfloat16), ((16, 2, 80, 80), torch.bfloat16), ((18, 3, 88, 88), torch.float16)]
+
+
+@pytest.mark.parametrize("shape,dtype", TMEM_SHAPES)
+@pytest.mark.parametrize("relu", [False, True])
+def test_selfnorm_tensor_memory_pipeline_vs_oracle(mod, shape, dtype, relu):
+    """The shared-memory + tensor-memory pipeline (selfnorm_tmem.cu), forced onto small tensors (tm_items = 0) so that
+    the numpy oracle can check every geometry it instantiates: 4..8 vectors per thread (planes of 6..16 KB), ragged last
+    items, persistent grids smaller than the item count (every CTA then runs many two-stage iterations), the ReLU of
+    a block tail; against the same call with the pipeline off (tm = 0) as well."""
+    x = O.varied_input(shape, seed=sum(shape), dtype=np.float32)
+    dy = np.random.RandomState(5).standard_normal(shape).astype(np.float32)
+    if dtype != torch.float32:
+        x = torch.from_numpy(x).to(dtype).float().numpy()
+        dy = torch.from_numpy(dy).to(dtype).float().numpy()
+    params, bufs = H.random_sn_params(shape[1], seed=6)
+    o = H.oracle_selfnorm(x, dy, params, bufs, True)
+    if relu:                                             # block tail relu(SelfNorm(x)): y clamps, dy masked where x <= 0
+        o = dict(o)
+        o["y"] = np.maximum(o["y"], 0.0)
+        dzo, gr = O.selfnorm_bwd(x.astype(np.float64), np.where(x > 0, dy, 0.0), params, bufs, True)
+        o["dx"], o["dg_w"], o["dg_gamma"], o["dg_beta"] = dzo, gr["g_w"], gr["g_gamma"], gr["g_beta"]
+    chk = close32 if dtype == torch.float32 else close16
+    # tm = 3: the pipeline for the 16-bit forward too (off by default there: issue-bound, slower than the plain kernel)
+    for knobs in ({"tm_items": 0, "tm": 3}, {"tm_items": 0, "tm": 3, "grid_cap": 2}, {"tm": 0}):
+        with L.tuned(**knobs):
+            n0 = L.launch_count()
+            m = H.make_selfnorm(mod, shape[1], params, bufs, DEV, False, True)
+            xt = torch.from_numpy(x).to(device=DEV, dtype=dtype).requires_grad_(True)
+            y = m(xt, None, True) if relu else m(xt)
+            y.backward(torch.from_numpy(dy).to(device=DEV, dtype=dtype))
+            torch.cuda.synchronize()
+            assert L.launch_count() - n0 == 2              # one kernel per direction
+        chk(y.detach().double().cpu().numpy(), o["y"], "y")
+        chk(xt.grad.double().cpu().numpy(), o["dx"], "dx")
+        tol = H.PARAM_RTOL if dtype == torch.float32 else 2e-4
+        assert H.relmax(m.g_fc.weight.grad.view(-1, 2).double().cpu().numpy(), o["dg_w"]) <= tol
+        assert H.relmax(m.g_bn.weight.grad.double().cpu().numpy(), o["dg_gamma"]) <= tol
+        assert H.relmax(m.g_bn.bias.grad.double().cpu().numpy(), o["dg_beta"]) <= tol
+        close32(m.g_bn.running_mean.double().cpu().numpy(), o["g_rm_after"], "running_mean")
+        close32(m.g_bn.running_var.double().cpu().numpy(), o["g_rv_after"], "running_var")
+    L.async_error()
 
 
 EDGE_SHAPES = [(700, 4, 8, 8), (2, 1, 4, 4), (3, 5, 2, 2), (1030, 2, 4, 4), (33, 7, 12, 12), (2, 3, 56, 56), (130, 8, 7, 7), (9, 16, 14, 14)]
