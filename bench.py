@@ -279,6 +279,22 @@ def bench_crossnorm(torch, M, dev, steps=30):
         f = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2]
         b = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2]
         out[name] = {"fwd_us": f * 1e3, "bwd_us": b * 1e3, "bytes_5S": 5 * S, "gbs": 5 * S / ((f + b) * 1e-3) / 1e9}
+        if S < (64 << 20):
+            # a lone autograd.grad pays the engine's start-up and thread hand-off (~40 us) on top of the node; inside a
+            # training graph the per-node cost is what counts: 8 calls chained, one backward, per node
+            chain = 8
+            ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+            for e in ev:
+                e[0].record()
+                v = x
+                for _ in range(chain):
+                    v = M.cn_op_2ins_space_chan(v, crop=crop, beta=1)
+                e[1].record()
+                torch.autograd.grad(v, x, dy)
+                e[2].record()
+            torch.cuda.synchronize()
+            out[name]["fwd_us_in_graph"] = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2] * 1e3 / chain
+            out[name]["bwd_us_in_graph"] = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2] * 1e3 / chain
         del x, dy
     return out
 
@@ -486,10 +502,32 @@ def main():
         b.record()
         barrier()
         e_ms = max_over_ranks(a.elapsed_time(b)) / e2e_steps
+        # the e2e leg's own roofline: the SAME pinned copies (2*S host->device and 2*S device->host per step, both
+        # directions at once) with no compute in between -- what this box's host side delivers to N ranks at a time
+        torch.cuda.synchronize()
+        barrier()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        for i in range(e2e_steps):
+            bx, bdy = bufs[i % 2]
+            with torch.cuda.stream(h2d):
+                bx.copy_(hx, non_blocking=True)
+                bdy.copy_(hdy, non_blocking=True)
+            with torch.cuda.stream(d2h):
+                hy.copy_(bx, non_blocking=True)
+                hdx.copy_(bdy, non_blocking=True)
+        comp.wait_stream(d2h)
+        comp.wait_stream(h2d)
+        b2.record()
+        barrier()
+        c_ms = max_over_ranks(a2.elapsed_time(b2)) / e2e_steps
         e2e = {"value": world * 5 * S / (e_ms * 1e-3) / 1e9, "unit": "GB/s", "h2d_bytes_per_step": 2 * S,
                "d2h_bytes_per_step": 2 * S, "ms_per_step": e_ms, "steps": e2e_steps,
                "api": "cnsn_b200.cnsn.SelfNorm forward + autograd backward on pinned host tensors; "
-                      "double-buffered: H2D / compute / D2H of consecutive steps overlap on three streams"}
+                      "double-buffered: H2D / compute / D2H of consecutive steps overlap on three streams",
+               "copy_only": {"ms_per_step": c_ms, "gbs_per_direction_per_gpu": 2 * S / (c_ms * 1e-3) / 1e9,
+                             "what": "the same pinned copies without the compute, all ranks at once: the host-side ceiling of this leg"},
+               "frac_of_copy_only": c_ms / e_ms}
         if numa is not None:
             e2e["numa_cpus"] = numa if isinstance(numa, str) else "%d cpus bound (NVML affinity of the GPU)" % len(numa)
         del bufs

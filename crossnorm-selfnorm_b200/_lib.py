@@ -18,7 +18,7 @@ EXT_PATH = os.path.join(_PKG, "_cnsn_torch.so")
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
 CNSN_E_TIMEOUT = -6
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 _DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
 
@@ -67,9 +67,9 @@ SIGNATURES = {
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),
-    "cnsn_ibn_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_float, c_float, c_float,
+    "cnsn_ibn_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_int, c_float, c_float, c_float,
                              c_void_p, c_void_p]),
-    "cnsn_ibn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_void_p,
+    "cnsn_ibn_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, POINTER(IbnParams), c_int, c_int, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "cnsn_jsd_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -400,7 +400,7 @@ class CudaBackend:
         with _on(x.device):
             return bool(_size("cnsn_ibn_resident", _dtype_code(x), N, C, H, W, int(half), int(training)))
 
-    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
+    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn, relu=False):
         _require_cuda(x)
         N, C, H, W = x.shape
         keep = []
@@ -409,7 +409,7 @@ class CudaBackend:
         y = torch.empty_like(x)
         with _on(x.device):
             _check(lib().cnsn_ibn_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
-                                      momentum, eps_in, eps_bn, _p(save), _stream(x)))
+                                      int(relu), momentum, eps_in, eps_bn, _p(save), _stream(x)))
         if training:                     # buffers that were not fp32-contiguous were updated in a temporary: write back
             for name, tmp in (("run_mean", keep[4]), ("run_var", keep[5])):
                 buf = p.get(name)
@@ -417,7 +417,7 @@ class CudaBackend:
                     buf.copy_(tmp)
         return y, save
 
-    def ibn_bwd(self, x, dy, half, p, training, save):
+    def ibn_bwd(self, x, dy, half, p, training, save, relu=False):
         _require_cuda(x, dy)
         N, C, H, W = x.shape
         keep = []
@@ -429,7 +429,7 @@ class CudaBackend:
         dx = torch.empty_like(x)
         with _on(dev):
             _check(lib().cnsn_ibn_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, half, ctypes.byref(ps), int(training),
-                                      _p(save), _p(d_in_w), _p(d_in_b), _p(d_bn_w), _p(d_bn_b), _p(ws), _stream(x)))
+                                      int(relu), _p(save), _p(d_in_w), _p(d_in_b), _p(d_bn_w), _p(d_bn_b), _p(ws), _stream(x)))
         return dx, (d_in_w, d_in_b, d_bn_w, d_bn_b)
 
     # -- JSD consistency --------------------------------------------------------------------

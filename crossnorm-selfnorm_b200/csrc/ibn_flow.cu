@@ -33,6 +33,7 @@ struct IArgs {
     const void* x; const void* dy; void* out;
     int N, C, M, half;
     int nI, poll_ns, pf_dist, training;
+    int relu;                                   // y = max(y, 0) (forward) / dy masked where y <= 0 (backward, y rebuilt from x)
     unsigned items;
     float eps_in, eps_bn, momentum;
     const float* in_w; const float* in_b;       // [half]
@@ -92,13 +93,17 @@ __device__ __forceinline__ void ibn_res_item(const IArgs& a, const unsigned t, c
     const bool folder = j == nI - 1;
     const bool coupled = !is_in && a.training != 0;          // only training-mode batch norm waits for the channel
     const float gam = is_in ? a.in_w[c] : a.bn_w[cb];
-    const float bet = BWD ? 0.f : (is_in ? a.in_b[c] : a.bn_b[cb]);
+    const bool relu = a.relu != 0;
+    const float bet = (BWD && !relu) ? 0.f : (is_in ? a.in_b[c] : a.bn_b[cb]);
     // backward: the statistics the forward saved
     float mean = 0.f, rstd = 1.f;
     if (BWD) {
         if (is_in) { if (live) { mean = a.in_mean[(size_t)n * half + c]; rstd = a.in_rstd[(size_t)n * half + c]; } }
         else { mean = a.bn_mean[cb]; rstd = a.bn_rstd[cb]; }
     }
+    // backward with a fused ReLU: the forward output y = fy*x + fc is rebuilt from x (same fp32 expressions as the forward:
+    // same bits), dy passes where y > 0
+    const float fy = rstd * gam, fc = bet - mean * fy;
     mbar_wait(bar, par, a.err);
 
     // ---- per-instance reduction ------------------------------------------------------------------
@@ -135,7 +140,10 @@ __device__ __forceinline__ void ibn_res_item(const IArgs& a, const unsigned t, c
                     unpack<T>(lds128(sx + 16u * i), vx);
                     unpack<T>(lds128(sdy + 16u * i), vd);
 #pragma unroll
-                    for (int e = 0; e < V; ++e) { s0 += vd[e]; s1 = fmaf(vd[e], (vx[e] - mean) * rstd, s1); }
+                    for (int e = 0; e < V; ++e) {
+                        const float d = (relu && !(fmaf(fy, vx[e], fc) > 0.f)) ? 0.f : vd[e];
+                        s0 += d; s1 = fmaf(d, (vx[e] - mean) * rstd, s1);
+                    }
                 }
             }
             own_x = team_sum<TPI>(s0, s_f[0]);
@@ -236,7 +244,15 @@ __device__ __forceinline__ void ibn_res_item(const IArgs& a, const unsigned t, c
         unpack<T>(lds128(sx + 16u * i), vx);
         if (BWD) unpack<T>(lds128(sdy + 16u * i), vd);
 #pragma unroll
-        for (int e = 0; e < V; ++e) vo[e] = BWD ? fmaf(ca, vd[e], fmaf(cbx, vx[e], cc)) : fmaf(cbx, vx[e], cc);
+        for (int e = 0; e < V; ++e) {
+            if (BWD) {
+                const float d = (relu && !(fmaf(fy, vx[e], fc) > 0.f)) ? 0.f : vd[e];
+                vo[e] = fmaf(ca, d, fmaf(cbx, vx[e], cc));
+            } else {
+                const float y = fmaf(cbx, vx[e], cc);
+                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            }
+        }
         stg_stream(po + i, pack<T>(vo));
     }
 }
@@ -327,7 +343,7 @@ extern "C" int cnsn_ibn_resident(int dtype, int N, int C, int H, int W, int half
 }
 
 extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, int half,
-                            const cnsn_ibn_params* p, int training, float momentum, float eps_in, float eps_bn,
+                            const cnsn_ibn_params* p, int training, int relu, float momentum, float eps_in, float eps_bn,
                             float* save, void* stream) {
     if (!x || !y || !p || !save || check_dims(N, C, H, W) || half < 0 || half > C) return CNSN_E_BADARG;
     if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
@@ -337,38 +353,39 @@ extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int
     if (training && half < C && (long long)N * H * W < 2) return CNSN_E_BATCH1;
     flow::IArgs a{};
     a.x = x; a.dy = nullptr; a.out = y; a.N = N; a.C = C; a.M = H * W; a.half = half;
-    a.training = training; a.momentum = momentum; a.eps_in = eps_in; a.eps_bn = eps_bn;
+    a.training = training; a.relu = relu ? 1 : 0; a.momentum = momentum; a.eps_in = eps_in; a.eps_bn = eps_bn;
     a.in_w = p->in_w; a.in_b = p->in_b; a.bn_w = p->bn_w; a.bn_b = p->bn_b;
     a.run_mean = p->run_mean; a.run_var = p->run_var; a.nbt = p->nbt;
     a.in_mean = save; a.in_rstd = save + (size_t)N * half;
     a.bn_mean = save + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     float* scratch = save + ibn_stats_floats(N, C, half);
     const int rc = vec ? flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
-    if (rc != CNSN_E_UNSUPPORTED) return rc;
+    if (rc != CNSN_E_UNSUPPORTED || relu) return rc;  // the fused ReLU exists in the resident kernel only (cnsn_ibn_resident)
     ibn_general::GArgs g = general_args(a);          // odd / oversized planes, misaligned slices: the three-kernel path
     return ibn_general::ibn_general_fwd(g, dtype, scratch, (cudaStream_t)stream);
 }
 
 extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W, int half,
-                            const cnsn_ibn_params* p, int training, const float* save,
+                            const cnsn_ibn_params* p, int training, int relu, const float* save,
                             float* d_in_w, float* d_in_b, float* d_bn_w, float* d_bn_b,
                             float* workspace, void* stream) {
     if (!x || !dy || !dx || !p || !save || !workspace || check_dims(N, C, H, W) || half < 0 || half > C) return CNSN_E_BADARG;
     if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
     if ((half > 0 && (!p->in_w || !d_in_w || !d_in_b)) || (half < C && (!p->bn_w || !d_bn_w || !d_bn_b))) return CNSN_E_BADARG;
+    if (relu && ((half > 0 && !p->in_b) || (half < C && !p->bn_b))) return CNSN_E_BADARG;      // the mask is rebuilt from x: needs the bias
     if (reinterpret_cast<uintptr_t>(x) % esize(dtype) || reinterpret_cast<uintptr_t>(dy) % esize(dtype) ||
         reinterpret_cast<uintptr_t>(dx) % esize(dtype)) return CNSN_E_ALIGN;
     const bool vec = aligned16(x) && aligned16(dy) && aligned16(dx);
     flow::IArgs a{};
     a.x = x; a.dy = dy; a.out = dx; a.N = N; a.C = C; a.M = H * W; a.half = half;
-    a.training = training;
-    a.in_w = p->in_w; a.bn_w = p->bn_w;
+    a.training = training; a.relu = relu ? 1 : 0;
+    a.in_w = p->in_w; a.bn_w = p->bn_w; a.in_b = p->in_b; a.bn_b = p->bn_b;
     float* sv = const_cast<float*>(save);
     a.in_mean = sv; a.in_rstd = sv + (size_t)N * half;
     a.bn_mean = sv + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     a.d_in_w = d_in_w; a.d_in_b = d_in_b; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b;
     const int rc = vec ? flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
-    if (rc != CNSN_E_UNSUPPORTED) return rc;
+    if (rc != CNSN_E_UNSUPPORTED || relu) return rc;
     ibn_general::GArgs g = general_args(a);
     return ibn_general::ibn_general_bwd(g, dtype, workspace, (cudaStream_t)stream);
 }

@@ -284,7 +284,7 @@ struct SiteNode : public torch::autograd::Function<SiteNode> {
 
 // ---- IBN / InstanceNorm2d / BatchNorm2d (cnsn_ibn_fwd/_bwd: half == C instance norm, half == 0 batch norm) --------
 struct IbnNode : public torch::autograd::Function<IbnNode> {
-    static at::Tensor forward(AutogradContext* ctx, const at::Tensor& x_in, int64_t half, bool training, double momentum,
+    static at::Tensor forward(AutogradContext* ctx, const at::Tensor& x_in, int64_t half, bool training, bool relu, double momentum,
                               double eps_in, double eps_bn, GateBufs bufs, const c10::optional<at::Tensor>& in_w,
                               const c10::optional<at::Tensor>& in_b, const c10::optional<at::Tensor>& bn_w,
                               const c10::optional<at::Tensor>& bn_b) {
@@ -303,21 +303,22 @@ struct IbnNode : public torch::autograd::Function<IbnNode> {
         p.nbt = bufs.nbt.defined() ? reinterpret_cast<long long*>(bufs.nbt.data_ptr<int64_t>()) : nullptr;
         at::Tensor save = f32_buffer(x, (int64_t)cnsn_ibn_save_floats(N, C, (int)half));
         at::Tensor y = at::empty_like(x);
-        check(cnsn_ibn_fwd(x.data_ptr(), y.data_ptr(), dtype_code(x), N, C, H, W, (int)half, &p, training ? 1 : 0, (float)momentum,
-                           (float)eps_in, (float)eps_bn, save.data_ptr<float>(), stream));
+        check(cnsn_ibn_fwd(x.data_ptr(), y.data_ptr(), dtype_code(x), N, C, H, W, (int)half, &p, training ? 1 : 0, relu ? 1 : 0,
+                           (float)momentum, (float)eps_in, (float)eps_bn, save.data_ptr<float>(), stream));
         at::Tensor none;
-        ctx->save_for_backward({x, save, (in_w.has_value() && in_w->defined()) ? *in_w : none,
-                                (bn_w.has_value() && bn_w->defined()) ? *bn_w : none});
+        auto opt = [&](const c10::optional<at::Tensor>& t) { return (t.has_value() && t->defined()) ? *t : none; };
+        ctx->save_for_backward({x, save, opt(in_w), opt(bn_w), opt(in_b), opt(bn_b)});
         ctx->saved_data["half"] = half;
         ctx->saved_data["training"] = training;
+        ctx->saved_data["relu"] = relu;
         return y;
     }
 
     static variable_list backward(AutogradContext* ctx, variable_list grads) {
         const auto saved = ctx->get_saved_variables();
-        const at::Tensor &x = saved[0], &save = saved[1], &in_w = saved[2], &bn_w = saved[3];
+        const at::Tensor &x = saved[0], &save = saved[1], &in_w = saved[2], &bn_w = saved[3], &in_b = saved[4], &bn_b = saved[5];
         const int half = (int)ctx->saved_data["half"].toInt();
-        const bool training = ctx->saved_data["training"].toBool();
+        const bool training = ctx->saved_data["training"].toBool(), relu = ctx->saved_data["relu"].toBool();
         const at::Tensor dy = grads[0].contiguous();
         const c10::cuda::CUDAGuard guard(x.device());
         cudaStream_t stream = at::cuda::getCurrentCUDAStream();
@@ -328,12 +329,14 @@ struct IbnNode : public torch::autograd::Function<IbnNode> {
         cnsn_ibn_params p{};
         p.in_w = in_w.defined() ? in_w.data_ptr<float>() : nullptr;
         p.bn_w = bn_w.defined() ? bn_w.data_ptr<float>() : nullptr;
+        p.in_b = in_b.defined() ? in_b.data_ptr<float>() : nullptr;
+        p.bn_b = bn_b.defined() ? bn_b.data_ptr<float>() : nullptr;
         float* g = pg.data_ptr<float>();
         check(cnsn_ibn_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dtype_code(x), N, C, H, W, half, &p, training ? 1 : 0,
-                           save.data_ptr<float>(), g, g + half, g + 2 * half, g + C + half, ws.data_ptr<float>(), stream));
+                           relu ? 1 : 0, save.data_ptr<float>(), g, g + half, g + 2 * half, g + C + half, ws.data_ptr<float>(), stream));
         at::Tensor none;
         const int nb = C - half;
-        return {dx, none, none, none, none, none, none,
+        return {dx, none, none, none, none, none, none, none,
                 half > 0 ? pg.narrow(0, 0, half) : none, half > 0 ? pg.narrow(0, half, half) : none,
                 nb > 0 ? pg.narrow(0, 2 * half, nb) : none, nb > 0 ? pg.narrow(0, C + half, nb) : none};
     }
@@ -380,7 +383,7 @@ bool site_supported(const at::Tensor& x) {
     return cnsn_site_supported(dtype_code(x), (int)x.size(0), (int)x.size(1), (int)x.size(2), (int)x.size(3)) != 0;
 }
 
-at::Tensor ibn(const at::Tensor& x, int64_t half, bool training, double momentum, double eps_in, double eps_bn,
+at::Tensor ibn(const at::Tensor& x, int64_t half, bool training, bool relu, double momentum, double eps_in, double eps_bn,
                const c10::optional<at::Tensor>& run_mean, const c10::optional<at::Tensor>& run_var,
                const c10::optional<at::Tensor>& nbt, const c10::optional<at::Tensor>& in_w, const c10::optional<at::Tensor>& in_b,
                const c10::optional<at::Tensor>& bn_w, const c10::optional<at::Tensor>& bn_b) {
@@ -395,7 +398,7 @@ at::Tensor ibn(const at::Tensor& x, int64_t half, bool training, double momentum
     if (half < C) { ok(bn_w, C - half, "BN.weight"); ok(bn_b, C - half, "BN.bias"); ok(run_mean, C - half, "BN.running_mean"); ok(run_var, C - half, "BN.running_var"); }
     GateBufs b{run_mean.has_value() ? *run_mean : at::Tensor(), run_var.has_value() ? *run_var : at::Tensor(),
                nbt.has_value() ? *nbt : at::Tensor()};
-    return IbnNode::apply(x, half, training, momentum, eps_in, eps_bn, b, in_w, in_b, bn_w, bn_b);
+    return IbnNode::apply(x, half, training, relu, momentum, eps_in, eps_bn, b, in_w, in_b, bn_w, bn_b);
 }
 
 bool ibn_resident(const at::Tensor& x, int64_t half, bool training) {

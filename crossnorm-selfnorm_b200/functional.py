@@ -173,22 +173,24 @@ class JsdConsistencyFn(torch.autograd.Function):
 
 
 class IbnFn(torch.autograd.Function):
-    """IBN.forward (models/imagenet/resnet_ibn_cnsn.py:38-44) and its backward, one kernel each."""
+    """IBN.forward (models/imagenet/resnet_ibn_cnsn.py:38-44) and its backward, one kernel each; ``relu``: the ReLU that
+    follows the norm in the host blocks, in the same kernels."""
 
     @staticmethod
-    def forward(ctx, x, half, training, momentum, eps_in, eps_bn, bufs, in_w, in_b, bn_w, bn_b):
+    def forward(ctx, x, half, training, momentum, eps_in, eps_bn, bufs, in_w, in_b, bn_w, bn_b, relu=False):
         x = _dense(x)
         p = {"in_w": in_w, "in_b": in_b, "bn_w": bn_w, "bn_b": bn_b, "run_mean": bufs[0], "run_var": bufs[1], "nbt": bufs[2]}
-        y, save = _lib.backend().ibn_fwd(x, half, p, training, momentum, eps_in, eps_bn)
-        ctx.save_for_backward(x, in_w, bn_w)
-        ctx.ibn = (half, training, save)
+        y, save = _lib.backend().ibn_fwd(x, half, p, training, momentum, eps_in, eps_bn, relu)
+        ctx.save_for_backward(x, in_w, bn_w, in_b, bn_b)
+        ctx.ibn = (half, training, save, bool(relu))
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, in_w, bn_w = ctx.saved_tensors
-        half, training, save = ctx.ibn
-        dx, g = _lib.backend().ibn_bwd(x, _dense(dy), half, {"in_w": in_w, "bn_w": bn_w}, training, save)
+        x, in_w, bn_w, in_b, bn_b = ctx.saved_tensors
+        half, training, save, relu = ctx.ibn
+        dx, g = _lib.backend().ibn_bwd(x, _dense(dy), half, {"in_w": in_w, "bn_w": bn_w, "in_b": in_b, "bn_b": bn_b}, training,
+                                       save, relu)
         gi = (g[0].to(in_w.dtype), g[1].to(in_w.dtype)) if in_w is not None else (None, None)
         gb = (g[2].to(bn_w.dtype), g[3].to(bn_w.dtype)) if bn_w is not None else (None, None)   # half == C: no BN half
-        return (dx, None, None, None, None, None, None) + gi + gb
+        return (dx, None, None, None, None, None, None) + gi + gb + (None,)

@@ -10,3 +10,12 @@ def batchnorm2d_for(ops, fast_bn=True):
         from ..ibn import BatchNorm2d
         return BatchNorm2d
     return nn.BatchNorm2d
+
+
+def bn_relu(bn, relu, x):
+    """``relu(bn(x))`` of a host block: ONE fused call when ``bn`` is the package's BatchNorm2d drop-in (the ReLU runs
+    inside the batch-norm kernels, forward and backward), the two modules one after the other otherwise."""
+    from ..ibn import BatchNorm2d
+    if isinstance(bn, BatchNorm2d):
+        return bn(x, True)
+    return relu(bn(x))

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._norm import batchnorm2d_for
+from ._norm import batchnorm2d_for, bn_relu
 
 _POSITIONS = ("residual", "pre", "post", "identity")
 _EXPANSION = 4
@@ -70,8 +70,8 @@ class Bottleneck(nn.Module):
         h = self.cnsn(x) if self.pos == "pre" else x
         if self.ibn_variant and self.pos == "pre" and self.downsample is not None:
             x = h                                        # the IBN host feeds the projection from the site's output (:98-99,:112-113)
-        h = self.relu(self.bn1(self.conv1(h)))
-        h = self.relu(self.bn2(self.conv2(h)))
+        h = bn_relu(self.bn1, self.relu, self.conv1(h))
+        h = bn_relu(self.bn2, self.relu, self.conv2(h))
         h = self.bn3(self.conv3(h))
         skip = x if self.downsample is None else self.downsample(x)
         if self.pos == "residual":
@@ -151,7 +151,7 @@ class ResNet(nn.Module):
     def forward(self, x, aug=False):
         if aug:
             self._enable_cross_norm()
-        h = self.maxpool(self.relu(self.bn1(self.conv1(x))))
+        h = self.maxpool(bn_relu(self.bn1, self.relu, self.conv1(x)))
         h = self.layer4(self.layer3(self.layer2(self.layer1(h))))
         return self.fc(torch.flatten(self.avgpool(h), 1))
 

@@ -13,7 +13,11 @@ import numpy as np
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ._norm import batchnorm2d_for
+from ._norm import batchnorm2d_for, bn_relu
+
+
+def _relu_(t):
+    return F.relu(t, inplace=True)
 
 _POSITIONS = ("residual", "identity", "pre", "post")
 _EXPANSION = 4
@@ -47,8 +51,8 @@ class _Bottleneck(nn.Module):
         skip = x
         if self.pos == "pre":
             x = self.cnsn(x)
-        h = F.relu(self.bn_reduce(self.conv_reduce(x)), inplace=True)
-        h = F.relu(self.bn(self.conv_conv(h)), inplace=True)
+        h = bn_relu(self.bn_reduce, _relu_, self.conv_reduce(x))
+        h = bn_relu(self.bn, _relu_, self.conv_conv(h))
         h = self.bn_expand(self.conv_expand(h))
         if self.pos == "residual":
             h = self.cnsn(h)
@@ -111,7 +115,7 @@ class CifarResNeXt(nn.Module):
     def forward(self, x, aug=False):
         if aug:
             self._enable_cross_norm()
-        h = F.relu(self.bn_1(self.conv_1_3x3(x)), inplace=True)
+        h = bn_relu(self.bn_1, _relu_, self.conv_1_3x3(x))
         h = self.avgpool(self.stage_3(self.stage_2(self.stage_1(h))))
         return self.classifier(h.view(h.size(0), -1))
 

@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ._norm import batchnorm2d_for
+from ._norm import batchnorm2d_for, bn_relu
 
 _POSITIONS = ("residual", "identity", "pre", "post")
 
@@ -54,13 +54,13 @@ class _PreActBlock(nn.Module):
     def forward(self, x):
         if self.same:
             h = self.cnsn(x) if self.pos == "pre" else x
-            h = self.relu1(self.bn1(h))
+            h = bn_relu(self.bn1, self.relu1, h)
             skip = x
         else:                                   # projection block: the pre-activation is shared
-            x = self.relu1(self.bn1(x))
+            x = bn_relu(self.bn1, self.relu1, x)
             h = self.cnsn(x) if self.pos == "pre" else x
             skip = None
-        h = self.relu2(self.bn2(self.conv1(h)))
+        h = bn_relu(self.bn2, self.relu2, self.conv1(h))
         if self.drop_rate > 0:
             h = F.dropout(h, p=self.drop_rate, training=self.training)
         h = self.conv2(h)
@@ -134,5 +134,5 @@ class WideResNet(nn.Module):
         if aug:
             self._enable_cross_norm()
         h = self.block3(self.block2(self.block1(self.conv1(x))))
-        h = F.avg_pool2d(self.relu(self.bn1(h)), 8)
+        h = F.avg_pool2d(bn_relu(self.bn1, self.relu, h), 8)
         return self.fc(h.view(h.size(0), -1))

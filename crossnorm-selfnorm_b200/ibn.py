@@ -38,7 +38,7 @@ class IBN(nn.Module):
         momentum = bn_momentum(bn)
         ext = _lib.fast_binding() if (x.is_cuda and bn.weight.dtype is torch.float32) else None
         if ext is not None:                           # C++ autograd node
-            return ext.ibn(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps), bn.running_mean,
+            return ext.ibn(x, self.half, bn.training, False, momentum, float(self.IN.eps), float(bn.eps), bn.running_mean,
                            bn.running_var, bn.num_batches_tracked, self.IN.weight, self.IN.bias, bn.weight, bn.bias)
         return IbnFn.apply(x, self.half, bn.training, momentum, float(self.IN.eps), float(bn.eps),
                            (bn.running_mean, bn.running_var, bn.num_batches_tracked),
@@ -59,8 +59,8 @@ class InstanceNorm2d(nn.InstanceNorm2d):
         assert x.dim() == 4 and x.size(1) == self.num_features
         ext = _lib.fast_binding() if (x.is_cuda and self.weight.dtype is torch.float32) else None
         if ext is not None:
-            return ext.ibn(x, self.num_features, False, 0.1, float(self.eps), 1e-5, None, None, None, self.weight, self.bias,
-                           None, None)
+            return ext.ibn(x, self.num_features, False, False, 0.1, float(self.eps), 1e-5, None, None, None, self.weight,
+                           self.bias, None, None)
         return IbnFn.apply(x, self.num_features, False, 0.1, float(self.eps), 1e-5, (None, None, None),
                            self.weight, self.bias, None, None)
 
@@ -75,7 +75,9 @@ class BatchNorm2d(nn.BatchNorm2d):
     Anything the resident kernels do not take (CPU tensors, planes that are not 16-byte multiples or do not fit shared
     memory, ``affine=False`` / no running statistics) goes to the torch implementation."""
 
-    def forward(self, x):
+    def forward(self, x, relu=False):
+        """``forward(x)`` is ``nn.BatchNorm2d.forward``; ``forward(x, relu=True)`` is ``relu(bn(x))`` -- the pair the host
+        blocks apply -- in the same kernels when the resident path takes the shape, else torch's batch norm + relu."""
         if (x.is_cuda and x.dim() == 4 and self.affine and self.track_running_stats and self.weight.dtype is torch.float32
                 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
             training = self.training
@@ -84,9 +86,11 @@ class BatchNorm2d(nn.BatchNorm2d):
                 momentum = bn_momentum(self)
                 ext = _lib.fast_binding()
                 if ext is not None:
-                    return ext.ibn(x, 0, training, momentum, 1e-5, float(self.eps), self.running_mean, self.running_var,
-                                   self.num_batches_tracked, None, None, self.weight, self.bias)
+                    return ext.ibn(x, 0, training, bool(relu), momentum, 1e-5, float(self.eps), self.running_mean,
+                                   self.running_var, self.num_batches_tracked, None, None, self.weight, self.bias)
                 return IbnFn.apply(x, 0, training, momentum, 1e-5, float(self.eps),
                                    (self.running_mean, self.running_var, self.num_batches_tracked),
-                                   None, None, self.weight, self.bias)
-        return super().forward(x)
+                                   None, None, self.weight, self.bias, bool(relu))
+        y = super().forward(x)
+        return torch.relu_(y) if relu else y
+

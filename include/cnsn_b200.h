@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CNSN_ABI_VERSION 5
+#define CNSN_ABI_VERSION 6
 
 enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
 
@@ -268,11 +268,15 @@ size_t cnsn_ibn_workspace_floats(int N, int C);
  * a host model asks before it routes an nn.BatchNorm2d -- half == 0 -- through these entry points instead of cuDNN), else 0
  * (the entry points then take the three-kernel general path: correct, not tuned). */
 int cnsn_ibn_resident(int dtype, int N, int C, int H, int W, int half, int training);
+/* relu != 0: the ReLU that follows the norm in the host blocks (relu(bn(x)), wideresnet_cnsn.py:66-72, resnet_cnsn.py:
+ * 100-110) in the same kernels -- forward y = max(y, 0); backward dy masked where y <= 0, y rebuilt from x and the saved
+ * statistics (p->in_b / p->bn_b must then be given to the backward too).  Resident kernel only: CNSN_E_UNSUPPORTED for a
+ * shape cnsn_ibn_resident() declines. */
 int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W, int half,
-                 const cnsn_ibn_params* p, int training, float momentum, float eps_in, float eps_bn,
+                 const cnsn_ibn_params* p, int training, int relu, float momentum, float eps_in, float eps_bn,
                  float* save, void* stream);
 int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W, int half,
-                 const cnsn_ibn_params* p, int training, const float* save,
+                 const cnsn_ibn_params* p, int training, int relu, const float* save,
                  float* d_in_w, float* d_in_b, float* d_bn_w, float* d_bn_b,
                  float* workspace, void* stream);
 

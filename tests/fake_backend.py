@@ -96,7 +96,10 @@ class OracleBackend:
         dz, gg, _ = self.selfnorm_bwd(z, d, g, None, training, save)
         return dz, gg
 
-    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn):
+    def ibn_resident(self, x, half, training):
+        return False                                        # the drop-in BatchNorm2d then takes torch's implementation
+
+    def ibn_fwd(self, x, half, p, training, momentum, eps_in, eps_bn, relu=False):
         self.calls.append("ibn_fwd")
         e = np.zeros(0)                                      # half == C: no batch-norm half
         pp = {k: (_np(p[k]) if p.get(k) is not None else e) for k in ("in_w", "in_b", "bn_w", "bn_b")}
@@ -108,12 +111,19 @@ class OracleBackend:
             p["run_var"].copy_(_t(rv, p["run_var"]))
             if p.get("nbt") is not None:
                 p["nbt"] += 1
-        return _t(y, x), {"bufs": bufs, "eps": (eps_in, eps_bn)}
+        mask = (y > 0) if relu else None
+        if relu:
+            y = np.maximum(y, 0.0)
+        return _t(y, x), {"bufs": bufs, "eps": (eps_in, eps_bn), "mask": mask}
 
-    def ibn_bwd(self, x, dy, half, p, training, save):
+    def ibn_bwd(self, x, dy, half, p, training, save, relu=False):
         self.calls.append("ibn_bwd")
-        pp = {"in_w": _np(p["in_w"]), "bn_w": _np(p["bn_w"]) if p.get("bn_w") is not None else np.zeros(0)}
-        dx, a, b, c, d = IB.ibn_bwd(_np(x), _np(dy), half, pp, save["bufs"], training, *save["eps"])
+        pp = {"in_w": _np(p["in_w"]) if p.get("in_w") is not None else np.zeros(0),
+              "bn_w": _np(p["bn_w"]) if p.get("bn_w") is not None else np.zeros(0)}
+        dyn = _np(dy)
+        if relu:
+            dyn = np.where(save["mask"], dyn, 0.0)
+        dx, a, b, c, d = IB.ibn_bwd(_np(x), dyn, half, pp, save["bufs"], training, *save["eps"])
         return _t(dx, x), tuple(_t(v, x, torch.float32) for v in (a, b, c, d))
 
     @staticmethod

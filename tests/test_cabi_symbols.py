@@ -53,7 +53,7 @@ def test_argument_validation_without_gpu():
     assert h.cnsn_site_bwd(None, None, None, 0, 4, 16, 8, 8, None, None, None, 0.0, 1e-5, 0, None, None, None, None, None) == -1
     assert h.cnsn_site_supported(7, 4, 16, 8, 8) == 0 and h.cnsn_site_supported(0, 0, 16, 8, 8) == 0    # bad dtype / dims
     assert h.cnsn_site_supported(0, 4, 16, 7, 7) == 0          # 7x7 fp32 planes are not 16-byte multiples
-    assert h.cnsn_ibn_fwd(None, None, 0, 4, 16, 8, 8, 8, None, 1, 0.1, 1e-5, 1e-5, None, None) == -1
+    assert h.cnsn_ibn_fwd(None, None, 0, 4, 16, 8, 8, 8, None, 1, 0, 0.1, 1e-5, 1e-5, None, None) == -1
 
 
 def test_error_strings_cover_every_code():

@@ -283,3 +283,52 @@ def test_batchnorm2d_dropin_momentum_none_and_fallbacks():
     assert torch.allclose(c(x), nn.functional.batch_norm(x, None, None, training=True), atol=1e-5)
     d = BatchNorm2d(8).train()
     assert d(torch.randn(4, 8, 5, 5)).shape == (4, 8, 5, 5)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((64, 16, 32, 32), torch.float32), ((96, 64, 16, 16), torch.float32), ((16, 64, 56, 56), torch.float32),
+                                         ((32, 8, 32, 32), torch.bfloat16)])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("binding", ["ext", "ctypes"])
+def test_batchnorm2d_fused_relu_matches_torch(shape, dtype, training, binding):
+    """relu(bn(x)) in one kernel per direction (BatchNorm2d.forward(x, relu=True): the pair the host blocks apply) against
+    torch's batch norm + relu in fp64: y, dx, dweight, dbias, running statistics; through both host bindings."""
+    import torch.nn as nn
+    import cnsn_b200._lib as L
+    from cnsn_b200.ibn import BatchNorm2d
+    dev = "cuda:0"
+    g = torch.Generator().manual_seed(0)
+    C = shape[1]
+    x0 = (torch.randn(shape, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g)) + 0.3 * torch.randn(1, C, 1, 1, generator=g)).to(dtype)
+    dy0 = torch.randn(shape, generator=g).to(dtype)
+    ref = nn.BatchNorm2d(C).to(dev).double().train(training)
+    ours = BatchNorm2d(C).to(dev).train(training)
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref.bias.copy_(torch.randn(C, generator=g) * 0.5)
+        ref.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ours.load_state_dict({k: (v.float() if v.dtype.is_floating_point else v) for k, v in ref.state_dict().items()})
+    old = L.set_binding(binding)
+    try:
+        res = []
+        for m, dt in ((ref, torch.float64), (ours, dtype)):
+            x = x0.to(dev).to(dt).requires_grad_(True)
+            y = torch.relu(m(x)) if m is ref else m(x, True)
+            y.backward(dy0.to(dev).to(dt))
+            res.append((y.detach().double(), x.grad.double(), m.weight.grad.double(), m.bias.grad.double(),
+                        m.running_mean.double(), m.running_var.double()))
+    finally:
+        L.set_binding(old)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for name, a, b in zip(("y", "dx", "dweight", "dbias", "running_mean", "running_var"), res[0], res[1]):
+        if name == "dx":
+            # an output within rounding of 0 may fall on the other side of the ReLU than in fp64 (its dx then differs by
+            # dy): compare where the fp64 pre-activation is clear of the edge
+            xr = x0.to(dev).double()
+            pre = torch.nn.functional.batch_norm(xr, ref.running_mean if not training else None, ref.running_var if not training else None,
+                                                 ref.weight, ref.bias, training, 0.0, ref.eps)
+            clear = pre.abs() > (1e-4 if dtype == torch.float32 else 0.05)
+            a, b = a[clear], b[clear]
+        err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-12))
+        assert err <= tol, (name, err)
