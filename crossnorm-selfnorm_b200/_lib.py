@@ -49,6 +49,8 @@ SIGNATURES = {
     "cnsn_tune": (c_int, [c_char_p, c_int]),
     "cnsn_instance_stats": (c_int, [c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int, c_float,
                                     c_void_p, c_void_p, c_void_p]),
+    "cnsn_instance_stats_strided": (c_int, [c_void_p, c_int, *_DIMS, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_longlong,
+                                            ctypes.c_longlong, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "cnsn_instance_stats_bwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_instance_affine": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p, c_void_p]),
@@ -245,13 +247,18 @@ class CudaBackend:
 
     # -- statistics ---------------------------------------------------------------------
     def instance_stats(self, x, window, eps):
+        """x: any strides (a sliced / transposed view, a crop, channels_last): reduced in place, no dense copy."""
         _require_cuda(x)
         N, C, H, W = x.shape
         mean = torch.empty((N, C), dtype=torch.float32, device=x.device)
         std = torch.empty_like(mean)
         with _on(x.device):
-            _check(lib().cnsn_instance_stats(_p(x), _dtype_code(x), N, C, H, W, *window, eps,
-                                             _p(mean), _p(std), _stream(x)))
+            if x.is_contiguous():
+                _check(lib().cnsn_instance_stats(_p(x), _dtype_code(x), N, C, H, W, *window, eps,
+                                                 _p(mean), _p(std), _stream(x)))
+            else:
+                _check(lib().cnsn_instance_stats_strided(_p(x), _dtype_code(x), N, C, H, W, *x.stride(), *window, eps,
+                                                         _p(mean), _p(std), _stream(x)))
         return mean, std
 
     def instance_stats_bwd(self, x, window, mean, std, dmean, dstd):

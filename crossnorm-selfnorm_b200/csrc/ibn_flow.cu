@@ -273,7 +273,7 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     const int tpi = kIbnT / inst;
     const size_t dsmem = 128 + (size_t)inst * inst_bytes;
     const DeviceShape ds = device_shape();
-    if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_UNSUPPORTED;
+    if (dsmem > (size_t)ds.smem_optin / 2) return CNSN_E_UNSUPPORTED;      // at least two CTAs per SM
     a.nI = (N + inst - 1) / inst;
     const Knobs& kn = knobs();
     if (!dry_run) {
@@ -297,7 +297,9 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream, 
         if (e != cudaSuccess) return (int)e;                                                             \
         /* a channel must be co-resident when its items wait for each other (training-mode batch-norm channels); */ \
         /* instance-norm channels never wait (their folder only collects words of earlier tickets) */          \
-        if (a.half < C && a.training && (long long)per_sm * ds.sms < 2ll * a.nI) return CNSN_E_UNSUPPORTED;    \
+        /* (the persistent cooperative grid makes ONE co-resident channel sufficient; large planes -- the 112x112 stem */ \
+        /* of ResNet-50, 2 CTAs per SM backward -- then run a channel at a time, still far ahead of the alternative)   */ \
+        if (a.half < C && a.training && (long long)per_sm * ds.sms < (long long)a.nI) return CNSN_E_UNSUPPORTED;       \
         if (dry_run) return 0;                                                                           \
         a.pf_dist = kn.pf >= 0 ? kn.pf : per_sm * ds.sms / 2;                                            \
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \

@@ -56,6 +56,58 @@ k_instance_affine(const T* __restrict__ x, T* __restrict__ out, long long instan
                                   [=](float xv, float, int) { return fmaf(a, xv, b); });
 }
 
+
+// ---- strided input (sN, sC, sH, sW) -- no dense copy for sliced / transposed views or channels_last ----
+// Generic: one warp per instance walks the window row-major (coalesced when sW == 1: NCHW views, crops).
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_instance_stats_strided(const T* __restrict__ x, int N, int C, long long sN, long long sC, long long sH, long long sW,
+                         Window win, float eps, float* __restrict__ mean, float* __restrict__ sd) {
+    const long long inst = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (inst >= (long long)N * C) return;
+    const int n = (int)(inst / C), c = (int)(inst - (long long)n * C);
+    const T* base = x + n * sN + c * sC;
+    const int cols = win.cols(), area = win.area(), lane = threadIdx.x & 31;
+    Moments acc = moments_zero();
+    int hh = lane / cols, ww = lane - hh * cols;
+    const int dh = 32 / cols, dw = 32 - dh * cols;
+    for (int i = lane; i < area; i += 32) {
+        fold1(acc, to_f(base[(win.h0 + hh) * sH + (win.w0 + ww) * sW]));
+        hh += dh; ww += dw;
+        if (ww >= cols) { ww -= cols; ++hh; }
+    }
+    acc = warp_merge(acc);
+    if (lane == 0) { mean[inst] = acc.mean; sd[inst] = std_from(acc, eps); }
+}
+// channels_last (sC == 1): a CTA takes one sample and 32 adjacent channels; lane = channel (the contiguous dimension),
+// the 8 warps split the window's pixels, partial moments merge through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(kBlock)
+k_instance_stats_cl(const T* __restrict__ x, int N, int C, long long sN, long long sH, long long sW, Window win, float eps,
+                    float* __restrict__ mean, float* __restrict__ sd) {
+    __shared__ Moments part[kWarpsPerBlock][32];
+    const int tiles = (C + 31) / 32;
+    const int n = blockIdx.x / tiles, c = (blockIdx.x - n * tiles) * 32 + (threadIdx.x & 31);
+    const int warp = threadIdx.x >> 5, cols = win.cols(), area = win.area();
+    Moments acc = moments_zero();
+    if (c < C) {
+        const T* base = x + n * sN + c;
+        for (int i = warp; i < area; i += kWarpsPerBlock) {
+            const int hh = i / cols, ww = i - hh * cols;
+            fold1(acc, to_f(base[(win.h0 + hh) * sH + (win.w0 + ww) * sW]));
+        }
+    }
+    part[warp][threadIdx.x & 31] = acc;
+    __syncthreads();
+    if (warp == 0 && c < C) {
+        Moments m = part[0][threadIdx.x];
+#pragma unroll
+        for (int w = 1; w < kWarpsPerBlock; ++w) m = merge(m, part[w][threadIdx.x]);
+        mean[(size_t)n * C + c] = m.mean;
+        sd[(size_t)n * C + c] = std_from(m, eps);
+    }
+}
+
 int check_dims(int N, int C, int H, int W) { return (N > 0 && C > 0 && H > 0 && W > 0) ? 0 : CNSN_E_BADARG; }
 int check_window(const Window& w, int H, int W) {
     return (w.h0 >= 0 && w.w0 >= 0 && w.h1 <= H && w.w1 <= W && w.h0 < w.h1 && w.w0 < w.w1) ? 0 : CNSN_E_BADARG;
@@ -86,6 +138,29 @@ extern "C" int cnsn_instance_stats(const void* x, int dtype, int N, int C, int H
     if (check_window(win, H, W)) return CNSN_E_BADARG;
     if (reinterpret_cast<uintptr_t>(x) % esize(dtype)) return CNSN_E_ALIGN;
     return launch_instance_stats(x, dtype, (long long)N * C, H, W, win, eps, mean, sd, (cudaStream_t)stream);
+}
+
+extern "C" int cnsn_instance_stats_strided(const void* x, int dtype, int N, int C, int H, int W,
+                                           long long sN, long long sC, long long sH, long long sW,
+                                           int h0, int h1, int w0, int w1, float eps,
+                                           float* mean, float* sd, void* stream) {
+    if (!x || !mean || !sd || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    const Window win{h0, h1, w0, w1};
+    if (check_window(win, H, W)) return CNSN_E_BADARG;
+    if (sN < 0 || sC < 0 || sH < 0 || sW < 0) return CNSN_E_BADARG;
+    if (reinterpret_cast<uintptr_t>(x) % esize(dtype)) return CNSN_E_ALIGN;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (sC == (long long)H * W && sH == W && sW == 1 && sN == (long long)C * H * W)      // dense NCHW: the vectorised kernel
+        return launch_instance_stats(x, dtype, (long long)N * C, H, W, win, eps, mean, sd, s);
+    if (sC == 1 && C >= 8) {
+        const unsigned blocks = (unsigned)N * (unsigned)((C + 31) / 32);
+        CNSN_DISPATCH_DTYPE(dtype, T, k_instance_stats_cl<T><<<blocks, kBlock, 0, s>>>((const T*)x, N, C, sN, sH, sW, win, eps, mean, sd));
+    } else {
+        const long long inst = (long long)N * C;
+        const unsigned blocks = (unsigned)((inst + kWarpsPerBlock - 1) / kWarpsPerBlock);
+        CNSN_DISPATCH_DTYPE(dtype, T, k_instance_stats_strided<T><<<blocks, kBlock, 0, s>>>((const T*)x, N, C, sN, sC, sH, sW, win, eps, mean, sd));
+    }
+    return launch_status();
 }
 
 extern "C" int cnsn_instance_stats_bwd(const void* x, void* dx, int dtype, int N, int C, int H, int W,

@@ -19,7 +19,9 @@ class InstanceStats(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, window, eps):
-        x = _dense(x)
+        # strided views (crops, transposes, channels_last) are reduced where they lie: no dense copy in the forward
+        if not getattr(_lib.backend(), "strided_stats", True) or any(s < 0 for s in x.stride()):
+            x = _dense(x)
         mean, std = _lib.backend().instance_stats(x, window, eps)
         ctx.save_for_backward(x, mean, std)
         ctx.window = window
@@ -28,7 +30,7 @@ class InstanceStats(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmean, dstd):
         x, mean, std = ctx.saved_tensors
-        dx = _lib.backend().instance_stats_bwd(x, ctx.window, mean, std,
+        dx = _lib.backend().instance_stats_bwd(_dense(x), ctx.window, mean, std,
                                                dmean.contiguous().float(), dstd.contiguous().float())
         return dx, None, None
 

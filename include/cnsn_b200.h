@@ -77,6 +77,16 @@ int cnsn_instance_stats(const void* x, int dtype, int N, int C, int H, int W,
                         float* mean, float* std, void* stream);
 
 /*
+ * The same statistics of a STRIDED view (element strides sN, sC, sH, sW >= 0): sliced / transposed
+ * views, crops and channels_last tensors are reduced where they lie -- the reference copies them first
+ * (.contiguous(), models/cnsn.py:14,16).  Coalesced for W-contiguous views (sW == 1) and for channels_last (sC == 1).
+ */
+int cnsn_instance_stats_strided(const void* x, int dtype, int N, int C, int H, int W,
+                                long long sN, long long sC, long long sH, long long sW,
+                                int h0, int h1, int w0, int w1, float eps,
+                                float* mean, float* std, void* stream);
+
+/*
  * Backward of cnsn_instance_stats (autograd of models/cnsn.py:14-16):
  *   dx = dmean/M + (x - mean)/std * dstd/(M-1) inside the window, 0 outside.
  */

@@ -214,3 +214,39 @@ def test_async_error_state_is_clear_and_clearable():
     assert L.lib().cnsn_async_error(0) == 0
     L.async_error()                                   # no-op when nothing happened
     assert L.lib().cnsn_tune(b"no_such_knob", 1) != 0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("how", ["channels_last", "crop_view", "transposed", "channels_last_crop", "few_channels_last"])
+def test_strided_statistics_in_place(mod, how, dtype):
+    """calc_ins_mean_std (models/cnsn.py:8-17) on views the reference would copy first (.contiguous(), :14,:16): the
+    strided entry point cnsn_instance_stats_strided reduces them where they lie -- channels_last (lane = channel),
+    W-contiguous crops / slices, transposes -- and agrees with torch on the densified tensor, gradients included."""
+    import cnsn_b200._lib as L
+    g = torch.Generator().manual_seed(0)
+    base = (torch.randn(5, 40, 13, 11, generator=g) * 1.4 + 0.3).to(dtype).to(DEV)
+    if how == "channels_last":
+        x = base.contiguous(memory_format=torch.channels_last)
+    elif how == "crop_view":
+        x = base[:, :, 2:11, 1:9]                        # what cn_op_2ins_space_chan crops (:66, :77)
+    elif how == "transposed":
+        x = base.transpose(2, 3)
+    elif how == "channels_last_crop":
+        x = base.contiguous(memory_format=torch.channels_last)[1:, 3:37, 1:12, 2:10]
+    else:
+        x = base[:, :5].contiguous(memory_format=torch.channels_last)
+    assert not x.is_contiguous()
+    n0 = L.launch_count()
+    xt = x.detach().requires_grad_(True)
+    mean, std = mod.calc_ins_mean_std(xt, eps=1e-5)
+    assert L.launch_count() - n0 == 1                    # one statistics kernel, no copy kernel of ours in front
+    xr = x.detach().float().contiguous().requires_grad_(True)
+    N, C = xr.shape[:2]
+    rm = xr.view(N, C, -1).mean(2).view(N, C, 1, 1)
+    rs = (xr.view(N, C, -1).var(2) + 1e-5).sqrt().view(N, C, 1, 1)
+    tol = dict(atol=2e-5, rtol=1e-5) if dtype == torch.float32 else dict(atol=2e-2, rtol=1e-2)
+    assert mean.shape == (N, C, 1, 1) and torch.allclose(mean.float(), rm, **tol) and torch.allclose(std.float(), rs, **tol)
+    gm, gs = torch.randn(N, C, 1, 1, device=DEV), torch.randn(N, C, 1, 1, device=DEV)
+    (mean.float() * gm + std.float() * gs).sum().backward()
+    (rm * gm + rs * gs).sum().backward()
+    assert torch.allclose(xt.grad.float(), xr.grad, **tol)
