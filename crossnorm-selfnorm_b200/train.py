@@ -57,8 +57,11 @@ class GraphedStep:
     without its per-step host work; running statistics stay per replica (the reference's DataParallel behaviour).
     The per-step ``float(loss)`` host read of the reference stays."""
 
-    def __init__(self, net, images, targets, world=1, capture=True):
+    def __init__(self, net, images, targets, world=1, capture=True, loss_fn=None):
+        """loss_fn(net, images, targets, aug) -> scalar loss; default: cross-entropy of ``net(images, aug=aug)``
+        (cifar.py:132-133).  Everything loss_fn launches is captured, so it must not read the host RNG or sync."""
         self.net, self.world = net, world
+        self.loss_fn = loss_fn or (lambda n, x, y, aug: F.cross_entropy(n(x, aug=aug), y))
         self.params = [p for p in net.parameters() if p.requires_grad]
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=self.params[0].dtype, device=images.device)
         off = 0
@@ -72,8 +75,7 @@ class GraphedStep:
 
     def _forward_backward(self, aug):
         self.flat.zero_()
-        logits = self.net(self.x, aug=aug)
-        loss = F.cross_entropy(logits, self.y)
+        loss = self.loss_fn(self.net, self.x, self.y, aug)
         loss.backward()                                   # accumulates into the views of the (zeroed) flat buffer
         return loss
 
@@ -97,16 +99,7 @@ class GraphedStep:
                 b.copy_(v)
         torch.cuda.synchronize()
 
-    def step(self, images, targets, opt, sched, cn_prob):
-        aug = bool(np.random.rand(1) < cn_prob)           # cifar.py:127
-        if images is not self.x:
-            self.x.copy_(images, non_blocking=True)
-            self.y.copy_(targets, non_blocking=True)
-        if aug or self.graph is None:
-            loss = self._forward_backward(aug)
-        else:
-            self.graph.replay()
-            loss = self.loss
+    def _finish(self, loss, opt, sched):
         if self.world > 1:
             import torch.distributed as dist
             dist.all_reduce(self.flat)                    # sum, then the mean DistributedDataParallel would deliver
@@ -115,6 +108,38 @@ class GraphedStep:
         if sched is not None:
             sched.step()
         return float(loss.detach())
+
+    def _load(self, images, targets):
+        if images is not self.x:
+            self.x.copy_(images, non_blocking=True)
+        if targets is not self.y:
+            self.y.copy_(targets, non_blocking=True)
+
+    def step(self, images, targets, opt, sched, cn_prob):
+        """``train_cn`` (cifar.py:117-145): the coin activates CrossNorm sites INSIDE the network -> eager step;
+        otherwise the captured step is replayed."""
+        aug = bool(np.random.rand(1) < cn_prob)           # cifar.py:127
+        self._load(images, targets)
+        if aug or self.graph is None:
+            loss = self._forward_backward(aug)
+        else:
+            self.graph.replay()
+            loss = self.loss
+        return self._finish(loss, opt, sched)
+
+    def step_image_cn(self, images, targets, opt, sched, cn_prob, ops, beta=1, crop="neither"):
+        """``train_cn_image`` / ``train_cn_image_consist`` (imagenet.py:205-230, :348-385): the coin sends the BATCH through
+        image-space CrossNorm before the network (eager: fresh host draws), the network itself never fires CrossNorm
+        (``aug=False``) -> EVERY step replays the captured forward + loss + backward."""
+        if np.random.rand(1) < cn_prob:                   # imagenet.py:213-215
+            images = ops.cn_op_2ins_space_chan(images, beta=beta, crop=crop)
+        self._load(images, targets)
+        if self.graph is None:
+            loss = self._forward_backward(False)
+        else:
+            self.graph.replay()
+            loss = self.loss
+        return self._finish(loss, opt, sched)
 
 
 def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False, graph=None):
@@ -217,9 +242,20 @@ def resnet50_step(net, images, targets, opt, cn_prob, ops, beta=1, crop="neither
     return float(loss.detach())
 
 
-def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5, fuse_post=True, ops=None):
+def _broadcast_model(net, world):
+    if world > 1:
+        import torch.distributed as dist
+        with torch.no_grad():
+            for t in list(net.parameters()) + list(net.buffers()):
+                dist.broadcast(t, 0)
+
+
+def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5, fuse_post=True, ops=None, graph=True):
     """images/s of ResNet-50 + SelfNorm ('post') training with image-space CrossNorm on synthetic 224x224 data
-    (BASELINE config 4: batch 256 per GPU, SGD lr 0.1 momentum 0.9 wd 1e-4; imagenet-scripts/run-cnsn.sh)."""
+    (BASELINE config 4: batch 256 per GPU, SGD lr 0.1 momentum 0.9 wd 1e-4; imagenet-scripts/run-cnsn.sh).
+    graph: GraphedStep.step_image_cn -- the network's forward + loss + backward replayed from a CUDA graph on every step
+    (CrossNorm acts on the images, before the network), one flat-buffer gradient all-reduce; else the eager step under
+    DistributedDataParallel."""
     import torch.distributed as dist
     from . import _lib
     from .hosts.resnet import resnet50
@@ -230,14 +266,22 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
     np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
     net = resnet50(fuse_post=fuse_post, ops=ops).to(dev).train()
     model = net
-    if world > 1:
+    _broadcast_model(net, world)
+    if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
     opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(batch, 3, 224, 224, device=dev)
     y = torch.randint(0, 1000, (batch,), device=dev)
     launches0 = _lib.launch_count()
+    gs = GraphedStep(net, x, y, world, loss_fn=lambda n, xx, yy, aug: F.cross_entropy(n(xx, aug=False), yy)) if graph else None
+
+    def one_step():
+        if gs is not None:
+            return gs.step_image_cn(x, y, opt, None, cn_prob, ops)
+        return resnet50_step(model, x, y, opt, cn_prob, ops)
+
     for _ in range(warmup):
-        resnet50_step(model, x, y, opt, cn_prob, ops)
+        one_step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -245,7 +289,7 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
     t0.record()
     loss = 0.0
     for _ in range(steps):
-        loss = resnet50_step(model, x, y, opt, cn_prob, ops)
+        loss = one_step()
     t1.record()
     if world > 1:
         dist.barrier()
@@ -261,6 +305,8 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
             "config": "resnet50 cnsn_type=sn pos=post, image-space CrossNorm crop=neither beta=1 cn_prob=%g, SGD lr 0.1 "
                       "momentum 0.9 wd 1e-4, synthetic 224x224, fuse_post=%s" % (cn_prob, bool(fuse_post)),
             "final_loss": loss, "params": sum(p.numel() for p in net.parameters()),
+            "graph": "CUDA graph for the network's forward + loss + backward on every step (image-space CrossNorm eager, in "
+                     "front); one flat-buffer gradient all-reduce" if gs is not None and gs.graph is not None else "eager",
             "cnsn_kernel_launches": _lib.launch_count() - launches0}
 
 
@@ -280,9 +326,9 @@ def resnet50_jsd_step(net, images_all, targets, opt, cn_prob, ops, jsd, beta=1, 
     return float(loss.detach())
 
 
-def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0.5, fuse_post=True):
+def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0.5, fuse_post=True, graph=True):
     """images/s (clean images: the step processes 3x as many views) of ResNet-50 + SelfNorm with the 3-view JSD
-    consistency step, bf16 autocast (BASELINE config 5: 3 x 256 = 768 views per GPU)."""
+    consistency step, bf16 autocast (BASELINE config 5: 3 x 256 = 768 views per GPU).  graph: as bench_resnet50."""
     import torch.distributed as dist
     from . import _lib, cnsn as ops
     from .hosts.resnet import resnet50
@@ -292,14 +338,29 @@ def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0
     np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
     net = resnet50(fuse_post=fuse_post).to(dev).train()
     model = net
-    if world > 1:
+    _broadcast_model(net, world)
+    if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
     opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(3 * batch, 3, 224, 224, device=dev)
     y = torch.randint(0, 1000, (batch,), device=dev)
     launches0 = _lib.launch_count()
+
+    def jsd_loss(n, xx, yy, aug):              # imagenet.py:352-380: one forward of the 3B batch, CE on the clean third + 12 x JSD
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            logits_all = n(xx, aug=False)
+        lc, l1, l2 = torch.split(logits_all, yy.size(0))
+        return F.cross_entropy(lc, yy) + 12 * jsd_consistency(lc, l1, l2)
+
+    gs = GraphedStep(net, x, y, world, loss_fn=jsd_loss) if graph else None
+
+    def one_step():
+        if gs is not None:
+            return gs.step_image_cn(x, y, opt, None, cn_prob, ops)
+        return resnet50_jsd_step(model, x, y, opt, cn_prob, ops, jsd_consistency)
+
     for _ in range(warmup):
-        resnet50_jsd_step(model, x, y, opt, cn_prob, ops, jsd_consistency)
+        one_step()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -307,7 +368,7 @@ def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0
     t0.record()
     loss = 0.0
     for _ in range(steps):
-        loss = resnet50_jsd_step(model, x, y, opt, cn_prob, ops, jsd_consistency)
+        loss = one_step()
     t1.record()
     if world > 1:
         dist.barrier()

@@ -51,3 +51,40 @@ def test_graph_replay_is_the_eager_step():
         else:
             assert torch.equal(se[k], sg[k]), k
     assert worst <= 2e-3, worst
+
+
+def _run_r50(capture, steps=3):
+    """A small ResNet ([1,1,1,1] bottlenecks) through GraphedStep.step_image_cn: image-space CrossNorm eager in front,
+    the network replayed."""
+    import cnsn_b200.cnsn as ops
+    from cnsn_b200.hosts import ResNet
+    from cnsn_b200.train import GraphedStep
+    torch.manual_seed(0)
+    np.random.seed(0)
+    net = ResNet([1, 1, 1, 1], num_classes=10, active_num=1, pos="post", beta=1, crop="neither", cnsn_type="sn", fuse_post=True).to(DEV).train()
+    opt = torch.optim.SGD(net.parameters(), 0.05, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(16, 3, 64, 64, generator=g).to(DEV)
+    y = torch.randint(0, 10, (16,), generator=g).to(DEV)
+    gs = GraphedStep(net, x, y, 1, capture=capture, loss_fn=lambda n, xx, yy, aug: torch.nn.functional.cross_entropy(n(xx, aug=False), yy))
+    torch.manual_seed(2)
+    np.random.seed(3)
+    losses = [gs.step_image_cn(x, y, opt, None, 0.5, ops, crop="both") for _ in range(steps)]
+    return losses, {k: v.clone() for k, v in net.state_dict().items()}
+
+
+def test_graphed_image_crossnorm_step_is_the_eager_step():
+    saved = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
+    try:
+        le, se = _run_r50(False)
+        lg, sg = _run_r50(True)
+    finally:
+        torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = saved
+    for a, b in zip(le, lg):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(a)), (le, lg)
+    for k in se:
+        if se[k].dtype.is_floating_point:
+            assert float((se[k] - sg[k]).abs().max() / se[k].abs().max().clamp_min(1e-12)) <= 2e-3, k
+        else:
+            assert torch.equal(se[k], sg[k]), k
