@@ -69,9 +69,17 @@ class GraphedStep:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
             off += p.numel()
         self.x, self.y = images.clone(), targets.clone()
-        self.graph = None
+        self.graph, self.capture_error = None, None
         if capture and images.is_cuda:
-            self._capture()
+            try:                                          # warm-up on a side stream is intended: no warning per parameter
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
+            try:
+                self._capture()
+            except Exception as e:      # noqa: BLE001 -- a step that cannot be captured still trains, eagerly
+                self.graph, self.capture_error = None, repr(e)[:300]
+                torch.cuda.synchronize()
 
     def _forward_backward(self, aug):
         self.flat.zero_()
