@@ -625,6 +625,7 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
     uint64_t* bar = reinterpret_cast<uint64_t*>(dsm);
     const unsigned nI = (unsigned)a.nI;
     const unsigned g = t / nI, j = t - g * nI;
+    CNSN_FTRACE(0);                                          // 0 ticket taken
     const int N = a.N, C = a.C, M = a.M, kk = a.kk, I = P / kk;
     const unsigned pbytes = (unsigned)M * (unsigned)sizeof(T), sp = (unsigned)kk * pbytes;
     const int first = (int)j * I, nlive = min(I, N - first);
@@ -673,8 +674,20 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
         p_b = a.beta[c];
     }
     mbar_wait(bar, par, a.err);
+    CNSN_FTRACE(1);                                          // 1 planes landed
     const int vps = (int)(sp / 16u), nvec = nlive * vps;     // 128-bit vectors per super-plane / in the item
+    // Flat walk over the item's 128-bit vectors, division-free: thread tid takes vectors tid, tid + TH, ...; (sample qv,
+    // vector w within its super-plane) advance incrementally, the plane of an element comes from a multiply-high
+    // (integer divisions by runtime values cost ~30 instructions each and made this walk the longest phase of an item:
+    // 3.8 us of 12.8, gpurun_out/r3d_trace_grp_fwd.log).
+    const int vq0 = (int)threadIdx.x / vps, vw0 = (int)threadIdx.x - vq0 * vps;       // one division per thread and item
+    const int vdq = TH / vps, vdw = TH - vdq * vps;
+    const unsigned magicM = 0xffffffffu / (unsigned)M + 1u;  // floor(e / M) = umulhi(e, magicM) for e * M < 2^32
+    const size_t srow = (size_t)C * M;                       // elements between consecutive samples
+    const size_t gbase = ((size_t)first * C + (size_t)g * kk) * M;
     if (ADD) {                                               // z = x + res over the item, in place and written out
+        T* zb = static_cast<T*>(a.zout) + gbase;
+        int qv = vq0, w = vw0;
         for (int vi = threadIdx.x; vi < nvec; vi += TH) {
             float vx[V], vr[V];
             unpack<T>(lds128(sbase + 16u * vi), vx);
@@ -683,9 +696,9 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
             for (int e = 0; e < V; ++e) vx[e] += vr[e];
             const uint4 z = pack<T>(vx);
             sts128(sbase + 16u * vi, z);
-            const int qv = vi / vps, w = vi - qv * vps;
-            uint4* pz = reinterpret_cast<uint4*>(static_cast<T*>(a.zout) + ((size_t)(first + qv) * C + (size_t)g * kk) * M) + w;
-            stg_stream(pz, z);
+            stg_stream(reinterpret_cast<uint4*>(zb + (size_t)qv * srow) + w, z);
+            qv += vdq; w += vdw;
+            if (w >= vps) { w -= vps; ++qv; }
         }
         __syncthreads();
     }
@@ -712,6 +725,7 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
         if (live && r == 0) { a.mu[nc] = own_x; a.sd[nc] = own_y; }
     }
     if (live && r == 0 && (BWD || batch_coupled)) ll_publish(a.pub + (size_t)c * N + n, own_x, own_y);
+    CNSN_FTRACE(2);                                          // 2 reduced + published
     // ---- channel constants ------------------------------------------------------------------------
     if (BWD || batch_coupled) {                              // channel k of the group: folded by ticket nI-1-(k mod nI)
         for (int k = (int)(nI - 1u - j); k < kk; k += (int)nI) {
@@ -723,6 +737,7 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
             fold_publish<BWD, TH>(a, ch, a.chan + 4u * ch, w0, w1, ga, pb2, rm, rv, s_f);
         }
     }
+    CNSN_FTRACE(3);                                          // 3 this item's folds (if any) done
     float2 cm;
     if (batch_coupled) {
         cm = poll_word(a.chan + 4u * c, a.poll_ns, a.err);          // 4 lanes per address; the folder's own words are there
@@ -733,6 +748,7 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
         cm = make_float2(a.run_mean[c], rstd);
         if (folder && q == 0 && r == 0) a.r[c] = rstd;
     }
+    CNSN_FTRACE(4);                                          // 4 (thread 0's) channel constants known
     if (live && r == 0) {
         if (BWD) {
             const float ds = p_b * (own_x * p_ga - cm.x - own_y * cm.y);
@@ -747,28 +763,33 @@ __device__ __forceinline__ void sn_grp_item(const FArgs& a, const unsigned t, co
     }
     __syncthreads();
     // ---- apply: the item's super-planes as flat 128-bit vectors ------------------------------------------
-    for (int vi = threadIdx.x; vi < nvec; vi += TH) {
-        const int qv = vi / vps, w = vi - qv * vps;
-        const int e0 = w * V, cl0 = e0 / M, bound = (cl0 + 1) * M;
-        const float4 k0 = s_coef[qv * kk + cl0];
-        const float4 k1 = (cl0 + 1 < kk) ? s_coef[qv * kk + cl0 + 1] : k0;     // a vector spans at most two planes (M >= V)
-        float vx[V], vd[V], vo[V];
-        unpack<T>(lds128(sbase + 16u * vi), vx);
-        if (BWD) unpack<T>(lds128(sbase + soff2 + 16u * vi), vd);
+    {
+        T* ob = static_cast<T*>(a.out) + gbase;
+        int qv = vq0, w = vw0;
+        for (int vi = threadIdx.x; vi < nvec; vi += TH) {
+            const int e0 = w * V, cl0 = (int)__umulhi((unsigned)e0, magicM), bound = (cl0 + 1) * M;
+            const float4 k0 = s_coef[qv * kk + cl0];
+            const float4 k1 = (cl0 + 1 < kk) ? s_coef[qv * kk + cl0 + 1] : k0;     // a vector spans at most two planes (M >= V)
+            float vx[V], vd[V], vo[V];
+            unpack<T>(lds128(sbase + 16u * vi), vx);
+            if (BWD) unpack<T>(lds128(sbase + soff2 + 16u * vi), vd);
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-            const float4 k = (e0 + e < bound) ? k0 : k1;
-            if (BWD) {
-                const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
-                vo[e] = fmaf(k.x, d, fmaf(k.y, vx[e], k.z));
-            } else {
-                const float y = fmaf(k.y, vx[e], 0.f);
-                vo[e] = relu ? fmaxf(y, 0.f) : y;
+            for (int e = 0; e < V; ++e) {
+                const float4 k = (e0 + e < bound) ? k0 : k1;
+                if (BWD) {
+                    const float d = (relu && !(vx[e] > 0.f)) ? 0.f : vd[e];
+                    vo[e] = fmaf(k.x, d, fmaf(k.y, vx[e], k.z));
+                } else {
+                    const float y = fmaf(k.y, vx[e], 0.f);
+                    vo[e] = relu ? fmaxf(y, 0.f) : y;
+                }
             }
+            stg_stream(reinterpret_cast<uint4*>(ob + (size_t)qv * srow) + w, pack<T>(vo));
+            qv += vdq; w += vdw;
+            if (w >= vps) { w -= vps; ++qv; }
         }
-        uint4* po = reinterpret_cast<uint4*>(static_cast<T*>(a.out) + ((size_t)(first + qv) * C + (size_t)g * kk) * M) + w;
-        stg_stream(po, pack<T>(vo));
     }
+    CNSN_FTRACE(5);                                          // 5 applied
 }
 
 template <typename T, bool BWD, bool ADD, int TPI>
@@ -841,6 +862,31 @@ static int launch(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
     return launch_status();
 }
 
+
+// Debug only (cnsn_tune("trace", 1) + $CNSN_FLOW_TRACE = output path): per-item globaltimer stamps, written synchronously.
+static const char* trace_begin(FArgs& a, unsigned long long items, cudaStream_t stream) {
+    a.trace = nullptr;
+    const char* path = knobs().trace ? getenv("CNSN_FLOW_TRACE") : nullptr;
+    const size_t bytes = (size_t)items * 8 * sizeof(unsigned long long);
+    if (path && cudaMalloc(&a.trace, bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, bytes, stream);
+    return path;
+}
+static void trace_end(FArgs& a, const char* path, unsigned long long items, int per_sm, bool bwd, cudaStream_t stream) {
+    if (!a.trace) return;
+    const size_t bytes = (size_t)items * 8 * sizeof(unsigned long long);
+    cudaStreamSynchronize(stream);
+    unsigned long long* h = (unsigned long long*)malloc(bytes);
+    cudaMemcpy(h, a.trace, bytes, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(path, "wb")) {
+        const int hdr[4] = {(int)items, a.nI, per_sm, bwd ? 1 : 0};
+        fwrite(hdr, sizeof(int), 4, f);
+        fwrite(h, 1, bytes, f);
+        fclose(f);
+    }
+    free(h);
+    cudaFree(a.trace);
+    a.trace = nullptr;
+}
 
 constexpr int kResT = 128;              // threads per CTA of the shared-memory-resident kernel
 
@@ -933,10 +979,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
-    const char* trace_path = kn.trace ? getenv("CNSN_FLOW_TRACE") : nullptr;   // debug: per-item timestamps (synchronous)
-    const size_t trace_bytes = (size_t)items * 8 * sizeof(unsigned long long);
-    a.trace = nullptr;
-    if (trace_path && cudaMalloc(&a.trace, trace_bytes) == cudaSuccess) cudaMemsetAsync(a.trace, 0, trace_bytes, stream);
+    const char* trace_path = trace_begin(a, items, stream);
 #define CNSN_RES_CASE(TPI_)                                                                              \
     case TPI_: {                                                                                         \
         auto fn = add ? k_sn_res<T, false, !BWD, false, TPI_, kResT>                                     \
@@ -956,19 +999,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
         default: return -100;
     });
 #undef CNSN_RES_CASE
-    if (a.trace) {
-        cudaStreamSynchronize(stream);
-        unsigned long long* h = (unsigned long long*)malloc(trace_bytes);
-        cudaMemcpy(h, a.trace, trace_bytes, cudaMemcpyDeviceToHost);
-        if (FILE* f = fopen(trace_path, "wb")) {
-            const int hdr[4] = {(int)items, a.nI, per_sm, BWD ? 1 : 0};
-            fwrite(hdr, sizeof(int), 4, f);
-            fwrite(h, 1, trace_bytes, f);
-            fclose(f);
-        }
-        free(h);
-        cudaFree(a.trace);
-    }
+    trace_end(a, trace_path, items, per_sm, BWD, stream);
     if (kn.debug)
         fprintf(stderr, "[cnsn flow/res] %s tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d dyg=%d\n", BWD ? "bwd" : "fwd",
                 tpi, inst, a.nI, items, dsmem, per_sm, (int)dyg);
@@ -1007,7 +1038,8 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
     a.pub = reinterpret_cast<float2*>(scratch);
     a.chan = a.pub + (size_t)N * C;
     a.ticket = reinterpret_cast<unsigned*>(a.chan + 4 * (size_t)C);
-    a.done = nullptr; a.ready = nullptr; a.trace = nullptr;
+    a.done = nullptr; a.ready = nullptr;
+    const char* trace_path = trace_begin(a, items, stream);
     const size_t fill_bytes = ((size_t)N * C + 4 * (size_t)C + 1) * sizeof(float2);
     cudaError_t e = cudaSuccess;
     int per_sm = 0;
@@ -1024,6 +1056,7 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kGrpT, dsmem, stream);
         if (e != cudaSuccess) return (int)e;
     });
+    trace_end(a, trace_path, items, per_sm, BWD, stream);
     if (kn.debug)
         fprintf(stderr, "[cnsn flow/grp] %s kk=%d tpi=%d I=%d nI=%d items=%llu smem=%zu ctas/sm=%d add=%d\n", BWD ? "bwd" : "fwd", kk,
                 tpi, I, a.nI, items, dsmem, per_sm, (int)add);

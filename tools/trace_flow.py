@@ -19,7 +19,8 @@ shape = tuple(int(v) for v in (sys.argv[1] if len(sys.argv) > 1 else "256,256,56
 bwd = len(sys.argv) > 2 and sys.argv[2] == "bwd"
 out = sys.argv[3] if len(sys.argv) > 3 else os.path.join(ROOT, "gpurun_out", "flow_trace.bin")
 os.makedirs(os.path.dirname(out) or ".", exist_ok=True)
-L.tune(flow_mode="res", flow_bwd="res")
+if (shape[2] * shape[3] * 4) % 16 == 0:
+    L.tune(flow_mode="res", flow_bwd="res", tm=0)      # the shared-memory-resident kernel; odd planes: the channel-group kernel
 L.tune_from_env()
 x = torch.randn(shape, device="cuda:0").requires_grad_(True)
 dy = torch.randn(shape, device="cuda:0")
@@ -56,7 +57,7 @@ first = tc[:, :, 0].min(axis=1)
 lastd = tc[:, :, 0].max(axis=1)
 landed = tc[:, :, 1].max(axis=1)
 published = tc[:, :, 2].max(axis=1)
-words = tc[:, nI - 1, 3]                  # the folder is the channel's last item
+words = tc[:, :, 3].max(axis=1)           # folds done (resident kernel: the folder is the channel's last item)
 known = tc[:, nI - 1, 4]
 seen = tc[:, :, 4].max(axis=1)
 done = tc[:, :, 5].max(axis=1)
