@@ -46,12 +46,14 @@ def test_alternating_plane_sizes_above_48k_share_one_kernel(mod):
 
 
 def test_concurrent_streams_and_a_busy_gpu(mod):
-    """Several dataflow kernels in flight at once -- two streams running SelfNorm / CrossNorm forward + backward while a
-    third keeps the SMs busy with matmuls: the cooperative persistent launch guarantees each kernel's CTAs are
+    """Several dataflow kernels in flight at once -- three streams running SelfNorm (shared-memory-resident and the
+    tensor-memory pipeline, whose CTAs each want all 512 TMEM columns of an SM) / CrossNorm forward + backward while a
+    fourth keeps the SMs -- and their tensor memory: cuBLAS runs tcgen05 GEMMs -- busy with matmuls: the cooperative persistent launch guarantees each kernel's CTAs are
     co-resident whatever else runs, so nothing stalls or times out and the results are bit-identical to the
     single-stream results (the kernels are deterministic)."""
     import cnsn_b200._lib as L
-    shapes = [(64, 32, 32, 32), (48, 16, 56, 56)]
+    L.tune(tm_items=0)                                 # the 56x56 shapes below then take the shared + tensor memory pipeline
+    shapes = [(64, 32, 32, 32), (48, 16, 56, 56), (40, 12, 56, 56)]
     work = []
     for i, shape in enumerate(shapes):
         g = torch.Generator(device=DEV).manual_seed(i)
