@@ -41,35 +41,10 @@
 
 #include <algorithm>
 
-#include "selfnorm_fold.cuh"
+#include "tmem_common.cuh"
 
 namespace cnsn {
 namespace flow {
-
-constexpr int kTmT = 128;               // threads per group: one TMEM lane each
-constexpr int kTmGroups = 4;            // groups per CTA
-constexpr int kTmCta = kTmT * kTmGroups;
-constexpr int kTmCols = 128;            // TMEM columns per group (4 x 128 = all 512 of the SM)
-
-__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint4& v) {
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
-                 :: "r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ uint4 tmem_ld4(uint32_t taddr) {
-    uint4 v;
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(taddr) : "memory");
-    return v;
-}
-// tcgen05.ld is asynchronous: the destination registers are valid after the wait.  The registers are in/out operands of
-// the wait so that the compiler cannot schedule their uses above it.
-template <int K>
-__device__ __forceinline__ void tmem_wait_ld(uint4 (&v)[K]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int k = 0; k < K; ++k) asm volatile("" : "+r"(v[k].x), "+r"(v[k].y), "+r"(v[k].z), "+r"(v[k].w));
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 template <typename T, bool BWD, int P, int SL>
 __global__ void __launch_bounds__(kTmCta, 1) k_sn_tm(const FArgs a) {
@@ -95,14 +70,7 @@ __global__ void __launch_bounds__(kTmCta, 1) k_sn_tm(const FArgs a) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 32) {                                  // one warp allocates the SM's tensor memory (may block: fine, see above)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&s_tmem)), "r"(kTmCols * kTmGroups) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tbase = s_tmem;
+    const uint32_t tbase = tmem_alloc_all(&s_tmem);
     // lane field (bits 31:16) = 32 * (warp % 4): the warp's quadrant; column field: this group's 128 columns
     const uint32_t trow = tbase + ((uint32_t)(warp & 3) << 21) + (uint32_t)(grp * kTmCols);
 
@@ -340,9 +308,7 @@ __global__ void __launch_bounds__(kTmCta, 1) k_sn_tm(const FArgs a) {
         t_new = take();                                      // (its barriers also order the shared-memory reads of every thread)
         if (t_new < a.items) issue(t_new);
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();                                         // every group is done with tensor memory
-    if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tbase), "r"(kTmCols * kTmGroups) : "memory");
+    tmem_free_all(tbase);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -33,22 +33,13 @@
 // is_two): cnsn_site_supported() says so and the host runs the two operators one after the other.
 #include <stdio.h>
 
-#include "selfnorm_fold.cuh"
+#include "site_args.cuh"
 
 namespace cnsn {
 namespace flow {
 
 constexpr int kSiteT = 128;             // threads per CTA
 
-struct SiteArgs {
-    FArgs sn;               // SelfNorm half: x / dy / out, N, C, M, nI, parameters, save block, sn words (pub), chan, ticket
-    int H, W;
-    Window cw, sw;          // content / style window
-    float lam, cn_eps;
-    const int* perm;        // [N] style source of every sample
-    float* mu_c; float* sd_c; float* mu_s; float* sd_s;     // CrossNorm save block
-    float2* pub_cn;         // CrossNorm words, pre-filled with the sentinel: forward [C][N], backward [C][N][3]
-};
 
 // One 16-byte vector of the CrossNorm output: ca*x + cb inside the content window, x outside, rounded to T.
 template <typename T>
@@ -483,6 +474,8 @@ extern "C" int cnsn_site_fwd(const void* x, void* y, int dtype, int N, int C, in
     a.mu = save + L.mu; a.sd = save + L.sd; a.gate = save + L.g; a.shat = save + L.shat; a.r = save + L.r;
     s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = cn_eps; s.perm = perm;
     s.mu_c = save + L.mu_c; s.sd_c = save + L.sd_c; s.mu_s = save + L.mu_s; s.sd_s = save + L.sd_s;
+    const int trc = flow::site_tmem_fwd(s, dtype, save + L.scratch, (cudaStream_t)stream);     // whole-plane windows, 6-16 KB planes
+    if (trc != -100) return trc;
     const int frc = flow::launch_site<false>(s, dtype, save + L.scratch, (cudaStream_t)stream, false);
     return frc == -100 ? CNSN_E_UNSUPPORTED : frc;
 }
@@ -507,6 +500,8 @@ extern "C" int cnsn_site_bwd(const void* x, const void* dy, void* dx, int dtype,
     a.dw = dg->dw; a.dgamma = dg->dgamma; a.dbeta = dg->dbeta;
     s.H = H; s.W = W; s.cw = cw; s.sw = sw; s.lam = lam; s.cn_eps = cn_eps; s.perm = perm;
     s.mu_c = sv + L.mu_c; s.sd_c = sv + L.sd_c; s.mu_s = sv + L.mu_s; s.sd_s = sv + L.sd_s;
+    const int trc = flow::site_tmem_bwd(s, dtype, workspace, (cudaStream_t)stream);
+    if (trc != -100) return trc;
     const int frc = flow::launch_site<true>(s, dtype, workspace, (cudaStream_t)stream, false);
     return frc == -100 ? CNSN_E_UNSUPPORTED : frc;
 }

@@ -242,3 +242,71 @@ def test_site_lam_blend_vs_oracle(mod, shape, crop, relu):
     for a, k in zip(gg, ("g_w", "g_gamma", "g_beta")):
         assert H.relmax(a.double().cpu().numpy(), gr[k]) <= H.PARAM_RTOL, k
     close32(bn.running_var.double().cpu().numpy(), nb["g_rv"], "running_var")
+
+
+# ------------------------------------------------------------------ shared + tensor memory pipeline (site_tmem.cu)
+TM_SITE_SHAPES = [((19, 3, 40, 40), torch.float32), ((16, 2, 48, 48), torch.float32), ((13, 3, 52, 52), torch.float32),
+                  ((11, 4, 56, 56), torch.float32), ((9, 2, 64, 64), torch.float32), ((33, 3, 56, 56), torch.bfloat16),
+                  ((16, 2, 80, 80), torch.float16)]
+
+
+@pytest.mark.parametrize("shape,dtype", TM_SITE_SHAPES)
+@pytest.mark.parametrize("relu,lam", [(False, None), (True, None), (False, 0.3)])
+def test_site_tensor_memory_pipeline_vs_oracle(mod, shape, dtype, relu, lam):
+    """Whole-plane windows (crop = 'neither') through the shared + tensor memory pipeline, forced onto small tensors
+    (tm_items = 0; tm = 3 also admits the 16-bit types) in every geometry it instantiates: 4..8 vectors per thread,
+    ragged last items, persistent grids smaller than the item count (two CTAs: every group runs many two-stage
+    iterations and instances regularly find their style source in the same item, the same group or the other CTA),
+    the fused ReLU and the lam blend -- against the numpy oracle's composition, and the launch count says one kernel
+    per direction."""
+    import functools
+    import cnsn_b200
+    import cnsn_b200._lib as L
+    x = O.varied_input(shape, seed=71, dtype=np.float32)
+    dy = np.random.RandomState(72).standard_normal(shape).astype(np.float32)
+    if dtype != torch.float32:
+        x = torch.from_numpy(x).to(dtype).float().numpy()
+        dy = torch.from_numpy(dy).to(dtype).float().numpy()
+    params, bufs = H.random_sn_params(shape[1], seed=73)
+    C = shape[1]
+    for knobs in ({"tm_items": 0, "tm": 3}, {"tm_items": 0, "tm": 3, "grid_cap": 2}, {"tm": 0}):
+        with L.tuned(**knobs):
+            sn = H.make_selfnorm(mod, C, params, bufs, DEV)
+            blk = mod.CNSN(mod.CrossNorm(crop="neither", beta=1), sn).train()
+            if lam is not None:
+                blk.crossnorm.cn_op = functools.partial(mod.cn_op_2ins_space_chan, crop="neither", beta=1, lam=lam)
+            blk.crossnorm.active = True
+            torch.manual_seed(81)
+            np.random.seed(82)
+            xt = torch.from_numpy(x).to(device=DEV, dtype=dtype).requires_grad_(True)
+            n0 = cnsn_b200.launch_count()
+            y = blk(xt, None, True) if relu else blk(xt)
+            y.backward(torch.from_numpy(dy).to(device=DEV, dtype=dtype))
+            torch.cuda.synchronize()
+            assert cnsn_b200.launch_count() - n0 == 2
+        r = {"y": y.detach().double().cpu().numpy(), "dx": xt.grad.double().cpu().numpy(),
+             "dg_w": sn.g_fc.weight.grad.view(C, 2).double().cpu().numpy(), "dg_gamma": sn.g_bn.weight.grad.double().cpu().numpy(),
+             "dg_beta": sn.g_bn.bias.grad.double().cpu().numpy(), "rm": sn.g_bn.running_mean.double().cpu().numpy(),
+             "rv": sn.g_bn.running_var.double().cpu().numpy()}
+        torch.manual_seed(81)
+        np.random.seed(82)
+        plan = O.draw_plan(shape, crop="neither", beta=1)
+        z = O.crossnorm_fwd(x, plan, lam)
+        yo, nb = O.selfnorm_fwd(z, params, bufs, True)
+        mask = (r["y"] > 0) if relu else None
+        d = np.where(mask, dy, 0.0) if relu else dy
+        dz, gr = O.selfnorm_bwd(z, d, params, bufs, True)
+        dxo = O.crossnorm_bwd(x, dz, plan, lam)
+        if relu:
+            yo = np.maximum(yo, 0.0)
+        chk = close32 if dtype == torch.float32 else close16
+        chk(r["y"], yo, "y")
+        chk(r["dx"], dxo, "dx")
+        # parameter gradients: 2-4 channels and batches of 9-33 -- the sums over the batch cancel to a few units and the
+        # only scale to judge them against is themselves: 3e-5 here (1e-5 at the sizes of test_site_vs_oracle_f32)
+        tol = 3e-5 if dtype == torch.float32 else 1e-2
+        for k, v in (("dg_w", gr["g_w"]), ("dg_gamma", gr["g_gamma"]), ("dg_beta", gr["g_beta"])):
+            assert H.relmax(r[k], v) <= tol, (k, H.relmax(r[k], v), knobs)
+        close32(r["rm"], nb["g_rm"], "running_mean")
+        close32(r["rv"], nb["g_rv"], "running_var")
+    L.async_error()
