@@ -252,3 +252,57 @@ def test_strided_statistics_in_place(mod, how, dtype):
     (mean.float() * gm + std.float() * gs).sum().backward()
     (rm * gm + rs * gs).sum().backward()
     assert torch.allclose(xt.grad.float(), xr.grad, **tol)
+
+
+def test_tensor_memory_pipeline_fuzz_against_the_general_path(mod):
+    """Seeded fuzz of the shared + tensor memory pipeline (SelfNorm and the whole-plane site): random batch sizes (ragged
+    last items, N barely above two items), channel counts, plane sizes across all five vector-per-thread geometries,
+    dtypes, the fused ReLU, persistent grids of 1..5 CTAs -- every run against the three-kernel general path / the
+    two-operator sequence of the same library on identical inputs and host draws."""
+    import cnsn_b200._lib as L
+    rs = np.random.RandomState(2024)
+    sides = [40, 44, 48, 52, 56, 60, 64]
+    for it in range(36):
+        hw = sides[rs.randint(len(sides))]
+        dtype = [torch.float32, torch.float32, torch.bfloat16][rs.randint(3)]
+        if dtype != torch.float32:
+            hw = [56, 64, 72, 80, 88][rs.randint(5)]
+        N, C = int(rs.randint(16, 45)), int(rs.randint(1, 5))
+        relu, site = bool(rs.randint(2)), bool(rs.randint(2))
+        cap = int(rs.randint(1, 6))
+        g = torch.Generator().manual_seed(it)
+        x0 = (torch.randn(N, C, hw, hw, generator=g) * (0.5 + torch.rand(N, C, 1, 1, generator=g)) + torch.randn(N, C, 1, 1, generator=g)).to(dtype).to(DEV)
+        dy = torch.randn(N, C, hw, hw, generator=g).to(dtype).to(DEV)
+        torch.manual_seed(it)
+        sn = mod.SelfNorm(C).to(DEV).train()
+        blk = mod.CNSN(mod.CrossNorm(crop="neither", beta=1), sn).train()
+        state = {k: v.clone() for k, v in sn.state_dict().items()}
+        outs = []
+        for knobs, fused in (({"tm": 3, "tm_items": 0, "grid_cap": cap}, True), ({"tm": 0, "selfnorm_impl": "v1", "crossnorm_impl": "v1"}, False)):
+            sn.load_state_dict(state)
+            sn.zero_grad(set_to_none=True)
+            mod.CNSN.fuse_site = fused
+            try:
+                with L.tuned(**knobs):
+                    torch.manual_seed(100 + it)
+                    x = x0.clone().requires_grad_(True)
+                    if site:
+                        blk.crossnorm.active = True
+                        y = blk(x, None, True) if relu else blk(x)
+                    else:
+                        y = sn(x, None, True) if relu else sn(x)
+                    y.backward(dy)
+            finally:
+                mod.CNSN.fuse_site = True
+            outs.append([t.detach().float() for t in (y, x.grad, sn.g_fc.weight.grad, sn.g_bn.weight.grad, sn.g_bn.bias.grad,
+                                                      sn.g_bn.running_mean, sn.g_bn.running_var)])
+        torch.cuda.synchronize()
+        tol = 3e-5 if dtype == torch.float32 else 3e-2
+        for name, a, b in zip(("y", "dx", "dW", "dgamma", "dbeta", "running_mean", "running_var"), outs[0], outs[1]):
+            if relu and name == "dx":
+                keep = outs[1][0] != 0                   # clear of the ReLU edge on the reference side ...
+                keep &= outs[0][0] != 0                  # ... and on ours
+                a, b = a[keep], b[keep]
+            err = float((a - b).abs().max() / b.abs().max().clamp_min(1e-6))
+            assert err <= tol, (it, name, err, dict(N=N, C=C, hw=hw, dtype=dtype, relu=relu, site=site, cap=cap))
+    L.async_error()
