@@ -225,6 +225,7 @@ static int launch_cn(CNArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
         e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, sms, kCnT, dsmem, stream);                         \
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }          \
         if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {

@@ -367,7 +367,9 @@ static inline cudaError_t prepare_kernel(K fn, int threads, size_t dsmem, int* c
 // host: launch a persistent ticket kernel.  The grid is capped at the number of CTAs the GPU holds at once
 // (occupancy x SMs) and launched COOPERATIVELY: the driver then guarantees that every CTA of the grid is resident
 // at the same time whatever else shares the GPU (NCCL kernels, other streams, MPS), which is what the spin-waits
-// between the CTAs of a channel rely on.  Each CTA loops over tickets until they run out.
+// between the CTAs of a channel rely on.  Each CTA loops over tickets until they run out.  A grid the driver will not
+// co-schedule (cudaErrorCooperativeLaunchTooLarge: fewer SMs than the occupancy query assumed, e.g. under an SM
+// partition) is not launched: the callers then take the path that needs no residency (L2 items / general kernels).
 template <typename K, typename A>
 static inline cudaError_t launch_persistent(K fn, const A& args, unsigned items, unsigned channel_items, int per_sm, int sms,
                                             int threads, size_t dsmem, cudaStream_t stream) {

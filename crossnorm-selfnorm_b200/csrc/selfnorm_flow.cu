@@ -932,6 +932,7 @@ static int launch_res_i3(FArgs& a, int dtype, float* scratch, cudaStream_t strea
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
         if (e != cudaSuccess) return (int)e;
         e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kT3, dsmem, stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }
         if (e != cudaSuccess) return (int)e;
     });
     if (kn.debug)
@@ -992,6 +993,7 @@ static int launch_res(FArgs& a, int dtype, float* scratch, cudaStream_t stream, 
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
         e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, sms, kResT, dsmem, stream);                        \
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }          \
         if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (tpi) {
@@ -1054,6 +1056,7 @@ static int launch_grp(FArgs& a, int dtype, float* scratch, cudaStream_t stream) 
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);
         if (e != cudaSuccess) return (int)e;
         e = launch_persistent(fn, a, a.items, (unsigned)a.nI, per_sm, ds.sms, kGrpT, dsmem, stream);
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }
         if (e != cudaSuccess) return (int)e;
     });
     trace_end(a, trace_path, items, per_sm, BWD, stream);

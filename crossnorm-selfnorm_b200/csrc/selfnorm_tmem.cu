@@ -363,6 +363,7 @@ static int launch_tm(FArgs& a, int dtype, float* scratch, cudaStream_t stream) {
         /* grid: one CTA per SM; every CTA's four groups take tickets until they run out */             \
         e = launch_persistent(fn, a, (a.items + kTmGroups - 1) / kTmGroups, ((unsigned)a.nI + kTmGroups - 1) / kTmGroups, \
                               1, ds.sms, kTmCta, dsmem, stream);                                         \
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }          \
         if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (SL) {

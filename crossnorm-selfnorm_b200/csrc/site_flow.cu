@@ -399,6 +399,7 @@ static int launch_site(SiteArgs& s, int dtype, float* scratch, cudaStream_t stre
         e = cudaMemsetAsync(a.pub, 0xff, fill_bytes, stream);                                            \
         if (e != cudaSuccess) return (int)e;                                                             \
         e = launch_persistent(fn, s, a.items, (unsigned)a.nI, per_sm, sms, kSiteT, g.dsmem, stream);                     \
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }          \
         if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (g.tpi) {

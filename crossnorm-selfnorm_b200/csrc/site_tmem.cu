@@ -446,6 +446,7 @@ static int launch_site_tm(SiteArgs& s, int dtype, float* scratch, cudaStream_t s
         if (e != cudaSuccess) return (int)e;                                                             \
         e = launch_persistent(fn, s, (a.items + kTmGroups - 1) / kTmGroups, ((unsigned)a.nI + kTmGroups - 1) / kTmGroups, \
                               1, ds.sms, kTmCta, dsmem, stream);                                         \
+        if (e == cudaErrorCooperativeLaunchTooLarge) { (void)cudaGetLastError(); return -100; }          \
         if (e != cudaSuccess) return (int)e;                                                             \
     } break;
     CNSN_DISPATCH_DTYPE(dtype, T, switch (SL) {
