@@ -316,10 +316,21 @@ static int launch_ibn(IArgs& a, int dtype, float* scratch, cudaStream_t stream, 
     return launch_status();
 }
 
+// bn_grp.cu: batch norm (half == 0) over planes that are not multiples of 16 bytes, as channel groups
+int bn_grp_fwd(const void* x, void* y, int dtype, int N, int C, int M, const float* gamma, const float* beta, float* run_mean,
+               float* run_var, long long* nbt, int training, int relu, float momentum, float eps, float* save_mean,
+               float* save_rstd, float* scratch, cudaStream_t stream, bool dry_run);
+int bn_grp_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int M, const float* gamma, const float* beta,
+               int training, int relu, float* save_mean, float* save_rstd, float* dgamma, float* dbeta, float* scratch,
+               cudaStream_t stream, bool dry_run);
+
 }  // namespace flow
 }  // namespace cnsn
 
 using namespace cnsn;
+
+static bool odd_planes(int dtype, int M) { return ((size_t)M * esize(dtype)) % 16 != 0; }
+static int from_grp(int rc) { return rc == -100 ? CNSN_E_UNSUPPORTED : rc; }
 
 static ibn_general::GArgs general_args(const flow::IArgs& a) {
     ibn_general::GArgs g{};
@@ -341,6 +352,11 @@ extern "C" int cnsn_ibn_resident(int dtype, int N, int C, int H, int W, int half
     if (check_dims(N, C, H, W) || half < 0 || half > C || dtype < CNSN_F32 || dtype > CNSN_F16) return 0;
     flow::IArgs a{};
     a.N = N; a.C = C; a.M = H * W; a.half = half; a.training = training;
+    if (half == 0 && odd_planes(dtype, H * W))
+        return flow::bn_grp_fwd(nullptr, nullptr, dtype, N, C, H * W, nullptr, nullptr, nullptr, nullptr, nullptr, training, 0, 0.f, 0.f,
+                                nullptr, nullptr, nullptr, nullptr, true) == 0 &&
+               flow::bn_grp_bwd(nullptr, nullptr, nullptr, dtype, N, C, H * W, nullptr, nullptr, training, 0, nullptr, nullptr, nullptr,
+                                nullptr, nullptr, nullptr, true) == 0;
     if (flow::launch_ibn<false>(a, dtype, nullptr, nullptr, true) != 0) return 0;
     return flow::launch_ibn<true>(a, dtype, nullptr, nullptr, true) == 0 ? 1 : 0;
 }
@@ -362,7 +378,12 @@ extern "C" int cnsn_ibn_fwd(const void* x, void* y, int dtype, int N, int C, int
     a.in_mean = save; a.in_rstd = save + (size_t)N * half;
     a.bn_mean = save + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     float* scratch = save + ibn_stats_floats(N, C, half);
-    const int rc = vec ? flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
+    int rc = CNSN_E_UNSUPPORTED;
+    if (vec && half == 0 && odd_planes(dtype, a.M))
+        rc = from_grp(flow::bn_grp_fwd(x, y, dtype, N, C, a.M, a.bn_w, a.bn_b, a.run_mean, a.run_var, a.nbt, training, a.relu, momentum,
+                                       eps_bn, a.bn_mean, a.bn_rstd, scratch, (cudaStream_t)stream, false));
+    else if (vec)
+        rc = flow::launch_ibn<false>(a, dtype, scratch, (cudaStream_t)stream);
     if (rc != CNSN_E_UNSUPPORTED || relu) return rc;  // the fused ReLU exists in the resident kernel only (cnsn_ibn_resident)
     ibn_general::GArgs g = general_args(a);          // odd / oversized planes, misaligned slices: the three-kernel path
     return ibn_general::ibn_general_fwd(g, dtype, scratch, (cudaStream_t)stream);
@@ -387,7 +408,12 @@ extern "C" int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, 
     a.in_mean = sv; a.in_rstd = sv + (size_t)N * half;
     a.bn_mean = sv + 2 * (size_t)N * half; a.bn_rstd = a.bn_mean + (C - half);
     a.d_in_w = d_in_w; a.d_in_b = d_in_b; a.d_bn_w = d_bn_w; a.d_bn_b = d_bn_b;
-    const int rc = vec ? flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream) : CNSN_E_UNSUPPORTED;
+    int rc = CNSN_E_UNSUPPORTED;
+    if (vec && half == 0 && odd_planes(dtype, a.M))
+        rc = from_grp(flow::bn_grp_bwd(x, dy, dx, dtype, N, C, a.M, a.bn_w, a.bn_b, training, a.relu, a.bn_mean, a.bn_rstd, d_bn_w, d_bn_b,
+                                       workspace, (cudaStream_t)stream, false));
+    else if (vec)
+        rc = flow::launch_ibn<true>(a, dtype, workspace, (cudaStream_t)stream);
     if (rc != CNSN_E_UNSUPPORTED || relu) return rc;
     ibn_general::GArgs g = general_args(a);
     return ibn_general::ibn_general_bwd(g, dtype, workspace, (cudaStream_t)stream);

@@ -230,12 +230,15 @@ def test_ibn_general_path_vs_oracle(shape, dtype, half, training):
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,dtype", [((64, 16, 32, 32), torch.float32), ((128, 32, 32, 32), torch.float32), ((96, 64, 16, 16), torch.float32),
                                          ((64, 128, 8, 8), torch.float32), ((16, 64, 56, 56), torch.float32), ((32, 8, 32, 32), torch.bfloat16),
-                                         ((8, 16, 7, 7), torch.float32)])
+                                         ((8, 16, 7, 7), torch.float32), ((96, 64, 14, 14), torch.bfloat16), ((96, 128, 7, 7), torch.bfloat16),
+                                         ((300, 8, 7, 7), torch.float32), ((33, 24, 9, 9), torch.float16), ((5, 6, 7, 7), torch.float32),
+                                         ((64, 32, 14, 14), torch.float16)])
 @pytest.mark.parametrize("training", [True, False])
 def test_batchnorm2d_dropin_matches_torch(shape, dtype, training):
     """cnsn_b200.ibn.BatchNorm2d (the host blocks' nn.BatchNorm2d through cnsn_ibn_* with half = 0) against torch's own
     nn.BatchNorm2d in fp64 on the same GPU: y, dx, dweight, dbias, running statistics, num_batches_tracked; identical
-    state dict.  (8,16,7,7): planes that are not 16-byte multiples -- the drop-in hands those to torch.)"""
+    state dict.  Planes that are not 16-byte multiples (7x7 fp32, 14x14 / 7x7 / 9x9 16-bit: the last stages of ResNet-50
+    under autocast) run the channel-group kernel of csrc/bn_grp.cu; (5,6,7,7): no channel group fits -- torch.)"""
     import torch.nn as nn
     from cnsn_b200.ibn import BatchNorm2d
     dev = "cuda:0"
@@ -267,6 +270,29 @@ def test_batchnorm2d_dropin_matches_torch(shape, dtype, training):
 
 
 @pytest.mark.gpu
+def test_batchnorm2d_odd_planes_take_the_group_kernel():
+    """The shapes of ResNet-50's last two stages under autocast are claimed by the library (cnsn_ibn_resident), so the
+    drop-in runs csrc/bn_grp.cu for them rather than torch's batch norm; shapes with no 16-byte channel group are not."""
+    import cnsn_b200._lib as L
+    be = L.backend()
+    dev = "cuda:0"
+    for shape, dtype, want in (((96, 1024, 14, 14), torch.bfloat16, True), ((96, 2048, 7, 7), torch.bfloat16, True),
+                               ((96, 512, 7, 7), torch.bfloat16, True), ((32, 512, 7, 7), torch.float32, True),
+                               ((5, 6, 7, 7), torch.float32, False), ((4, 7, 7, 7), torch.bfloat16, False)):
+        x = torch.empty(shape, device=dev, dtype=dtype)
+        for training in (True, False):
+            assert bool(be.ibn_resident(x, 0, training)) == want, (shape, dtype, training)
+    n0 = L.launch_count()
+    from cnsn_b200.ibn import BatchNorm2d
+    m = BatchNorm2d(64).to(dev).train()
+    x = torch.randn(48, 64, 7, 7, device=dev, dtype=torch.bfloat16, requires_grad=True)
+    m(x, True).float().sum().backward()
+    torch.cuda.synchronize()
+    assert L.launch_count() - n0 >= 2
+    L.async_error()
+
+
+@pytest.mark.gpu
 def test_batchnorm2d_dropin_momentum_none_and_fallbacks():
     """momentum=None (cumulative average) follows torch; affine=False and CPU tensors take the torch implementation."""
     import torch.nn as nn
@@ -287,7 +313,8 @@ def test_batchnorm2d_dropin_momentum_none_and_fallbacks():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("shape,dtype", [((64, 16, 32, 32), torch.float32), ((96, 64, 16, 16), torch.float32), ((16, 64, 56, 56), torch.float32),
-                                         ((32, 8, 32, 32), torch.bfloat16)])
+                                         ((32, 8, 32, 32), torch.bfloat16), ((96, 64, 14, 14), torch.bfloat16), ((64, 32, 7, 7), torch.float32),
+                                         ((200, 16, 7, 7), torch.bfloat16)])
 @pytest.mark.parametrize("training", [True, False])
 @pytest.mark.parametrize("binding", ["ext", "ctypes"])
 def test_batchnorm2d_fused_relu_matches_torch(shape, dtype, training, binding):
