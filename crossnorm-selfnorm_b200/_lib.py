@@ -18,7 +18,7 @@ EXT_PATH = os.path.join(_PKG, "_cnsn_torch.so")
 CNSN_F32, CNSN_BF16, CNSN_F16 = 0, 1, 2
 CNSN_E_BATCH1 = -3
 CNSN_E_TIMEOUT = -6
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _DTYPES = {torch.float32: CNSN_F32, torch.bfloat16: CNSN_BF16, torch.float16: CNSN_F16}
 
@@ -66,6 +66,13 @@ SIGNATURES = {
                                         c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "cnsn_selfnorm_block_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
                                         c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_selfnorm_nhwc_supported": (c_int, [c_int, *_DIMS]),
+    "cnsn_selfnorm_nhwc_save_floats": (c_size_t, [c_int, *_DIMS]),
+    "cnsn_selfnorm_nhwc_workspace_floats": (c_size_t, [c_int, *_DIMS]),
+    "cnsn_selfnorm_block_fwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
+                                             c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_selfnorm_block_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
+                                             c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),
@@ -356,13 +363,19 @@ class CudaBackend:
         N, C, H, W = x.shape
         keep = []
         gs, g_rm, g_rv = self._gate_struct(g, keep)
-        save = torch.empty(_size("cnsn_selfnorm_save_floats", N, C, 0), dtype=torch.float32, device=x.device)
+        cl = self.is_nhwc(x)                 # channels_last tensors stay in their layout (y, z come out channels_last too)
+        if cl and res is not None and not self.is_nhwc(res):
+            res = res.contiguous(memory_format=torch.channels_last)
+        floats = (_size("cnsn_selfnorm_nhwc_save_floats", _dtype_code(x), N, C, H, W) if cl
+                  else _size("cnsn_selfnorm_save_floats", N, C, 0))
+        save = torch.empty(floats, dtype=torch.float32, device=x.device)
         y = torch.empty_like(x)
         z = torch.empty_like(x) if res is not None else x
+        fn = lib().cnsn_selfnorm_block_fwd_nhwc if cl else lib().cnsn_selfnorm_block_fwd
         with _on(x.device):
-            _check(lib().cnsn_selfnorm_block_fwd(_p(x), _p(res), _p(z) if res is not None else None, _p(y), int(relu),
-                                                 _dtype_code(x), N, C, H, W, ctypes.byref(gs), int(training),
-                                                 momentum, bn_eps, eps, _p(save), _stream(x)))
+            _check(fn(_p(x), _p(res), _p(z) if res is not None else None, _p(y), int(relu),
+                      _dtype_code(x), N, C, H, W, ctypes.byref(gs), int(training),
+                      momentum, bn_eps, eps, _p(save), _stream(x)))
         if training:
             if g_rm is not g.run_mean:
                 g.run_mean.copy_(g_rm)
@@ -379,13 +392,26 @@ class CudaBackend:
         buf = torch.empty(4 * C, dtype=torch.float32, device=dev)
         out_g = (buf[:2 * C].view(C, 2), buf[2 * C:3 * C], buf[3 * C:])
         gg = GateGrads(*[_p(t).value for t in out_g])
-        ws = torch.empty(_size("cnsn_selfnorm_workspace_floats", N, C, 0), dtype=torch.float32, device=dev)
+        cl = self.is_nhwc(z)
+        if cl and not self.is_nhwc(dy):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        floats = (_size("cnsn_selfnorm_nhwc_workspace_floats", _dtype_code(z), N, C, H, W) if cl
+                  else _size("cnsn_selfnorm_workspace_floats", N, C, 0))
+        ws = torch.empty(floats, dtype=torch.float32, device=dev)
         dz = torch.empty_like(z)
+        fn = lib().cnsn_selfnorm_block_bwd_nhwc if cl else lib().cnsn_selfnorm_block_bwd
         with _on(dev):
-            _check(lib().cnsn_selfnorm_block_bwd(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
-                                                 ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg),
-                                                 _p(ws), _stream(z)))
+            _check(fn(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
+                      ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg), _p(ws), _stream(z)))
         return dz, out_g
+
+    @staticmethod
+    def is_nhwc(x):
+        """x is a dense channels_last tensor (and not at the same time dense NCHW) that the NHWC kernels take."""
+        if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+            return False
+        N, C, H, W = x.shape
+        return x.data_ptr() % 16 == 0 and bool(_size("cnsn_selfnorm_nhwc_supported", _dtype_code(x), N, C, H, W))
 
     # -- IBN ----------------------------------------------------------------------------------
     @staticmethod

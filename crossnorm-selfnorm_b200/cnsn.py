@@ -216,7 +216,9 @@ class SelfNorm(nn.Module):
             if ext is not None:                       # C++ autograd node: one call per direction
                 return ext.selfnorm(x, residual, bool(relu), self.g_fc.weight, bn.weight, bn.bias, bn.running_mean,
                                     bn.running_var, bn.num_batches_tracked, bn.training, _bn_momentum(bn), float(bn.eps), 1e-12)
-        if residual is not None or relu:
+        nhwc = (self.f_fc is None and x.is_cuda and not x.is_contiguous()
+                and x.is_contiguous(memory_format=torch.channels_last))    # channels_last: the block entry has NHWC kernels
+        if residual is not None or relu or nhwc:
             assert self.f_fc is None, "the fused block supports the single-gate SelfNorm"
             assert residual is None or residual.shape == x.shape
             return SelfNormBlockFn.apply(x, residual, bool(relu), bn.training, _bn_momentum(bn), float(bn.eps), 1e-12,

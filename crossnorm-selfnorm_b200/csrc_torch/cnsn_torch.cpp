@@ -127,27 +127,44 @@ Win window(const std::vector<int64_t>& w) {
     return Win{{(int)w[0], (int)w[1], (int)w[2], (int)w[3]}};
 }
 
+// A channels_last caller gets channels_last back from the operators whose kernels are NCHW (CrossNorm, the fused site):
+// whatever follows (cuDNN's NHWC convolutions, forward and backward) then keeps seeing ONE layout -- no new cuDNN plans,
+// no conversions further down.
+bool is_channels_last(const at::Tensor& t) {
+    return t.dim() == 4 && !t.is_contiguous() && t.is_contiguous(at::MemoryFormat::ChannelsLast);
+}
+at::Tensor like_input(const at::Tensor& t, bool cl) { return cl ? t.contiguous(at::MemoryFormat::ChannelsLast) : t; }
+
 // ---- SelfNorm (single gate), optionally relu?(SelfNorm(x + res)) ---------------------------------------------------
 struct SelfNormNode : public torch::autograd::Function<SelfNormNode> {
     static at::Tensor forward(AutogradContext* ctx, const at::Tensor& x_in, const c10::optional<at::Tensor>& res_in, bool relu,
                               bool block, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta, GateBufs bufs,
                               bool training, double momentum, double bn_eps, double eps) {
         require_cuda4(x_in);
-        const at::Tensor x = x_in.contiguous();
+        const int N = (int)x_in.size(0), C = (int)x_in.size(1), H = (int)x_in.size(2), W = (int)x_in.size(3);
+        // a dense channels_last tensor stays in its layout when the NHWC kernels take the shape (y, z, dz come out channels_last)
+        const bool cl = !x_in.is_contiguous() && x_in.is_contiguous(at::MemoryFormat::ChannelsLast) &&
+                        (reinterpret_cast<uintptr_t>(x_in.data_ptr()) & 15u) == 0 &&
+                        cnsn_selfnorm_nhwc_supported(dtype_code(x_in), N, C, H, W) != 0;
+        const at::MemoryFormat fmt = cl ? at::MemoryFormat::ChannelsLast : at::MemoryFormat::Contiguous;
+        const at::Tensor x = x_in.contiguous(fmt);
         const bool has_res = res_in.has_value() && res_in->defined();
         at::Tensor res;
         if (has_res) {
             TORCH_CHECK(res_in->sizes() == x.sizes() && res_in->scalar_type() == x.scalar_type() && res_in->is_cuda(), "residual must match x");
-            res = res_in->contiguous();
+            res = res_in->contiguous(fmt);
         }
         const c10::cuda::CUDAGuard guard(x.device());
         cudaStream_t stream = at::cuda::getCurrentCUDAStream();
-        const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
-        at::Tensor save = f32_buffer(x, (int64_t)cnsn_selfnorm_save_floats(N, C, 0));
+        at::Tensor save = f32_buffer(x, (int64_t)(cl ? cnsn_selfnorm_nhwc_save_floats(dtype_code(x), N, C, H, W) : cnsn_selfnorm_save_floats(N, C, 0)));
         at::Tensor y = at::empty_like(x);
         at::Tensor z = has_res ? at::empty_like(x) : x;
         const cnsn_gate_params g = gate_params(w, gamma, beta, &bufs);
-        if (block) {
+        if (cl) {
+            check(cnsn_selfnorm_block_fwd_nhwc(x.data_ptr(), has_res ? res.data_ptr() : nullptr, has_res ? z.data_ptr() : nullptr,
+                                               y.data_ptr(), relu ? 1 : 0, dtype_code(x), N, C, H, W, &g, training ? 1 : 0,
+                                               (float)momentum, (float)bn_eps, (float)eps, save.data_ptr<float>(), stream));
+        } else if (block) {
             check(cnsn_selfnorm_block_fwd(x.data_ptr(), has_res ? res.data_ptr() : nullptr, has_res ? z.data_ptr() : nullptr,
                                           y.data_ptr(), relu ? 1 : 0, dtype_code(x), N, C, H, W, &g, training ? 1 : 0,
                                           (float)momentum, (float)bn_eps, (float)eps, save.data_ptr<float>(), stream));
@@ -160,6 +177,7 @@ struct SelfNormNode : public torch::autograd::Function<SelfNormNode> {
         ctx->saved_data["block"] = block;
         ctx->saved_data["training"] = training;
         ctx->saved_data["has_res"] = has_res;
+        ctx->saved_data["cl"] = cl;
         return y;
     }
 
@@ -168,17 +186,22 @@ struct SelfNormNode : public torch::autograd::Function<SelfNormNode> {
         const at::Tensor &z = saved[0], &w = saved[1], &gamma = saved[2], &beta = saved[3], &save = saved[4];
         const bool relu = ctx->saved_data["relu"].toBool(), block = ctx->saved_data["block"].toBool();
         const bool training = ctx->saved_data["training"].toBool(), has_res = ctx->saved_data["has_res"].toBool();
-        const at::Tensor dy = grads[0].contiguous();
+        const bool cl = ctx->saved_data["cl"].toBool();
+        const at::Tensor dy = grads[0].contiguous(cl ? at::MemoryFormat::ChannelsLast : at::MemoryFormat::Contiguous);
         const c10::cuda::CUDAGuard guard(z.device());
         cudaStream_t stream = at::cuda::getCurrentCUDAStream();
         const int N = (int)z.size(0), C = (int)z.size(1), H = (int)z.size(2), W = (int)z.size(3);
         at::Tensor pg = f32_buffer(z, 4 * (int64_t)C);                // dw (C,2) | dgamma (C) | dbeta (C)
-        at::Tensor ws = f32_buffer(z, (int64_t)cnsn_selfnorm_workspace_floats(N, C, 0));
+        at::Tensor ws = f32_buffer(z, (int64_t)(cl ? cnsn_selfnorm_nhwc_workspace_floats(dtype_code(z), N, C, H, W)
+                                                   : cnsn_selfnorm_workspace_floats(N, C, 0)));
         at::Tensor dz = at::empty_like(z);
         const cnsn_gate_params g = gate_params(w, gamma, beta, nullptr);
         float* p = pg.data_ptr<float>();
         const cnsn_gate_grads gg{p, p + 2 * C, p + 3 * C};
-        if (block) {
+        if (cl) {
+            check(cnsn_selfnorm_block_bwd_nhwc(z.data_ptr(), dy.data_ptr(), dz.data_ptr(), relu ? 1 : 0, dtype_code(z), N, C, H, W, &g,
+                                               training ? 1 : 0, save.data_ptr<float>(), &gg, ws.data_ptr<float>(), stream));
+        } else if (block) {
             check(cnsn_selfnorm_block_bwd(z.data_ptr(), dy.data_ptr(), dz.data_ptr(), relu ? 1 : 0, dtype_code(z), N, C, H, W, &g,
                                           training ? 1 : 0, save.data_ptr<float>(), &gg, ws.data_ptr<float>(), stream));
         } else {
@@ -209,7 +232,8 @@ struct CrossNormNode : public torch::autograd::Function<CrossNormNode> {
         ctx->saved_data["cw"] = std::vector<int64_t>(cw.v, cw.v + 4);
         ctx->saved_data["sw"] = std::vector<int64_t>(sw.v, sw.v + 4);
         ctx->saved_data["lam"] = lam;
-        return y;
+        ctx->saved_data["cl_in"] = is_channels_last(x_in);
+        return like_input(y, is_channels_last(x_in));
     }
 
     static variable_list backward(AutogradContext* ctx, variable_list grads) {
@@ -226,7 +250,7 @@ struct CrossNormNode : public torch::autograd::Function<CrossNormNode> {
         check(cnsn_crossnorm_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dtype_code(x), N, C, H, W, perm.data_ptr<int>(), nullptr,
                                  cw.v, sw.v, (float)lam, save.data_ptr<float>(), ws.data_ptr<float>(), stream));
         at::Tensor none;
-        return {dx, none, none, none, none};
+        return {like_input(dx, ctx->saved_data["cl_in"].toBool()), none, none, none, none};
     }
 };
 
@@ -254,7 +278,8 @@ struct SiteNode : public torch::autograd::Function<SiteNode> {
         ctx->saved_data["lam"] = lam;
         ctx->saved_data["cn_eps"] = cn_eps;
         ctx->saved_data["relu"] = relu;
-        return y;
+        ctx->saved_data["cl_in"] = is_channels_last(x_in);
+        return like_input(y, is_channels_last(x_in));
     }
 
     static variable_list backward(AutogradContext* ctx, variable_list grads) {
@@ -276,8 +301,8 @@ struct SiteNode : public torch::autograd::Function<SiteNode> {
         check(cnsn_site_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dtype_code(x), N, C, H, W, perm.data_ptr<int>(), cw.v, sw.v,
                             (float)lam, (float)cn_eps, relu ? 1 : 0, &g, save.data_ptr<float>(), &gg, ws.data_ptr<float>(), stream));
         at::Tensor none;
-        return {dx, none, none, none, none, none, pg.narrow(0, 0, 2 * C).view_as(w), pg.narrow(0, 2 * C, C), pg.narrow(0, 3 * C, C),
-                none, none, none, none};
+        return {like_input(dx, ctx->saved_data["cl_in"].toBool()), none, none, none, none, none, pg.narrow(0, 0, 2 * C).view_as(w),
+                pg.narrow(0, 2 * C, C), pg.narrow(0, 3 * C, C), none, none, none, none};
     }
 };
 

@@ -14,6 +14,24 @@ def _dense(x):
     return x if x.is_contiguous() else x.contiguous()
 
 
+def _is_cl(x):
+    return x.dim() == 4 and not x.is_contiguous() and x.is_contiguous(memory_format=torch.channels_last)
+
+
+def _like_input(t, cl):
+    """A channels_last caller gets channels_last back from the operators whose kernels are NCHW (CrossNorm, the fused
+    site), forward and backward: what follows (cuDNN's NHWC convolutions) keeps seeing one layout."""
+    return t.contiguous(memory_format=torch.channels_last) if cl else t
+
+
+def _dense_or_nhwc(x):
+    """Dense NCHW, or -- where the backend has channels-last kernels for the shape -- the channels_last tensor itself."""
+    if x.is_contiguous():
+        return x
+    is_nhwc = getattr(_lib.backend(), "is_nhwc", None)
+    return x if (is_nhwc is not None and x.is_cuda and is_nhwc(x)) else x.contiguous()
+
+
 class InstanceStats(torch.autograd.Function):
     """(mean, std) over a window -- calc_ins_mean_std, models/cnsn.py:8-17."""
 
@@ -94,8 +112,9 @@ class SelfNormBlockFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, res, relu, training, momentum, bn_eps, eps, g_bufs, g_w, g_gamma, g_beta):
-        x = _dense(x)
-        res = _dense(res) if res is not None else None
+        x = _dense_or_nhwc(x)
+        if res is not None:
+            res = _dense(res) if x.is_contiguous() else res      # a channels_last x: the backend brings res into its layout
         g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
         y, z, save = _lib.backend().selfnorm_block_fwd(x, res, relu, g, training, momentum, bn_eps, eps)
         ctx.save_for_backward(z, g_w, g_gamma, g_beta)
@@ -108,7 +127,7 @@ class SelfNormBlockFn(torch.autograd.Function):
         z, g_w, g_gamma, g_beta = ctx.saved_tensors
         relu, training, has_res = ctx.meta
         g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
-        dz, gg = _lib.backend().selfnorm_block_bwd(z, _dense(dy), relu, g, training, ctx.sn_save)
+        dz, gg = _lib.backend().selfnorm_block_bwd(z, dy if not z.is_contiguous() else _dense(dy), relu, g, training, ctx.sn_save)
         return (dz, dz if has_res else None, None, None, None, None, None, None,
                 gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype))
 
@@ -118,12 +137,13 @@ class CrossNormFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, perm, chan_perm, cwin, swin, lam, eps):
+        ctx.cl_in = _is_cl(x)
         x = _dense(x)
         y, save = _lib.backend().crossnorm_fwd(x, perm, chan_perm, cwin, swin, lam, eps)
         ctx.save_for_backward(x)
         ctx.cn_save = (perm, chan_perm, save)
         ctx.meta = (cwin, swin, lam)
-        return y
+        return _like_input(y, ctx.cl_in)
 
     @staticmethod
     def backward(ctx, dy):
@@ -131,7 +151,7 @@ class CrossNormFn(torch.autograd.Function):
         perm, chan_perm, save = ctx.cn_save
         cwin, swin, lam = ctx.meta
         dx = _lib.backend().crossnorm_bwd(x, _dense(dy), perm, chan_perm, cwin, swin, lam, save)
-        return dx, None, None, None, None, None, None
+        return _like_input(dx, ctx.cl_in), None, None, None, None, None, None
 
 
 class CnsnSiteFn(torch.autograd.Function):
@@ -141,12 +161,13 @@ class CnsnSiteFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, perm, cwin, swin, lam, cn_eps, relu, momentum, bn_eps, sn_eps, g_bufs, g_w, g_gamma, g_beta):
+        ctx.cl_in = _is_cl(x)
         x = _dense(x)
         g = _lib.GateTensors(g_w, g_gamma, g_beta, *g_bufs)
         y, save = _lib.backend().site_fwd(x, perm, cwin, swin, lam, cn_eps, g, momentum, bn_eps, sn_eps, relu)
         ctx.save_for_backward(x, g_w, g_gamma, g_beta)
         ctx.site = (perm, cwin, swin, lam, cn_eps, bool(relu), save)
-        return y
+        return _like_input(y, ctx.cl_in)
 
     @staticmethod
     def backward(ctx, dy):
@@ -154,7 +175,7 @@ class CnsnSiteFn(torch.autograd.Function):
         perm, cwin, swin, lam, cn_eps, relu, save = ctx.site
         g = _lib.GateTensors(g_w, g_gamma, g_beta, None, None, None)
         dx, gg = _lib.backend().site_bwd(x, _dense(dy), perm, cwin, swin, lam, cn_eps, g, save, relu)
-        return (dx, None, None, None, None, None, None, None, None, None, None,
+        return (_like_input(dx, ctx.cl_in), None, None, None, None, None, None, None, None, None, None,
                 gg[0].view_as(g_w).to(g_w.dtype), gg[1].to(g_gamma.dtype), gg[2].to(g_beta.dtype))
 
 

@@ -78,8 +78,9 @@ class BatchNorm2d(nn.BatchNorm2d):
     def forward(self, x, relu=False):
         """``forward(x)`` is ``nn.BatchNorm2d.forward``; ``forward(x, relu=True)`` is ``relu(bn(x))`` -- the pair the host
         blocks apply -- in the same kernels when the resident path takes the shape, else torch's batch norm + relu."""
-        if (x.is_cuda and x.dim() == 4 and self.affine and self.track_running_stats and self.weight.dtype is torch.float32
-                and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+        # channels_last activations stay with torch: cuDNN's NHWC batch norm keeps the layout (the library's kernels are NCHW)
+        if (x.is_cuda and x.dim() == 4 and x.is_contiguous() and self.affine and self.track_running_stats
+                and self.weight.dtype is torch.float32 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
             training = self.training
             be = _lib.backend()
             if getattr(be, "name", "") == "cuda" and be.ibn_resident(x, 0, training):

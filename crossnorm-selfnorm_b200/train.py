@@ -66,7 +66,12 @@ class GraphedStep:
         self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=self.params[0].dtype, device=images.device)
         off = 0
         for p in self.params:
-            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            chunk = self.flat[off:off + p.numel()]
+            if p.dim() == 4 and not p.is_contiguous() and p.is_contiguous(memory_format=torch.channels_last):
+                n, c, h, w = p.shape                      # same strides as the parameter (the gradient layout contract)
+                p.grad = chunk.view(n, h, w, c).permute(0, 3, 1, 2)
+            else:
+                p.grad = chunk.view_as(p)
             off += p.numel()
         self.x, self.y = images.clone(), targets.clone()
         self.graph, self.capture_error = None, None
@@ -150,8 +155,12 @@ class GraphedStep:
         return self._finish(loss, opt, sched)
 
 
-def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False, graph=None):
+def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops=None, fuse_post=False, graph=None,
+              channels_last=None):
     """images/s of WideResNet-40-2 + CNSN training on synthetic CIFAR-shaped data (fp32, batch per GPU).
+    channels_last (default: on CUDA with this package's operators): parameters and activations in torch.channels_last,
+    the layout cuDNN's tensor-core convolutions work in -- SelfNorm sites run their NHWC kernels (csrc/selfnorm_nhwc.cu),
+    a site whose CrossNorm fires converts to NCHW for that call.
     graph (default: on CUDA with this package's operators): GraphedStep -- CUDA graph for the steps without CrossNorm,
     one flat-buffer gradient all-reduce; otherwise the plain eager step (DistributedDataParallel when world > 1)."""
     import torch.distributed as dist
@@ -165,6 +174,10 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
     net = wrn40_2(ops=ops, fuse_post=fuse_post).to(dev).train()
     if graph is None:
         graph = dev.type == "cuda" and ops is None
+    if channels_last is None:
+        channels_last = dev.type == "cuda" and ops is None
+    if channels_last:
+        net = net.to(memory_format=torch.channels_last)
     model = net
     if world > 1:
         with torch.no_grad():
@@ -177,6 +190,8 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
                                                     broadcast_buffers=False, gradient_as_bucket_view=True)
     opt, sched = make_optimizer(model, total_steps=steps + warmup)
     x = torch.randn(batch, 3, 32, 32, device=dev)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 10, (batch,), device=dev)
     is_cuda = dev.type == "cuda"
     launches0 = None
@@ -234,6 +249,7 @@ def bench_wrn(dev, world, rank, batch=512, steps=20, warmup=5, cn_prob=0.25, ops
         from . import _lib
         out["cnsn_kernel_launches"] = _lib.launch_count() - launches0
     out["param_checksum"] = float(sum(p.detach().double().sum() for p in net.parameters()))
+    out["memory_format"] = "channels_last" if channels_last else "contiguous (NCHW)"
     return out
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define CNSN_ABI_VERSION 6
+#define CNSN_ABI_VERSION 7
 
 enum { CNSN_F32 = 0, CNSN_BF16 = 1, CNSN_F16 = 2 };
 
@@ -184,6 +184,25 @@ int cnsn_selfnorm_block_bwd(const void* z, const void* dy, void* dz, int relu, i
                             int N, int C, int H, int W, const cnsn_gate_params* g,
                             int training, const float* save, const cnsn_gate_grads* dg,
                             float* workspace, void* stream);
+
+/* Channels-last (NHWC) form of the block: the same operator on tensors whose logical shape is (N, C, H, W) and whose
+ * memory order is N, H, W, C (torch.channels_last, dense) -- what a network keeps its activations in when cuDNN's
+ * NHWC convolutions are not to convert around every call.  Same arguments and results as cnsn_selfnorm_block_fwd /
+ * _bwd (res = z = NULL, relu = 0 is the plain models/cnsn.py:130-150 SelfNorm); x, res, z, y (z, dy, dz) are all NHWC.
+ * Base pointers must be 16-byte aligned and C * sizeof(T) a multiple of 16 that divides 4096
+ * (cnsn_selfnorm_nhwc_supported), else CNSN_E_ALIGN / CNSN_E_UNSUPPORTED and the caller converts to NCHW.
+ * save / workspace sizes are this form's own (they hold the per-slab partial statistics as well). */
+int cnsn_selfnorm_nhwc_supported(int dtype, int N, int C, int H, int W);
+size_t cnsn_selfnorm_nhwc_save_floats(int dtype, int N, int C, int H, int W);
+size_t cnsn_selfnorm_nhwc_workspace_floats(int dtype, int N, int C, int H, int W);
+int cnsn_selfnorm_block_fwd_nhwc(const void* x, const void* res, void* z, void* y, int relu, int dtype,
+                                 int N, int C, int H, int W, const cnsn_gate_params* g,
+                                 int training, float momentum, float bn_eps, float eps,
+                                 float* save, void* stream);
+int cnsn_selfnorm_block_bwd_nhwc(const void* z, const void* dy, void* dz, int relu, int dtype,
+                                 int N, int C, int H, int W, const cnsn_gate_params* g,
+                                 int training, const float* save, const cnsn_gate_grads* dg,
+                                 float* workspace, void* stream);
 
 /* ---------------------------------------------------------------- CrossNorm --------------
  * Replaces cn_op_2ins_space_chan, models/cnsn.py:58-91 (+ instance_norm_mix :20-29), device

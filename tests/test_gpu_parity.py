@@ -197,6 +197,65 @@ def test_selfnorm_block_fusion_vs_oracle(mod, shape, dtype, add, relu, training)
     close32(m.g_bn.running_mean.double().cpu().numpy(), nb["g_rm"] if training else bufs["g_rm"], "running_mean")
 
 
+NHWC_SHAPES = [((8, 32, 32, 32), torch.float32), ((6, 64, 16, 16), torch.float32), ((4, 128, 8, 8), torch.float32),
+               ((5, 16, 20, 20), torch.float32), ((6, 8, 50, 50), torch.float32), ((4, 32, 32, 32), torch.bfloat16),
+               ((4, 256, 56, 56), torch.float32), ((3, 64, 13, 11), torch.float16), ((3, 24, 9, 9), torch.float32),
+               ((130, 16, 8, 8), torch.float32)]
+
+
+@pytest.mark.parametrize("shape,dtype", NHWC_SHAPES)
+@pytest.mark.parametrize("add,relu", [(True, True), (False, False), (False, True)])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("binding", ["ext", "ctypes"])
+def test_selfnorm_channels_last_vs_oracle(mod, shape, dtype, add, relu, training, binding):
+    """relu?(SelfNorm(x [+ res])) on torch.channels_last tensors through cnsn_selfnorm_block_fwd_nhwc / _bwd_nhwc
+    (csrc/selfnorm_nhwc.cu) against the NCHW oracle: one slab and many slabs per sample (Chan merge of the slab
+    statistics), ragged last slabs, 16-bit types, both host bindings; outputs and gradients stay channels_last.
+    (3,24,9,9): 96-byte pixels do not tile 256 threads -- the call converts to NCHW and takes the usual kernels.)"""
+    rs = np.random.RandomState(sum(shape))
+    x = O.varied_input(shape, seed=sum(shape) + 1, dtype=np.float32)
+    r = (rs.standard_normal(shape) * 0.7).astype(np.float32)
+    dy = rs.standard_normal(shape).astype(np.float32)
+    if dtype != torch.float32:
+        x, r, dy = (torch.from_numpy(v).to(dtype).float().numpy() for v in (x, r, dy))
+    params, bufs = H.random_sn_params(shape[1], seed=5)
+    cl = torch.channels_last
+    old = L.set_binding(binding)
+    try:
+        m = H.make_selfnorm(mod, shape[1], params, bufs, DEV, False, training)
+        xt = torch.from_numpy(x).to(device=DEV, dtype=dtype).contiguous(memory_format=cl).requires_grad_(True)
+        rt = torch.from_numpy(r).to(device=DEV, dtype=dtype).contiguous(memory_format=cl).requires_grad_(True)
+        n0 = L.launch_count()
+        y = m(xt, rt if add else None, relu)
+        y.backward(torch.from_numpy(dy).to(device=DEV, dtype=dtype).contiguous(memory_format=cl))
+        torch.cuda.synchronize()
+        launched = L.launch_count() - n0
+    finally:
+        L.set_binding(old)
+    supported = bool(L.lib().cnsn_selfnorm_nhwc_supported(L._dtype_code(xt), *shape))
+    assert supported == (shape != (3, 24, 9, 9))
+    if supported:
+        assert launched == 6                              # statistics, gate, apply -- per direction
+        assert y.is_contiguous(memory_format=cl) and xt.grad.is_contiguous(memory_format=cl)
+    z = (torch.from_numpy(x).to(dtype) + torch.from_numpy(r).to(dtype)).float().numpy() if add else x
+    yo, nb = O.selfnorm_fwd(z.astype(np.float64), params, bufs, training)
+    mask = (yo > 0) if relu else np.ones_like(yo, dtype=bool)
+    dzo, gr = O.selfnorm_bwd(z.astype(np.float64), np.where(mask, dy, 0.0), params, bufs, training)
+    chk = close32 if dtype == torch.float32 else close16
+    chk(y.detach().double().cpu().numpy(), np.where(mask, yo, 0.0), "y")
+    chk(xt.grad.double().cpu().numpy(), dzo, "dx")
+    if add:
+        assert torch.equal(xt.grad, rt.grad)
+    # parameter gradients: BatchNorm1d over a batch of 2-6 samples amplifies the fp32 rounding of the per-instance sums
+    # (2500-element columns summed in a different order than the oracle's) -- 3e-5 there, 1e-5 from 8 samples on
+    tol = (H.PARAM_RTOL if shape[0] >= 8 else 3e-5) if dtype == torch.float32 else 2e-4
+    assert H.relmax(m.g_fc.weight.grad.view(-1, 2).double().cpu().numpy(), gr["g_w"]) <= tol
+    assert H.relmax(m.g_bn.weight.grad.double().cpu().numpy(), gr["g_gamma"]) <= tol
+    assert H.relmax(m.g_bn.bias.grad.double().cpu().numpy(), gr["g_beta"]) <= tol
+    close32(m.g_bn.running_mean.double().cpu().numpy(), nb["g_rm"] if training else bufs["g_rm"], "running_mean")
+    close32(m.g_bn.running_var.double().cpu().numpy(), nb["g_rv"] if training else bufs["g_rv"], "running_var")
+
+
 CN_SHAPES = [(8, 6, 12, 10), (4, 16, 8, 8), (6, 5, 7, 7), (16, 8, 32, 32), (3, 2, 72, 72), (5, 3, 9, 14), (37, 3, 20, 20)]
 
 

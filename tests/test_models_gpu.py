@@ -122,10 +122,14 @@ def _train_step(net, opt, fwd):
 
 
 @pytest.mark.parametrize("aug", [True, False])
-@pytest.mark.parametrize("fuse_post,fuse_site", [(True, True), (False, True), (True, False), (False, False)])
-def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site):
+@pytest.mark.parametrize("fuse_post,fuse_site,channels_last", [(True, True, False), (False, True, False), (True, False, False),
+                                                               (False, False, False), (True, True, True), (False, True, True)])
+def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site, channels_last):
     """BASELINE config 3: WideResNet-40-2, cnsn_type='cnsn', pos='post', crop='both', active_num=2 (cifar10-scripts/
-    wideresnet/run-cnsn.sh), SGD nesterov lr 0.1 wd 5e-4 (cifar.py:398-402); batch 64 of synthetic 32x32 images."""
+    wideresnet/run-cnsn.sh), SGD nesterov lr 0.1 wd 5e-4 (cifar.py:398-402); batch 64 of synthetic 32x32 images.
+    channels_last: this package's network and its input in torch.channels_last (the layout train.bench_wrn runs in):
+    SelfNorm sites through the NHWC kernels, batch norm through cuDNN's NHWC kernels, a site whose CrossNorm fires
+    through the NCHW kernels and back."""
     import cnsn_b200
     import cnsn_b200.cnsn as M
     from cnsn_b200.hosts import WideResNet
@@ -137,6 +141,8 @@ def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site):
     t.load_state_dict(a.state_dict())
     b = WideResNet(40, 10, fuse_post=fuse_post, **kw).to(DEV).train()
     b.load_state_dict(a.state_dict())
+    if channels_last:
+        b = b.to(memory_format=torch.channels_last)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(64, 3, 32, 32, generator=g).to(DEV)
     y = torch.randint(0, 10, (64,), generator=g).to(DEV)
@@ -144,7 +150,10 @@ def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site):
     def fwd(net):
         torch.manual_seed(5)
         np.random.seed(6)
-        logits = net(x.to(next(net.parameters()).dtype), aug=aug)
+        xin = x.to(next(net.parameters()).dtype)
+        if channels_last and net is b:
+            xin = xin.contiguous(memory_format=torch.channels_last)
+        logits = net(xin, aug=aug)
         return logits, F.cross_entropy(logits, y)
 
     outs = []
@@ -160,7 +169,7 @@ def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site):
         M.CNSN.fuse_site = True
     # 18 sites, one kernel per direction each (sites where CrossNorm fires unfused: two)
     assert launched >= 36, launched
-    _compare("wrn40_2 aug=%s fuse_post=%s fuse_site=%s vs %s" % (aug, fuse_post, fuse_site, label),
+    _compare("wrn40_2 aug=%s fuse_post=%s fuse_site=%s channels_last=%s vs %s" % (aug, fuse_post, fuse_site, channels_last, label),
              (t, outs[0]), (a, outs[1]), (b, outs[2]))
 
 

@@ -21,6 +21,8 @@ if cl:
     net = net.to(memory_format=torch.channels_last)
 opt, sched = make_optimizer(net, 100)
 x = torch.randn(512, 3, 32, 32, device=dev)
+if cl:
+    x = x.contiguous(memory_format=torch.channels_last)
 y = torch.randint(0, 10, (512,), device=dev)
 
 
@@ -42,8 +44,17 @@ for _ in range(10):
 t1.record()
 torch.cuda.synchronize()
 print("cudnn.benchmark=%s channels_last=%s : %.2f ms/step (no CrossNorm steps)" % (bench, cl, t0.elapsed_time(t1) / 10))
+for _ in range(3):
+    step(True)
+torch.cuda.synchronize()
+t0.record()
+for _ in range(10):
+    step(True)
+t1.record()
+torch.cuda.synchronize()
+print("cudnn.benchmark=%s channels_last=%s : %.2f ms/step (eager steps WITH CrossNorm at 2 sites)" % (bench, cl, t0.elapsed_time(t1) / 10))
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
-        step()
+        step(len(sys.argv) > 3 and sys.argv[3] == "aug")
     torch.cuda.synchronize()
 print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=90))
