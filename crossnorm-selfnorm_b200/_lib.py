@@ -73,6 +73,13 @@ SIGNATURES = {
                                              c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
     "cnsn_selfnorm_block_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS, POINTER(GateParams),
                                              c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
+    "cnsn_bn_nhwc_supported": (c_int, [c_int, *_DIMS]),
+    "cnsn_bn_nhwc_save_floats": (c_size_t, [c_int, *_DIMS]),
+    "cnsn_bn_nhwc_workspace_floats": (c_size_t, [c_int, *_DIMS]),
+    "cnsn_bn_nhwc_fwd": (c_int, [c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_bn_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_int, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),
@@ -404,6 +411,38 @@ class CudaBackend:
             _check(fn(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
                       ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg), _p(ws), _stream(z)))
         return dz, out_g
+
+    # -- channels-last BatchNorm2d [+ ReLU] -------------------------------------------------------
+    @staticmethod
+    def bn_nhwc_ok(x):
+        """x is a dense channels_last tensor the NHWC batch-norm kernels take."""
+        if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+            return False
+        N, C, H, W = x.shape
+        return x.data_ptr() % 16 == 0 and bool(_size("cnsn_bn_nhwc_supported", _dtype_code(x), N, C, H, W))
+
+    def bn_nhwc_fwd(self, x, weight, bias, run_mean, run_var, nbt, training, relu, momentum, eps):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        save = torch.empty(_size("cnsn_bn_nhwc_save_floats", _dtype_code(x), N, C, H, W), dtype=torch.float32, device=x.device)
+        y = torch.empty_like(x)
+        with _on(x.device):
+            _check(lib().cnsn_bn_nhwc_fwd(_p(x), _p(y), _dtype_code(x), N, C, H, W, _p(weight), _p(bias), _p(run_mean), _p(run_var),
+                                          _p(nbt) if nbt is not None else None, int(training), int(relu), momentum, eps,
+                                          _p(save), _stream(x)))
+        return y, save
+
+    def bn_nhwc_bwd(self, x, dy, weight, training, relu, save):
+        _require_cuda(x, dy)
+        N, C, H, W = x.shape
+        dev = x.device
+        pg = torch.empty(2 * C, dtype=torch.float32, device=dev)
+        ws = torch.empty(_size("cnsn_bn_nhwc_workspace_floats", _dtype_code(x), N, C, H, W), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        with _on(dev):
+            _check(lib().cnsn_bn_nhwc_bwd(_p(x), _p(dy), _p(dx), _dtype_code(x), N, C, H, W, _p(weight), int(training), int(relu),
+                                          _p(save), _p(pg[:C]), _p(pg[C:]), _p(ws), _stream(x)))
+        return dx, pg[:C], pg[C:]
 
     @staticmethod
     def is_nhwc(x):

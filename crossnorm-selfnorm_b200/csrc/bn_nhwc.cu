@@ -1,0 +1,342 @@
+// bn_nhwc.cu -- BatchNorm2d (+ the ReLU that follows it in the host blocks) on CHANNELS-LAST tensors: logical shape
+// (N, C, H, W), memory order N, H, W, C.  The batch-norm side of cnsn_ibn_* (half = 0: every channel batch norm,
+// models/imagenet/resnet_ibn_cnsn.py:24-44 / nn.BatchNorm2d semantics) for a network that keeps its activations in the
+// layout cuDNN's convolutions work in (see selfnorm_nhwc.cu for why).
+//
+// In NHWC the tensor is a matrix [R = N*H*W rows][C columns] and a channel is a column of it:
+//   forward : k_bn_nhwc_stats   CTA (chunk, channel block): one pass over its rows, per-thread shifted sums (shift = the
+//                               thread's first element, so the sums stay small), merged (Chan) over the CTA's row lanes
+//                               -> one (mean, M2) pair per chunk and channel
+//             k_bn_nhwc_fold    one warp per channel: Chan merge of the chunk pairs in double -> batch mean / rstd,
+//                               running statistics, the two coefficients of y = scale * x + shift
+//             k_bn_nhwc_apply   y = relu?(scale * x + shift), coefficients in registers (a thread's channels never change)
+//   backward: k_bn_nhwc_reduce  per chunk and channel (sum d, sum d * xhat), d = dy masked where the forward output was
+//                               <= 0 (rebuilt from x with the forward's own coefficients: same fp32 expressions, same bits)
+//             k_bn_nhwc_fold_bwd  dgamma, dbeta, and the coefficients of dx = ca * d + cb * x + cc
+//             k_bn_nhwc_apply   dx
+// Algorithmic bytes 2 S forward, 3 S backward; moved: one more read of x (forward) / x and dy (backward), served by L2
+// when the tensor fits (16-64 MB at the WideResNet sites against 126 MB).  Eval mode: running statistics, fold + apply.
+#include <stdio.h>
+
+#include <algorithm>
+
+#include "flow_common.cuh"
+
+namespace cnsn {
+namespace bnl {
+
+constexpr int kT = 256;
+
+struct Geom {
+    long long R;       // rows = N * H * W
+    int C;
+    int CG;            // 16-byte vectors per row
+    int CGB;           // vectors per row handled by one CTA (channel block); CG % CGB == 0
+    int RL;            // row lanes = kT / CGB
+    int G;             // row chunks
+    long long rows;    // rows per chunk
+};
+
+__device__ __forceinline__ double shfl_xor_d(double v, int o) { return __shfl_xor_sync(0xffffffffu, v, o); }
+
+template <typename T>
+__global__ void __launch_bounds__(kT) k_bn_nhwc_stats(const T* __restrict__ x, const Geom g, float2* __restrict__ part) {
+    constexpr int V = VecOf<T>::n;
+    extern __shared__ float sm[];                            // mean [RL][CGB*V] | m2 [RL][CGB*V]
+    const int W = g.CGB * V;                                 // channels of this CTA
+    float* s_mean = sm;
+    float* s_m2 = sm + g.RL * W;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
+    const long long row0 = (long long)blockIdx.x * g.rows;
+    const long long nrows = min(g.rows, g.R - row0);
+    const uint4* vx = reinterpret_cast<const uint4*>(x) + (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
+    float k[V], s1[V], s2[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { k[e] = 0.f; s1[e] = 0.f; s2[e] = 0.f; }
+    if (rl < nrows) unpack<T>(__ldg(vx + (size_t)rl * g.CG), k);
+    int nt = 0;
+#pragma unroll 8
+    for (long long r = rl; r < nrows; r += g.RL) {
+        float a[V];
+        unpack<T>(__ldg(vx + (size_t)r * g.CG), a);
+#pragma unroll
+        for (int e = 0; e < V; ++e) { const float d = a[e] - k[e]; s1[e] += d; s2[e] = fmaf(d, d, s2[e]); }
+        ++nt;
+    }
+    const float inv = nt ? 1.f / nt : 0.f;
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        s_mean[rl * W + cg * V + e] = k[e] + s1[e] * inv;
+        s_m2[rl * W + cg * V + e] = fmaxf(s2[e] - s1[e] * s1[e] * inv, 0.f);
+    }
+    __syncthreads();
+    // merge the row lanes (lane l holds ceil((nrows - l) / RL) rows): mean = sum n_l m_l / n, M2 = sum (M2_l + n_l (m_l - mean)^2);
+    // double accumulators, no division inside the loops
+    const int nbase = (int)(nrows / g.RL), nrem = (int)(nrows - (long long)nbase * g.RL);      // lane l: nbase + (l < nrem) rows
+    for (int c = threadIdx.x; c < W; c += kT) {
+        double sm1 = 0.0;
+        for (int l = 0; l < g.RL; ++l) sm1 += (double)(nbase + (l < nrem)) * (double)s_mean[l * W + c];
+        const double m = sm1 / (double)nrows;
+        double q = 0.0;
+        for (int l = 0; l < g.RL; ++l) {
+            const double d = (double)s_mean[l * W + c] - m;
+            q += (double)s_m2[l * W + c] + (double)(nbase + (l < nrem)) * d * d;
+        }
+        part[(size_t)blockIdx.x * g.C + (size_t)blockIdx.y * W + c] = make_float2((float)m, (float)q);
+    }
+}
+
+// one warp per channel.  training: merge the G chunk pairs; eval: the running statistics.
+__global__ void __launch_bounds__(kT) k_bn_nhwc_fold(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
+                                                     const float* __restrict__ beta, float* __restrict__ run_mean,
+                                                     float* __restrict__ run_var, long long* __restrict__ nbt, int training,
+                                                     float momentum, float eps, float* __restrict__ save_mean,
+                                                     float* __restrict__ save_rstd, float2* __restrict__ coef) {
+    const int c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= g.C) return;
+    float mean, rstd;
+    if (training) {
+        // mean = sum n_j m_j / R, M2 = sum (M2_j + n_j (m_j - mean)^2): two passes over the (L2-resident) chunk pairs
+        double s1 = 0.0;
+#pragma unroll 4
+        for (int j = lane; j < g.G; j += 32) {
+            const long long nj = min(g.rows, g.R - (long long)j * g.rows);
+            s1 += (double)nj * (double)__ldcg(part + (size_t)j * g.C + c).x;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s1 += shfl_xor_d(s1, o);
+        const double ma = s1 / (double)g.R;
+        double qa = 0.0;
+#pragma unroll 4
+        for (int j = lane; j < g.G; j += 32) {
+            const float2 p = __ldcg(part + (size_t)j * g.C + c);
+            const long long nj = min(g.rows, g.R - (long long)j * g.rows);
+            const double d = (double)p.x - ma;
+            qa += (double)p.y + (double)nj * d * d;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) qa += shfl_xor_d(qa, o);
+        const double cnt = (double)g.R;
+        mean = (float)ma;
+        const float var_b = (float)(qa / cnt);
+        rstd = 1.f / sqrtf(var_b + eps);
+        if (lane == 0) {
+            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
+            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(qa / (cnt - 1.0));
+            if (nbt && c == 0) *nbt += 1;
+        }
+    } else {
+        mean = run_mean[c];
+        rstd = 1.f / sqrtf(run_var[c] + eps);
+    }
+    if (lane == 0) {
+        save_mean[c] = mean; save_rstd[c] = rstd;
+        const float sc = rstd * gamma[c];
+        coef[c] = make_float2(sc, beta[c] - mean * sc);
+    }
+}
+
+// per chunk and channel: (sum d, sum d * xhat)
+template <typename T>
+__global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, const T* __restrict__ dy, const Geom g, int relu,
+                                                       const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
+                                                       const float2* __restrict__ coef, float2* __restrict__ part) {
+    constexpr int V = VecOf<T>::n;
+    extern __shared__ float sm[];                            // a [RL][W] | b [RL][W]
+    const int W = g.CGB * V;
+    float* s_a = sm;
+    float* s_b = sm + g.RL * W;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
+    const long long row0 = (long long)blockIdx.x * g.rows;
+    const long long nrows = min(g.rows, g.R - row0);
+    const size_t vb = (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
+    const uint4* vx = reinterpret_cast<const uint4*>(x) + vb;
+    const uint4* vd = reinterpret_cast<const uint4*>(dy) + vb;
+    const int c0 = blockIdx.y * W + cg * V;
+    float mean[V], rstd[V], fs[V], fb[V], a[V], b[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        mean[e] = save_mean[c0 + e]; rstd[e] = save_rstd[c0 + e];
+        const float2 f = coef[c0 + e];
+        fs[e] = f.x; fb[e] = f.y; a[e] = 0.f; b[e] = 0.f;
+    }
+#pragma unroll 4
+    for (long long r = rl; r < nrows; r += g.RL) {
+        float xv[V], dv[V];
+        unpack<T>(__ldg(vx + (size_t)r * g.CG), xv);
+        unpack<T>(__ldg(vd + (size_t)r * g.CG), dv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float d = (relu && !(fmaf(fs[e], xv[e], fb[e]) > 0.f)) ? 0.f : dv[e];
+            a[e] += d;
+            b[e] = fmaf(d, (xv[e] - mean[e]) * rstd[e], b[e]);
+        }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s_a[rl * W + cg * V + e] = a[e]; s_b[rl * W + cg * V + e] = b[e]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < W; c += kT) {
+        double ta = 0.0, tb = 0.0;
+        for (int l = 0; l < g.RL; ++l) { ta += (double)s_a[l * W + c]; tb += (double)s_b[l * W + c]; }
+        part[(size_t)blockIdx.x * g.C + (size_t)blockIdx.y * W + c] = make_float2((float)ta, (float)tb);
+    }
+}
+
+// one warp per channel: dbeta = sum d, dgamma = sum d * xhat; dx = ca * d + cb * x + cc
+__global__ void __launch_bounds__(kT) k_bn_nhwc_fold_bwd(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
+                                                         int training, const float* __restrict__ save_mean,
+                                                         const float* __restrict__ save_rstd, float* __restrict__ dgamma,
+                                                         float* __restrict__ dbeta, float* __restrict__ cdx) {
+    const int c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= g.C) return;
+    double ta = 0.0, tb = 0.0;
+#pragma unroll 4
+    for (int j = lane; j < g.G; j += 32) { const float2 p = __ldcg(part + (size_t)j * g.C + c); ta += (double)p.x; tb += (double)p.y; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { ta += shfl_xor_d(ta, o); tb += shfl_xor_d(tb, o); }
+    if (lane == 0) {
+        dbeta[c] = (float)ta; dgamma[c] = (float)tb;
+        const float inv = training ? 1.f / (float)g.R : 0.f;     // eval: the statistics are constants, nothing to remove
+        const float ma = (float)ta * inv, mb = (float)tb * inv;
+        const float mean = save_mean[c], rstd = save_rstd[c];
+        const float ca = gamma[c] * rstd;
+        const float cb = -ca * mb * rstd;
+        cdx[c] = ca; cdx[g.C + c] = cb; cdx[2 * g.C + c] = -ca * ma - cb * mean;
+    }
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(kT) k_bn_nhwc_apply(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
+                                                      int relu, const float2* __restrict__ coef, const float* __restrict__ cdx) {
+    constexpr int V = VecOf<T>::n;
+    const int W = g.CGB * V;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
+    const long long row0 = (long long)blockIdx.x * g.rows;
+    const long long nrows = min(g.rows, g.R - row0);
+    const size_t vb = (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
+    const uint4* vx = reinterpret_cast<const uint4*>(x) + vb;
+    const uint4* vd = reinterpret_cast<const uint4*>(dy) + vb;
+    uint4* vo = reinterpret_cast<uint4*>(out) + vb;
+    const int c0 = blockIdx.y * W + cg * V;
+    float fs[V], fb[V], ca[V], cb[V], cc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+        const float2 f = coef[c0 + e];
+        fs[e] = f.x; fb[e] = f.y;
+        ca[e] = BWD ? cdx[c0 + e] : 0.f; cb[e] = BWD ? cdx[g.C + c0 + e] : 0.f; cc[e] = BWD ? cdx[2 * g.C + c0 + e] : 0.f;
+    }
+#pragma unroll 4
+    for (long long r = rl; r < nrows; r += g.RL) {
+        float xv[V], dv[V], o[V];
+        unpack<T>(ldg_stream(vx + (size_t)r * g.CG), xv);
+        if (BWD) unpack<T>(ldg_stream(vd + (size_t)r * g.CG), dv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float y = fmaf(fs[e], xv[e], fb[e]);
+            if (BWD) {
+                const float d = (relu && !(y > 0.f)) ? 0.f : dv[e];
+                o[e] = fmaf(ca[e], d, fmaf(cb[e], xv[e], cc[e]));
+            } else {
+                o[e] = relu ? fmaxf(y, 0.f) : y;
+            }
+        }
+        vo[(size_t)r * g.CG] = pack<T>(o);
+    }
+}
+
+constexpr int kMaxChunks = 2048;
+
+static int make_geom(Geom& g, int dtype, int N, int C, int H, int W) {
+    const int esz = (int)esize(dtype);
+    if (((size_t)C * esz) % 16) return CNSN_E_UNSUPPORTED;
+    g.R = (long long)N * H * W;
+    g.C = C;
+    g.CG = C * esz / 16;
+    g.CGB = std::min(g.CG, kT);
+    if (kT % g.CGB || g.CG % g.CGB) return CNSN_E_UNSUPPORTED;
+    if (g.R < 2) return CNSN_E_UNSUPPORTED;
+    g.RL = kT / g.CGB;
+    const int cblocks = g.CG / g.CGB;
+    // about 4 CTAs per SM over all channel blocks, at least 4 rows per row lane, at most kMaxChunks chunks
+    long long G = std::max<long long>(1, (148 * 4) / cblocks);
+    G = std::min<long long>(G, std::max<long long>(1, g.R / (4 * g.RL)));
+    G = std::min<long long>(G, kMaxChunks);
+    g.rows = (g.R + G - 1) / G;
+    g.G = (int)((g.R + g.rows - 1) / g.rows);
+    return 0;
+}
+static size_t smem_bytes(const Geom& g, int dtype) { return 2 * (size_t)g.RL * g.CGB * (16 / esize(dtype)) * sizeof(float); }
+
+}  // namespace bnl
+}  // namespace cnsn
+
+using namespace cnsn;
+
+extern "C" int cnsn_bn_nhwc_supported(int dtype, int N, int C, int H, int W) {
+    bnl::Geom g{};
+    if (check_dims(N, C, H, W) || dtype < CNSN_F32 || dtype > CNSN_F16) return 0;
+    return bnl::make_geom(g, dtype, N, C, H, W) == 0;
+}
+// save: [mean C | rstd C | (scale, shift) 2 C | chunk pairs 2 * kMaxChunks' worth at most: 2 G C]
+extern "C" size_t cnsn_bn_nhwc_save_floats(int dtype, int N, int C, int H, int W) {
+    bnl::Geom g{};
+    const size_t G = bnl::make_geom(g, dtype, N, C, H, W) ? 1 : (size_t)g.G;
+    return 4 * (size_t)C + 2 * G * C + 2;
+}
+// workspace: [chunk pairs 2 G C | (ca, cb, cc) 3 C]
+extern "C" size_t cnsn_bn_nhwc_workspace_floats(int dtype, int N, int C, int H, int W) {
+    bnl::Geom g{};
+    const size_t G = bnl::make_geom(g, dtype, N, C, H, W) ? 1 : (size_t)g.G;
+    return 2 * G * C + 3 * (size_t)C + 2;
+}
+
+extern "C" int cnsn_bn_nhwc_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                                const float* gamma, const float* beta, float* run_mean, float* run_var, long long* nbt,
+                                int training, int relu, float momentum, float eps, float* save, void* stream) {
+    if (!x || !y || !gamma || !beta || !run_mean || !run_var || !save || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    if (!aligned16(x) || !aligned16(y)) return CNSN_E_ALIGN;
+    if (training && (long long)N * H * W < 2) return CNSN_E_BATCH1;
+    bnl::Geom g{};
+    int rc = bnl::make_geom(g, dtype, N, C, H, W);
+    if (rc) return rc;
+    float* mean = save; float* rstd = save + C;
+    float2* coef = reinterpret_cast<float2*>(save + 2 * (size_t)C);
+    float2* part = reinterpret_cast<float2*>(save + 4 * (size_t)C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 grid((unsigned)g.G, (unsigned)(g.CG / g.CGB));
+    if (training) {
+        CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_stats<T><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>((const T*)x, g, part)));
+        if ((rc = launch_status())) return rc;
+    }
+    bnl::k_bn_nhwc_fold<<<(C + 7) / 8, bnl::kT, 0, s>>>(part, g, gamma, beta, run_mean, run_var, nbt, training, momentum, eps, mean, rstd, coef);
+    if ((rc = launch_status())) return rc;
+    CNSN_DISPATCH_DTYPE(dtype, T,
+        (bnl::k_bn_nhwc_apply<T, false><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, relu ? 1 : 0, coef, nullptr)));
+    return launch_status();
+}
+
+extern "C" int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                                const float* gamma, int training, int relu, const float* save,
+                                float* dgamma, float* dbeta, float* workspace, void* stream) {
+    if (!x || !dy || !dx || !gamma || !save || !dgamma || !dbeta || !workspace || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    if (!aligned16(x) || !aligned16(dy) || !aligned16(dx)) return CNSN_E_ALIGN;
+    bnl::Geom g{};
+    int rc = bnl::make_geom(g, dtype, N, C, H, W);
+    if (rc) return rc;
+    const float* mean = save; const float* rstd = save + C;
+    const float2* coef = reinterpret_cast<const float2*>(save + 2 * (size_t)C);
+    float2* part = reinterpret_cast<float2*>(workspace);
+    float* cdx = workspace + 2 * (size_t)g.G * C;
+    cudaStream_t s = (cudaStream_t)stream;
+    const dim3 grid((unsigned)g.G, (unsigned)(g.CG / g.CGB));
+    CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_reduce<T><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>(
+        (const T*)x, (const T*)dy, g, relu ? 1 : 0, mean, rstd, coef, part)));
+    if ((rc = launch_status())) return rc;
+    bnl::k_bn_nhwc_fold_bwd<<<(C + 7) / 8, bnl::kT, 0, s>>>(part, g, gamma, training, mean, rstd, dgamma, dbeta, cdx);
+    if ((rc = launch_status())) return rc;
+    CNSN_DISPATCH_DTYPE(dtype, T,
+        (bnl::k_bn_nhwc_apply<T, true><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, relu ? 1 : 0, coef, cdx)));
+    return launch_status();
+}

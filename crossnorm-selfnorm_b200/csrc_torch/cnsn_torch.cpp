@@ -367,6 +367,44 @@ struct IbnNode : public torch::autograd::Function<IbnNode> {
     }
 };
 
+// ---- channels-last BatchNorm2d [+ ReLU] (cnsn_bn_nhwc_fwd/_bwd) -----------------------------------------------------------
+struct BnNhwcNode : public torch::autograd::Function<BnNhwcNode> {
+    static at::Tensor forward(AutogradContext* ctx, const at::Tensor& x, bool training, bool relu, double momentum, double eps,
+                              GateBufs bufs, const at::Tensor& weight, const at::Tensor& bias) {
+        const c10::cuda::CUDAGuard guard(x.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+        at::Tensor save = f32_buffer(x, (int64_t)cnsn_bn_nhwc_save_floats(dtype_code(x), N, C, H, W));
+        at::Tensor y = at::empty_like(x);
+        check(cnsn_bn_nhwc_fwd(x.data_ptr(), y.data_ptr(), dtype_code(x), N, C, H, W, weight.data_ptr<float>(), bias.data_ptr<float>(),
+                               bufs.run_mean.data_ptr<float>(), bufs.run_var.data_ptr<float>(),
+                               bufs.nbt.defined() ? reinterpret_cast<long long*>(bufs.nbt.data_ptr<int64_t>()) : nullptr,
+                               training ? 1 : 0, relu ? 1 : 0, (float)momentum, (float)eps, save.data_ptr<float>(), stream));
+        ctx->save_for_backward({x, weight, save});
+        ctx->saved_data["training"] = training;
+        ctx->saved_data["relu"] = relu;
+        return y;
+    }
+
+    static variable_list backward(AutogradContext* ctx, variable_list grads) {
+        const auto saved = ctx->get_saved_variables();
+        const at::Tensor &x = saved[0], &weight = saved[1], &save = saved[2];
+        const bool training = ctx->saved_data["training"].toBool(), relu = ctx->saved_data["relu"].toBool();
+        const at::Tensor dy = grads[0].contiguous(at::MemoryFormat::ChannelsLast);
+        const c10::cuda::CUDAGuard guard(x.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+        at::Tensor pg = f32_buffer(x, 2 * (int64_t)C);                // dgamma | dbeta
+        at::Tensor ws = f32_buffer(x, (int64_t)cnsn_bn_nhwc_workspace_floats(dtype_code(x), N, C, H, W));
+        at::Tensor dx = at::empty_like(x);
+        float* g = pg.data_ptr<float>();
+        check(cnsn_bn_nhwc_bwd(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), dtype_code(x), N, C, H, W, weight.data_ptr<float>(),
+                               training ? 1 : 0, relu ? 1 : 0, save.data_ptr<float>(), g, g + C, ws.data_ptr<float>(), stream));
+        at::Tensor none;
+        return {dx, none, none, none, none, none, pg.narrow(0, 0, C), pg.narrow(0, C, C)};
+    }
+};
+
 void check_gate(const at::Tensor& x, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta, const GateBufs& b) {
     const int64_t C = x.size(1);
     for (const at::Tensor* t : {&w, &gamma, &beta, &b.run_mean, &b.run_var}) {
@@ -400,6 +438,19 @@ at::Tensor site(const at::Tensor& x, const std::vector<int64_t>& cwin, const std
     GateBufs b{run_mean, run_var, nbt.has_value() ? *nbt : at::Tensor()};
     check_gate(x, w, gamma, beta, b);
     return SiteNode::apply(x, window(cwin), window(swin), lam, cn_eps, relu, w, gamma, beta, b, momentum, bn_eps, sn_eps);
+}
+
+at::Tensor bn_nhwc(const at::Tensor& x, bool training, bool relu, double momentum, double eps, const at::Tensor& run_mean,
+                   const at::Tensor& run_var, const c10::optional<at::Tensor>& nbt, const at::Tensor& weight, const at::Tensor& bias) {
+    require_cuda4(x);
+    TORCH_CHECK(is_channels_last(x) && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15u) == 0, "bn_nhwc: x must be a dense, 16-byte aligned channels_last tensor");
+    const int64_t C = x.size(1);
+    for (const at::Tensor* t : {&weight, &bias, &run_mean, &run_var}) {
+        TORCH_CHECK(t->defined() && t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() == C &&
+                    t->device() == x.device(), "bn_nhwc: weight, bias and running statistics must be fp32 [C] on x's device");
+    }
+    GateBufs b{run_mean, run_var, nbt.has_value() ? *nbt : at::Tensor()};
+    return BnNhwcNode::apply(x, training, relu, momentum, eps, b, weight, bias);
 }
 
 bool site_supported(const at::Tensor& x) {
@@ -443,4 +494,5 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("site_supported", &site_supported);
     m.def("ibn", &ibn, "IBN / InstanceNorm2d (half == C) / BatchNorm2d (half == 0), one kernel per direction (resnet_ibn_cnsn.py:24-44)");
     m.def("ibn_resident", &ibn_resident);
+    m.def("bn_nhwc", &bn_nhwc, "nn.BatchNorm2d [+ ReLU] on a dense channels_last tensor, three kernels per direction (csrc/bn_nhwc.cu)");
 }

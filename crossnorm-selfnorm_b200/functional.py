@@ -217,3 +217,24 @@ class IbnFn(torch.autograd.Function):
         gi = (g[0].to(in_w.dtype), g[1].to(in_w.dtype)) if in_w is not None else (None, None)
         gb = (g[2].to(bn_w.dtype), g[3].to(bn_w.dtype)) if bn_w is not None else (None, None)   # half == C: no BN half
         return (dx, None, None, None, None, None, None) + gi + gb + (None,)
+
+
+class BnNhwcFn(torch.autograd.Function):
+    """nn.BatchNorm2d [+ ReLU] on a dense channels_last tensor (cnsn_bn_nhwc_fwd / _bwd, csrc/bn_nhwc.cu); output and input
+    gradient stay channels_last.  Saved for backward: x and O(C) fp32 statistics (not the normalised tensor, not the mask)."""
+
+    @staticmethod
+    def forward(ctx, x, training, relu, momentum, eps, bufs, weight, bias):
+        y, save = _lib.backend().bn_nhwc_fwd(x, weight, bias, bufs[0], bufs[1], bufs[2], training, relu, momentum, eps)
+        ctx.save_for_backward(x, weight)
+        ctx.bn = (training, bool(relu), save)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        training, relu, save = ctx.bn
+        if not dy.is_contiguous(memory_format=torch.channels_last):
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        dx, dw, db = _lib.backend().bn_nhwc_bwd(x, dy, weight, training, relu, save)
+        return dx, None, None, None, None, None, dw, db

@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .functional import IbnFn
+from .functional import BnNhwcFn, IbnFn
 
 
 def bn_momentum(bn):
@@ -92,6 +92,17 @@ class BatchNorm2d(nn.BatchNorm2d):
                 return IbnFn.apply(x, 0, training, momentum, 1e-5, float(self.eps),
                                    (self.running_mean, self.running_var, self.num_batches_tracked),
                                    None, None, self.weight, self.bias, bool(relu))
+        if (x.is_cuda and x.dim() == 4 and not x.is_contiguous() and self.affine and self.track_running_stats
+                and self.weight.dtype is torch.float32 and x.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+            be = _lib.backend()                       # channels_last: the NHWC kernels (csrc/bn_nhwc.cu), same fused ReLU
+            if getattr(be, "name", "") == "cuda" and be.bn_nhwc_ok(x):
+                momentum = bn_momentum(self)
+                ext = _lib.fast_binding()
+                if ext is not None:
+                    return ext.bn_nhwc(x, self.training, bool(relu), momentum, float(self.eps), self.running_mean, self.running_var,
+                                       self.num_batches_tracked, self.weight, self.bias)
+                return BnNhwcFn.apply(x, self.training, bool(relu), momentum, float(self.eps),
+                                      (self.running_mean, self.running_var, self.num_batches_tracked), self.weight, self.bias)
         y = super().forward(x)
         return torch.relu_(y) if relu else y
 

@@ -309,6 +309,22 @@ int cnsn_ibn_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int 
                  float* d_in_w, float* d_in_b, float* d_bn_w, float* d_bn_b,
                  float* workspace, void* stream);
 
+/* Channels-last (NHWC) BatchNorm2d [+ ReLU]: cnsn_ibn_fwd / _bwd with half = 0 on tensors whose logical shape is
+ * (N, C, H, W) and whose memory order is N, H, W, C (torch.channels_last, dense); nn.BatchNorm2d semantics (batch
+ * statistics when training, biased variance to normalise, unbiased into run_var; running statistics in eval mode),
+ * `relu`: y = max(y, 0) forward, dy masked where y <= 0 backward (y rebuilt from x).  gamma, beta, run_mean, run_var,
+ * dgamma, dbeta: fp32 [C].  C * sizeof(T) must be a multiple of 16 that divides, or is a multiple of, 4096
+ * (cnsn_bn_nhwc_supported); base pointers 16-byte aligned.  save is written by forward and read by backward. */
+int cnsn_bn_nhwc_supported(int dtype, int N, int C, int H, int W);
+size_t cnsn_bn_nhwc_save_floats(int dtype, int N, int C, int H, int W);
+size_t cnsn_bn_nhwc_workspace_floats(int dtype, int N, int C, int H, int W);
+int cnsn_bn_nhwc_fwd(const void* x, void* y, int dtype, int N, int C, int H, int W,
+                     const float* gamma, const float* beta, float* run_mean, float* run_var, long long* nbt,
+                     int training, int relu, float momentum, float eps, float* save, void* stream);
+int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dtype, int N, int C, int H, int W,
+                     const float* gamma, int training, int relu, const float* save,
+                     float* dgamma, float* dbeta, float* workspace, void* stream);
+
 /* ---------------------------------------------------------------- JSD consistency -----------
  * The Jensen-Shannon consistency term of the 3-view steps, imagenet.py:367-376 / cifar.py:173-182:
  *   p_v = softmax(logits_v); lm = log(clamp(mean_v p_v, 1e-7, 1));

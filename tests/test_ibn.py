@@ -359,3 +359,67 @@ def test_batchnorm2d_fused_relu_matches_torch(shape, dtype, training, binding):
             a, b = a[clear], b[clear]
         err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-12))
         assert err <= tol, (name, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((64, 32, 32, 32), torch.float32), ((32, 64, 16, 16), torch.float32), ((16, 128, 8, 8), torch.float32),
+                                         ((8, 16, 20, 20), torch.float32), ((6, 8, 50, 50), torch.float32), ((32, 32, 32, 32), torch.bfloat16),
+                                         ((4, 2048, 7, 7), torch.float32), ((3, 64, 13, 11), torch.float16), ((8, 24, 9, 9), torch.float32),
+                                         ((16, 256, 56, 56), torch.bfloat16)])
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("relu", [True, False])
+@pytest.mark.parametrize("binding", ["ext", "ctypes"])
+def test_batchnorm2d_channels_last_matches_torch(shape, dtype, training, relu, binding):
+    """[relu](bn(x)) on torch.channels_last tensors through cnsn_bn_nhwc_fwd / _bwd (csrc/bn_nhwc.cu) against torch's batch
+    norm [+ relu] in fp64: y, dx, dweight, dbias, running statistics, num_batches_tracked; outputs stay channels_last.
+    (4,2048,7,7): two channel blocks per row; (8,24,9,9): 96-byte pixels -- torch's own kernels take it."""
+    import torch.nn as nn
+    import cnsn_b200._lib as L
+    from cnsn_b200.ibn import BatchNorm2d
+    dev = "cuda:0"
+    cl = torch.channels_last
+    g = torch.Generator().manual_seed(0)
+    C = shape[1]
+    x0 = (torch.randn(shape, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g)) + 0.3 * torch.randn(1, C, 1, 1, generator=g)).to(dtype)
+    dy0 = torch.randn(shape, generator=g).to(dtype)
+    ref = nn.BatchNorm2d(C).to(dev).double().train(training)
+    ours = BatchNorm2d(C).to(dev).train(training)
+    with torch.no_grad():
+        ref.weight.copy_(torch.rand(C, generator=g) + 0.5)
+        ref.bias.copy_(torch.randn(C, generator=g) * 0.5)
+        ref.running_mean.copy_(torch.randn(C, generator=g) * 0.1)
+        ref.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    ours.load_state_dict({k: (v.float() if v.dtype.is_floating_point else v) for k, v in ref.state_dict().items()})
+    old = L.set_binding(binding)
+    try:
+        res = []
+        for m, dt in ((ref, torch.float64), (ours, dtype)):
+            x = x0.to(dev).to(dt).contiguous(memory_format=cl).requires_grad_(True)
+            n0 = L.launch_count()
+            if m is ref:
+                y = torch.relu(m(x)) if relu else m(x)
+            else:
+                y = m(x, relu)
+            y.backward(dy0.to(dev).to(dt).contiguous(memory_format=cl))
+            torch.cuda.synchronize()
+            launched = L.launch_count() - n0
+            res.append((y.detach().double(), x.grad.double(), m.weight.grad.double(), m.bias.grad.double(),
+                        m.running_mean.double(), m.running_var.double()))
+            assert int(m.num_batches_tracked) == (1 if training else 0)
+    finally:
+        L.set_binding(old)
+    x = x0.to(dev).to(dtype).contiguous(memory_format=cl)
+    if shape != (8, 24, 9, 9):
+        assert L.backend().bn_nhwc_ok(x)
+        assert launched == (6 if training else 5)          # statistics (training only), fold, apply | reduce, fold, apply
+        assert y.is_contiguous(memory_format=cl)
+    tol = 1e-5 if dtype == torch.float32 else 1e-2
+    for name, a, b in zip(("y", "dx", "dweight", "dbias", "running_mean", "running_var"), res[0], res[1]):
+        if name == "dx" and relu:
+            xr = x0.to(dev).double()
+            pre = torch.nn.functional.batch_norm(xr, ref.running_mean if not training else None, ref.running_var if not training else None,
+                                                 ref.weight, ref.bias, training, 0.0, ref.eps)
+            clear = pre.abs() > (1e-4 if dtype == torch.float32 else 0.05)
+            a, b = a[clear], b[clear]
+        err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-12))
+        assert err <= tol, (name, err)

@@ -53,8 +53,8 @@ for _ in range(10):
 t1.record()
 torch.cuda.synchronize()
 print("cudnn.benchmark=%s channels_last=%s : %.2f ms/step (eager steps WITH CrossNorm at 2 sites)" % (bench, cl, t0.elapsed_time(t1) / 10))
-with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(3):
         step(len(sys.argv) > 3 and sys.argv[3] == "aug")
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=28, max_name_column_width=90))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=40, max_name_column_width=90))
