@@ -7,7 +7,7 @@
 //   forward : k_bn_nhwc_stats   CTA (chunk, channel block): one pass over its rows, per-thread shifted sums (shift = the
 //                               thread's first element, so the sums stay small), merged (Chan) over the CTA's row lanes
 //                               -> one (mean, M2) pair per chunk and channel
-//             k_bn_nhwc_fold    one warp per channel: Chan merge of the chunk pairs in double -> batch mean / rstd,
+//             k_bn_nhwc_fold    one CTA per channel: merge of the chunk pairs in double -> batch mean / rstd,
 //                               running statistics, the two coefficients of y = scale * x + shift
 //             k_bn_nhwc_apply   y = relu?(scale * x + shift), coefficients in registers (a thread's channels never change)
 //   backward: k_bn_nhwc_reduce  per chunk and channel (sum d, sum d * xhat), d = dy masked where the forward output was
@@ -86,41 +86,65 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_stats(const T* __restrict__ x, c
     }
 }
 
-// one warp per channel.  training: merge the G chunk pairs; eval: the running statistics.
-__global__ void __launch_bounds__(kT) k_bn_nhwc_fold(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
-                                                     const float* __restrict__ beta, float* __restrict__ run_mean,
-                                                     float* __restrict__ run_var, long long* __restrict__ nbt, int training,
-                                                     float momentum, float eps, float* __restrict__ save_mean,
-                                                     float* __restrict__ save_rstd, float2* __restrict__ coef) {
-    const int c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= g.C) return;
+constexpr int kFoldT = 128;
+// sum of v over the CTA's kFoldT threads, in double; every thread gets the total
+__device__ __forceinline__ double fold_sum(double v, double* sm) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += shfl_xor_d(v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFoldT / 32; ++w) t += sm[w];
+    return t;
+}
+
+// one CTA per channel.  training: merge the G chunk pairs -- mean = sum n_j m_j / R, M2 = sum (M2_j + n_j (m_j - mean)^2),
+// two passes over the (L2-resident) pairs held in registers; eval: the running statistics.
+__global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
+                                                         const float* __restrict__ beta, float* __restrict__ run_mean,
+                                                         float* __restrict__ run_var, long long* __restrict__ nbt, int training,
+                                                         float momentum, float eps, float* __restrict__ save_mean,
+                                                         float* __restrict__ save_rstd, float2* __restrict__ coef) {
+    __shared__ double sm[kFoldT / 32];
+    const int c = blockIdx.x;
     float mean, rstd;
     if (training) {
-        // mean = sum n_j m_j / R, M2 = sum (M2_j + n_j (m_j - mean)^2): two passes over the (L2-resident) chunk pairs
+        constexpr int kHold = 8;                             // G <= 592 in practice: every pair stays in registers
+        float2 hold[kHold];
         double s1 = 0.0;
-#pragma unroll 4
-        for (int j = lane; j < g.G; j += 32) {
-            const long long nj = min(g.rows, g.R - (long long)j * g.rows);
-            s1 += (double)nj * (double)__ldcg(part + (size_t)j * g.C + c).x;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s1 += shfl_xor_d(s1, o);
-        const double ma = s1 / (double)g.R;
+        for (int u = 0; u < kHold; ++u) {
+            const int j = threadIdx.x + u * kFoldT;
+            hold[u] = make_float2(0.f, 0.f);
+            if (j < g.G) {
+                hold[u] = __ldcg(part + (size_t)j * g.C + c);
+                s1 += (double)min(g.rows, g.R - (long long)j * g.rows) * (double)hold[u].x;
+            }
+        }
+        for (int j = threadIdx.x + kHold * kFoldT; j < g.G; j += kFoldT)
+            s1 += (double)min(g.rows, g.R - (long long)j * g.rows) * (double)__ldcg(part + (size_t)j * g.C + c).x;
+        const double ma = fold_sum(s1, sm) / (double)g.R;
         double qa = 0.0;
-#pragma unroll 4
-        for (int j = lane; j < g.G; j += 32) {
-            const float2 p = __ldcg(part + (size_t)j * g.C + c);
-            const long long nj = min(g.rows, g.R - (long long)j * g.rows);
-            const double d = (double)p.x - ma;
-            qa += (double)p.y + (double)nj * d * d;
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) qa += shfl_xor_d(qa, o);
+        for (int u = 0; u < kHold; ++u) {
+            const int j = threadIdx.x + u * kFoldT;
+            if (j < g.G) {
+                const double d = (double)hold[u].x - ma;
+                qa += (double)hold[u].y + (double)min(g.rows, g.R - (long long)j * g.rows) * d * d;
+            }
+        }
+        for (int j = threadIdx.x + kHold * kFoldT; j < g.G; j += kFoldT) {
+            const float2 p = __ldcg(part + (size_t)j * g.C + c);
+            const double d = (double)p.x - ma;
+            qa += (double)p.y + (double)min(g.rows, g.R - (long long)j * g.rows) * d * d;
+        }
+        qa = fold_sum(qa, sm);
         const double cnt = (double)g.R;
         mean = (float)ma;
-        const float var_b = (float)(qa / cnt);
-        rstd = 1.f / sqrtf(var_b + eps);
-        if (lane == 0) {
+        rstd = 1.f / sqrtf((float)(qa / cnt) + eps);
+        if (threadIdx.x == 0) {
             run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
             run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(qa / (cnt - 1.0));
             if (nbt && c == 0) *nbt += 1;
@@ -129,7 +153,7 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_fold(const float2* __restrict__ 
         mean = run_mean[c];
         rstd = 1.f / sqrtf(run_var[c] + eps);
     }
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
         save_mean[c] = mean; save_rstd[c] = rstd;
         const float sc = rstd * gamma[c];
         coef[c] = make_float2(sc, beta[c] - mean * sc);
@@ -182,19 +206,19 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, 
     }
 }
 
-// one warp per channel: dbeta = sum d, dgamma = sum d * xhat; dx = ca * d + cb * x + cc
-__global__ void __launch_bounds__(kT) k_bn_nhwc_fold_bwd(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
-                                                         int training, const float* __restrict__ save_mean,
-                                                         const float* __restrict__ save_rstd, float* __restrict__ dgamma,
-                                                         float* __restrict__ dbeta, float* __restrict__ cdx) {
-    const int c = blockIdx.x * (kT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (c >= g.C) return;
+// one CTA per channel: dbeta = sum d, dgamma = sum d * xhat; dx = ca * d + cb * x + cc
+__global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2* __restrict__ part, const Geom g, const float* __restrict__ gamma,
+                                                             int training, const float* __restrict__ save_mean,
+                                                             const float* __restrict__ save_rstd, float* __restrict__ dgamma,
+                                                             float* __restrict__ dbeta, float* __restrict__ cdx) {
+    __shared__ double sm[kFoldT / 32];
+    const int c = blockIdx.x;
     double ta = 0.0, tb = 0.0;
 #pragma unroll 4
-    for (int j = lane; j < g.G; j += 32) { const float2 p = __ldcg(part + (size_t)j * g.C + c); ta += (double)p.x; tb += (double)p.y; }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { ta += shfl_xor_d(ta, o); tb += shfl_xor_d(tb, o); }
-    if (lane == 0) {
+    for (int j = threadIdx.x; j < g.G; j += kFoldT) { const float2 p = __ldcg(part + (size_t)j * g.C + c); ta += (double)p.x; tb += (double)p.y; }
+    ta = fold_sum(ta, sm);
+    tb = fold_sum(tb, sm);
+    if (threadIdx.x == 0) {
         dbeta[c] = (float)ta; dgamma[c] = (float)tb;
         const float inv = training ? 1.f / (float)g.R : 0.f;     // eval: the statistics are constants, nothing to remove
         const float ma = (float)ta * inv, mb = (float)tb * inv;
@@ -309,7 +333,7 @@ extern "C" int cnsn_bn_nhwc_fwd(const void* x, void* y, int dtype, int N, int C,
         CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_stats<T><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>((const T*)x, g, part)));
         if ((rc = launch_status())) return rc;
     }
-    bnl::k_bn_nhwc_fold<<<(C + 7) / 8, bnl::kT, 0, s>>>(part, g, gamma, beta, run_mean, run_var, nbt, training, momentum, eps, mean, rstd, coef);
+    bnl::k_bn_nhwc_fold<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, beta, run_mean, run_var, nbt, training, momentum, eps, mean, rstd, coef);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T,
         (bnl::k_bn_nhwc_apply<T, false><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, relu ? 1 : 0, coef, nullptr)));
@@ -334,7 +358,7 @@ extern "C" int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dty
     CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_reduce<T><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>(
         (const T*)x, (const T*)dy, g, relu ? 1 : 0, mean, rstd, coef, part)));
     if ((rc = launch_status())) return rc;
-    bnl::k_bn_nhwc_fold_bwd<<<(C + 7) / 8, bnl::kT, 0, s>>>(part, g, gamma, training, mean, rstd, dgamma, dbeta, cdx);
+    bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, training, mean, rstd, dgamma, dbeta, cdx);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T,
         (bnl::k_bn_nhwc_apply<T, true><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, relu ? 1 : 0, coef, cdx)));

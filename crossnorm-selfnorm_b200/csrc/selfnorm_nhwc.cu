@@ -35,7 +35,8 @@ constexpr int kT = 256;
 struct Geom {
     int N, C, HW;
     int CG;            // 16-byte vectors per pixel
-    int RL;            // row lanes = kT / CG
+    int CGB;           // vectors per pixel handled by one CTA (channel block, blockIdx.y); CG % CGB == 0
+    int RL;            // row lanes = kT / CGB
     int S;             // slabs per sample
     int rows;          // pixels per slab (the last slab of a sample may be shorter)
 };
@@ -43,12 +44,13 @@ struct Geom {
 // Sum over the row lanes: v[e] of every thread -> column totals in s_col[C].  red: [RL][C] floats.
 template <int V>
 __device__ __forceinline__ void column_sums(const float (&v)[V], float* red, float* s_col, const Geom& g, int cg, int rl) {
+    const int W = g.CGB * V;                                 // channels of this CTA
 #pragma unroll
-    for (int e = 0; e < V; ++e) red[rl * g.C + cg * V + e] = v[e];
+    for (int e = 0; e < V; ++e) red[rl * W + cg * V + e] = v[e];
     __syncthreads();
-    for (int c = threadIdx.x; c < g.C; c += kT) {            // a serial chain of up to 128 terms: in double (C threads, once per pass)
+    for (int c = threadIdx.x; c < W; c += kT) {              // a serial chain of up to 128 terms: in double (W threads, once per pass)
         double s = 0.0;
-        for (int k = 0; k < g.RL; ++k) s += (double)red[k * g.C + c];
+        for (int k = 0; k < g.RL; ++k) s += (double)red[k * W + c];
         s_col[c] = (float)s;
     }
     __syncthreads();
@@ -62,14 +64,15 @@ __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, cons
                                                    unsigned* __restrict__ cnt, float* __restrict__ mu, float* __restrict__ sd) {
     constexpr int V = VecOf<T>::n;
     extern __shared__ float sm[];                            // red [RL][C] | col [C] | mean [C]
+    const int W = g.CGB * V, c0 = blockIdx.y * W;            // this CTA's channels: c0 .. c0 + W - 1
     float* red = sm;
-    float* s_col = sm + g.RL * g.C;
-    float* s_mean = s_col + g.C;
+    float* s_col = sm + g.RL * W;
+    float* s_mean = s_col + W;
     __shared__ unsigned s_last;
     const int n = blockIdx.x / g.S, s = blockIdx.x - n * g.S;
-    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
     const int row0 = s * g.rows, nrows = min(g.rows, g.HW - row0);
-    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + cg;
+    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + (size_t)blockIdx.y * g.CGB + cg;
     const uint4* vx = reinterpret_cast<const uint4*>(x) + vbase;
     const uint4* vr = reinterpret_cast<const uint4*>(res) + vbase;
     uint4* vz = reinterpret_cast<uint4*>(z) + vbase;
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, cons
         for (int e = 0; e < V; ++e) acc[e] += a[e];
     }
     column_sums<V>(acc, red, s_col, g, cg, rl);
-    for (int c = threadIdx.x; c < g.C; c += kT) s_mean[c] = s_col[c] / nrows;
+    for (int c = threadIdx.x; c < W; c += kT) s_mean[c] = s_col[c] / nrows;
     __syncthreads();
     float m[V];
 #pragma unroll
@@ -111,22 +114,22 @@ __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, cons
     column_sums<V>(acc, red, s_col, g, cg, rl);
     const float M = (float)g.HW;
     if (g.S == 1) {
-        for (int c = threadIdx.x; c < g.C; c += kT) {
-            mu[(size_t)n * g.C + c] = s_mean[c];
-            sd[(size_t)n * g.C + c] = sqrtf(s_col[c] / (M - 1.f) + eps);
+        for (int c = threadIdx.x; c < W; c += kT) {
+            mu[(size_t)n * g.C + c0 + c] = s_mean[c];
+            sd[(size_t)n * g.C + c0 + c] = sqrtf(s_col[c] / (M - 1.f) + eps);
         }
         return;
     }
-    float2* mine = part + ((size_t)n * g.S + s) * g.C;
-    for (int c = threadIdx.x; c < g.C; c += kT) mine[c] = make_float2(s_mean[c], s_col[c]);
+    float2* mine = part + ((size_t)n * g.S + s) * g.C + c0;
+    for (int c = threadIdx.x; c < W; c += kT) mine[c] = make_float2(s_mean[c], s_col[c]);
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(cnt + n, 1u) == (unsigned)(g.S - 1);
+    if (threadIdx.x == 0) s_last = atomicAdd(cnt + (size_t)n * gridDim.y + blockIdx.y, 1u) == (unsigned)(g.S - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const float2* all = part + (size_t)n * g.S * g.C;
-    for (int c = threadIdx.x; c < g.C; c += kT) {            // Chan merge in slab order, in double (O(N C S) work in all)
+    const float2* all = part + (size_t)n * g.S * g.C + c0;
+    for (int c = threadIdx.x; c < W; c += kT) {              // Chan merge in slab order, in double (O(N C S) work in all)
         double cnt_a = 0.0, mean = 0.0, m2 = 0.0;
         for (int k = 0; k < g.S; ++k) {
             const float2 p = __ldcg(all + (size_t)k * g.C + c);
@@ -136,8 +139,8 @@ __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, cons
             m2 += (double)p.y + d * d * (cnt_a * cnt_b / tot);
             cnt_a = tot;
         }
-        mu[(size_t)n * g.C + c] = (float)mean;
-        sd[(size_t)n * g.C + c] = sqrtf((float)(m2 / ((double)M - 1.0)) + eps);
+        mu[(size_t)n * g.C + c0 + c] = (float)mean;
+        sd[(size_t)n * g.C + c0 + c] = sqrtf((float)(m2 / ((double)M - 1.0)) + eps);
     }
 }
 
@@ -148,13 +151,14 @@ __global__ void __launch_bounds__(kT) k_nhwc_reduce_bwd(const T* __restrict__ z,
                                                         float* __restrict__ sxy) {
     constexpr int V = VecOf<T>::n;
     extern __shared__ float sm[];
+    const int W = g.CGB * V, c0 = blockIdx.y * W;
     float* red = sm;
-    float* s_col = sm + g.RL * g.C;
+    float* s_col = sm + g.RL * W;
     __shared__ unsigned s_last;
     const int n = blockIdx.x / g.S, s = blockIdx.x - n * g.S;
-    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
     const int row0 = s * g.rows, nrows = min(g.rows, g.HW - row0);
-    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + cg;
+    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + (size_t)blockIdx.y * g.CGB + cg;
     const uint4* vz = reinterpret_cast<const uint4*>(z) + vbase;
     const uint4* vd = reinterpret_cast<const uint4*>(dy) + vbase;
     float acc[V];
@@ -170,22 +174,22 @@ __global__ void __launch_bounds__(kT) k_nhwc_reduce_bwd(const T* __restrict__ z,
     }
     column_sums<V>(acc, red, s_col, g, cg, rl);
     if (g.S == 1) {
-        for (int c = threadIdx.x; c < g.C; c += kT) sxy[(size_t)n * g.C + c] = s_col[c];
+        for (int c = threadIdx.x; c < W; c += kT) sxy[(size_t)n * g.C + c0 + c] = s_col[c];
         return;
     }
-    float* mine = part + ((size_t)n * g.S + s) * g.C;
-    for (int c = threadIdx.x; c < g.C; c += kT) mine[c] = s_col[c];
+    float* mine = part + ((size_t)n * g.S + s) * g.C + c0;
+    for (int c = threadIdx.x; c < W; c += kT) mine[c] = s_col[c];
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(cnt + n, 1u) == (unsigned)(g.S - 1);
+    if (threadIdx.x == 0) s_last = atomicAdd(cnt + (size_t)n * gridDim.y + blockIdx.y, 1u) == (unsigned)(g.S - 1);
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    const float* all = part + (size_t)n * g.S * g.C;
-    for (int c = threadIdx.x; c < g.C; c += kT) {
+    const float* all = part + (size_t)n * g.S * g.C + c0;
+    for (int c = threadIdx.x; c < W; c += kT) {
         double t = 0.0;
         for (int k = 0; k < g.S; ++k) t += (double)__ldcg(all + (size_t)k * g.C + c);
-        sxy[(size_t)n * g.C + c] = (float)t;
+        sxy[(size_t)n * g.C + c0 + c] = (float)t;
     }
 }
 
@@ -196,16 +200,16 @@ __global__ void __launch_bounds__(kT) k_nhwc_apply(const T* __restrict__ z, cons
                                                    const float* __restrict__ cc) {
     constexpr int V = VecOf<T>::n;
     const int n = blockIdx.x / g.S, s = blockIdx.x - n * g.S;
-    const int cg = threadIdx.x % g.CG, rl = threadIdx.x / g.CG;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
     const int row0 = s * g.rows, nrows = min(g.rows, g.HW - row0);
-    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + cg;
+    const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + (size_t)blockIdx.y * g.CGB + cg;
     const uint4* vz = reinterpret_cast<const uint4*>(z) + vbase;
     const uint4* vd = reinterpret_cast<const uint4*>(dy) + vbase;
     uint4* vo = reinterpret_cast<uint4*>(out) + vbase;
     float kg[V], kb[V], kc[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        const size_t i = (size_t)n * g.C + cg * V + e;
+        const size_t i = (size_t)n * g.C + (size_t)blockIdx.y * g.CGB * V + cg * V + e;
         kg[e] = gate[i];
         kb[e] = BWD ? cb[i] : 0.f;
         kc[e] = BWD ? cc[i] : 0.f;
@@ -235,9 +239,10 @@ static int make_geom(Geom& g, int dtype, int N, int C, int H, int W) {
     if (((size_t)C * esz) % 16) return CNSN_E_UNSUPPORTED;
     g.N = N; g.C = C; g.HW = H * W;
     g.CG = C * esz / 16;
-    if (g.CG > kT || kT % g.CG) return CNSN_E_UNSUPPORTED;
+    g.CGB = std::min(g.CG, kT);
+    if (kT % g.CGB || g.CG % g.CGB) return CNSN_E_UNSUPPORTED;
     if (g.HW < 2) return CNSN_E_UNSUPPORTED;
-    g.RL = kT / g.CG;
+    g.RL = kT / g.CGB;
     // slabs of about 32 KB, at least one pixel per row lane and pass; enough CTAs to fill the GPU
     const size_t tile = (size_t)g.HW * C * esz;
     int S = (int)std::max<size_t>(1, tile / (32u << 10));
@@ -251,7 +256,11 @@ static int max_slabs(int dtype, int C, int H, int W) {
     Geom g{};
     return make_geom(g, dtype, 1, C, H, W) ? 1 : g.S;
 }
-static size_t smem_bytes(const Geom& g) { return ((size_t)g.RL * g.C + 2 * (size_t)g.C) * sizeof(float); }
+static size_t smem_bytes(const Geom& g, int dtype) {
+    const size_t W = (size_t)g.CGB * (16 / esize(dtype));
+    return ((size_t)g.RL * W + 2 * W) * sizeof(float);
+}
+static int channel_blocks(int dtype, int C) { return std::max(1, (int)(C * esize(dtype) / 16) / kT); }
 
 }  // namespace nhwc
 }  // namespace cnsn
@@ -261,12 +270,12 @@ using namespace cnsn;
 // save: [SaveLayout(N, C, one gate) | slab partials float2 [N][S][C] | counters [N]]
 extern "C" size_t cnsn_selfnorm_nhwc_save_floats(int dtype, int N, int C, int H, int W) {
     const size_t S = (size_t)nhwc::max_slabs(dtype, C, H, W);
-    return SaveLayout(N, C, false).total + 2 * (size_t)N * S * C + (size_t)N + 2;
+    return SaveLayout(N, C, false).total + 2 * (size_t)N * S * C + (size_t)N * nhwc::channel_blocks(dtype, C) + 2;
 }
 // workspace: [sxy | st (unused) | cb | cc : 4 N C | slab partials [N][S][C] | counters [N]]
 extern "C" size_t cnsn_selfnorm_nhwc_workspace_floats(int dtype, int N, int C, int H, int W) {
     const size_t S = (size_t)nhwc::max_slabs(dtype, C, H, W);
-    return 4 * (size_t)N * C + (size_t)N * S * C + (size_t)N + 2;
+    return 4 * (size_t)N * C + (size_t)N * S * C + (size_t)N * nhwc::channel_blocks(dtype, C) + 2;
 }
 extern "C" int cnsn_selfnorm_nhwc_supported(int dtype, int N, int C, int H, int W) {
     nhwc::Geom g{};
@@ -293,11 +302,11 @@ extern "C" int cnsn_selfnorm_block_fwd_nhwc(const void* x, const void* res, void
     unsigned* cnt = reinterpret_cast<unsigned*>(save + L.total + 2 * (size_t)N * gm.S * C);
     cudaStream_t s = (cudaStream_t)stream;
     if (gm.S > 1) {
-        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * sizeof(unsigned), s);
+        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * (gm.CG / gm.CGB) * sizeof(unsigned), s);
         if (e != cudaSuccess) return (int)e;
     }
-    const unsigned grid = (unsigned)((long long)N * gm.S);
-    const size_t smem = nhwc::smem_bytes(gm);
+    const dim3 grid((unsigned)((long long)N * gm.S), (unsigned)(gm.CG / gm.CGB));
+    const size_t smem = nhwc::smem_bytes(gm, dtype);
     CNSN_DISPATCH_DTYPE(dtype, T, {
         if (res) nhwc::k_nhwc_stats<T, true><<<grid, nhwc::kT, smem, s>>>((const T*)x, (const T*)res, (T*)z, gm, eps, part, cnt,
                                                                          save + L.mu, save + L.sd);
@@ -332,11 +341,11 @@ extern "C" int cnsn_selfnorm_block_bwd_nhwc(const void* z, const void* dy, void*
     unsigned* cnt = reinterpret_cast<unsigned*>(part + (size_t)N * gm.S * C);
     cudaStream_t s = (cudaStream_t)stream;
     if (gm.S > 1) {
-        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * sizeof(unsigned), s);
+        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * (gm.CG / gm.CGB) * sizeof(unsigned), s);
         if (e != cudaSuccess) return (int)e;
     }
-    const unsigned grid = (unsigned)((long long)N * gm.S);
-    const size_t smem = nhwc::smem_bytes(gm);
+    const dim3 grid((unsigned)((long long)N * gm.S), (unsigned)(gm.CG / gm.CGB));
+    const size_t smem = nhwc::smem_bytes(gm, dtype);
     CNSN_DISPATCH_DTYPE(dtype, T,
         (nhwc::k_nhwc_reduce_bwd<T><<<grid, nhwc::kT, smem, s>>>((const T*)z, (const T*)dy, gm, relu ? 1 : 0, part, cnt, sxy)));
     if ((rc = launch_status())) return rc;

@@ -274,7 +274,8 @@ def _broadcast_model(net, world):
                 dist.broadcast(t, 0)
 
 
-def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5, fuse_post=True, ops=None, graph=True):
+def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5, fuse_post=True, ops=None, graph=True,
+                   channels_last=None):
     """images/s of ResNet-50 + SelfNorm ('post') training with image-space CrossNorm on synthetic 224x224 data
     (BASELINE config 4: batch 256 per GPU, SGD lr 0.1 momentum 0.9 wd 1e-4; imagenet-scripts/run-cnsn.sh).
     graph: GraphedStep.step_image_cn -- the network's forward + loss + backward replayed from a CUDA graph on every step
@@ -288,13 +289,19 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
     torch.backends.cudnn.benchmark = True      # imagenet.py:534
     torch.manual_seed(1 + rank)
     np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
+    if channels_last is None:                  # default: on, with this package's operators (they have the NHWC kernels)
+        channels_last = ops.__name__.startswith("cnsn_b200")
     net = resnet50(fuse_post=fuse_post, ops=ops).to(dev).train()
+    if channels_last:                          # parameters and activations in the layout cuDNN's convolutions work in
+        net = net.to(memory_format=torch.channels_last)
     model = net
     _broadcast_model(net, world)
     if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
     opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(batch, 3, 224, 224, device=dev)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (batch,), device=dev)
     launches0 = _lib.launch_count()
     gs = GraphedStep(net, x, y, world, loss_fn=lambda n, xx, yy, aug: F.cross_entropy(n(xx, aug=False), yy)) if graph else None
@@ -331,6 +338,7 @@ def bench_resnet50(dev, world, rank, batch=256, steps=10, warmup=3, cn_prob=0.5,
             "final_loss": loss, "params": sum(p.numel() for p in net.parameters()),
             "graph": "CUDA graph for the network's forward + loss + backward on every step (image-space CrossNorm eager, in "
                      "front); one flat-buffer gradient all-reduce" if gs is not None and gs.graph is not None else "eager",
+            "memory_format": "channels_last" if channels_last else "contiguous (NCHW)",
             "cnsn_kernel_launches": _lib.launch_count() - launches0}
 
 
@@ -350,7 +358,8 @@ def resnet50_jsd_step(net, images_all, targets, opt, cn_prob, ops, jsd, beta=1, 
     return float(loss.detach())
 
 
-def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0.5, fuse_post=True, graph=True):
+def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0.5, fuse_post=True, graph=True,
+                       channels_last=True):
     """images/s (clean images: the step processes 3x as many views) of ResNet-50 + SelfNorm with the 3-view JSD
     consistency step, bf16 autocast (BASELINE config 5: 3 x 256 = 768 views per GPU).  graph: as bench_resnet50."""
     import torch.distributed as dist
@@ -361,12 +370,16 @@ def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0
     torch.manual_seed(1 + rank)
     np.random.seed(1)                          # one coin per step for all ranks, as in the reference's single process
     net = resnet50(fuse_post=fuse_post).to(dev).train()
+    if channels_last:
+        net = net.to(memory_format=torch.channels_last)
     model = net
     _broadcast_model(net, world)
     if world > 1 and not graph:
         model = nn.parallel.DistributedDataParallel(net, device_ids=[dev.index], broadcast_buffers=False)
     opt = torch.optim.SGD(model.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
     x = torch.randn(3 * batch, 3, 224, 224, device=dev)
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
     y = torch.randint(0, 1000, (batch,), device=dev)
     launches0 = _lib.launch_count()
 
@@ -409,6 +422,7 @@ def bench_resnet50_jsd(dev, world, rank, batch=256, steps=5, warmup=2, cn_prob=0
             "config": "resnet50 cnsn_type=sn pos=post, image-space CrossNorm cn_prob=%g, CE + 12 x JSD (cnsn_jsd kernels), SGD lr "
                       "0.1 momentum 0.9 wd 1e-4, synthetic 224x224, fuse_post=%s" % (cn_prob, bool(fuse_post)),
             "final_loss": loss, "cnsn_kernel_launches": _lib.launch_count() - launches0,
+            "memory_format": "channels_last" if channels_last else "contiguous (NCHW)",
             "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
 
 

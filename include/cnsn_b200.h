@@ -189,7 +189,7 @@ int cnsn_selfnorm_block_bwd(const void* z, const void* dy, void* dz, int relu, i
  * memory order is N, H, W, C (torch.channels_last, dense) -- what a network keeps its activations in when cuDNN's
  * NHWC convolutions are not to convert around every call.  Same arguments and results as cnsn_selfnorm_block_fwd /
  * _bwd (res = z = NULL, relu = 0 is the plain models/cnsn.py:130-150 SelfNorm); x, res, z, y (z, dy, dz) are all NHWC.
- * Base pointers must be 16-byte aligned and C * sizeof(T) a multiple of 16 that divides 4096
+ * Base pointers must be 16-byte aligned and C * sizeof(T) a multiple of 16 that divides, or is a multiple of, 4096
  * (cnsn_selfnorm_nhwc_supported), else CNSN_E_ALIGN / CNSN_E_UNSUPPORTED and the caller converts to NCHW.
  * save / workspace sizes are this form's own (they hold the per-slab partial statistics as well). */
 int cnsn_selfnorm_nhwc_supported(int dtype, int N, int C, int H, int W);

@@ -200,7 +200,7 @@ def test_selfnorm_block_fusion_vs_oracle(mod, shape, dtype, add, relu, training)
 NHWC_SHAPES = [((8, 32, 32, 32), torch.float32), ((6, 64, 16, 16), torch.float32), ((4, 128, 8, 8), torch.float32),
                ((5, 16, 20, 20), torch.float32), ((6, 8, 50, 50), torch.float32), ((4, 32, 32, 32), torch.bfloat16),
                ((4, 256, 56, 56), torch.float32), ((3, 64, 13, 11), torch.float16), ((3, 24, 9, 9), torch.float32),
-               ((130, 16, 8, 8), torch.float32)]
+               ((130, 16, 8, 8), torch.float32), ((4, 2048, 7, 7), torch.float32), ((6, 1024, 14, 14), torch.float32)]
 
 
 @pytest.mark.parametrize("shape,dtype", NHWC_SHAPES)

@@ -174,8 +174,8 @@ def test_wrn40_2_step_matches_reference(aug, fuse_post, fuse_site, channels_last
 
 
 @pytest.mark.parametrize("cn_image", [True, False])
-@pytest.mark.parametrize("fuse_post", [True, False])
-def test_resnet50_step_matches_reference(cn_image, fuse_post):
+@pytest.mark.parametrize("fuse_post,channels_last", [(True, False), (False, False), (True, True)])
+def test_resnet50_step_matches_reference(cn_image, fuse_post, channels_last):
     """BASELINE config 4: ResNet-50, cnsn_type='sn', pos='post' with image-space CrossNorm (imagenet.py:205-230,
     imagenet-scripts/run-cnsn.sh), SGD lr 0.1 momentum 0.9 wd 1e-4; batch 8 of synthetic 224x224 images (the 7x7
     stage then has N = 8 instances per channel: channel-group kernels)."""
@@ -189,6 +189,8 @@ def test_resnet50_step_matches_reference(cn_image, fuse_post):
     t.load_state_dict(a.state_dict())
     b = ResNet([3, 4, 6, 3], fuse_post=fuse_post, **kw).to(DEV).train()
     b.load_state_dict(a.state_dict())
+    if channels_last:                        # the layout the benchmark runs in: NHWC SelfNorm and batch-norm kernels
+        b = b.to(memory_format=torch.channels_last)
     g = torch.Generator().manual_seed(2)
     x = torch.randn(8, 3, 224, 224, generator=g).to(DEV)
     y = torch.randint(0, 1000, (8,), generator=g).to(DEV)
@@ -198,6 +200,8 @@ def test_resnet50_step_matches_reference(cn_image, fuse_post):
             torch.manual_seed(5)
             np.random.seed(6)
             xx = x.to(next(net.parameters()).dtype)
+            if channels_last and net is b:
+                xx = xx.contiguous(memory_format=torch.channels_last)
             images = ops.cn_op_2ins_space_chan(xx, beta=1, crop="both") if cn_image else xx     # imagenet.py:215
             logits = net(images, aug=False)
             return logits, F.cross_entropy(logits, y)
@@ -207,7 +211,8 @@ def test_resnet50_step_matches_reference(cn_image, fuse_post):
     for net, ops in ((t, ref_ops), (a, ref_ops), (b, M)):
         opt = torch.optim.SGD(net.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
         outs.append(_train_step(net, opt, make_fwd(ops)))
-    _compare("resnet50 cn_image=%s fuse_post=%s vs %s" % (cn_image, fuse_post, label), (t, outs[0]), (a, outs[1]), (b, outs[2]))
+    _compare("resnet50 cn_image=%s fuse_post=%s channels_last=%s vs %s" % (cn_image, fuse_post, channels_last, label),
+             (t, outs[0]), (a, outs[1]), (b, outs[2]))
 
 
 def _reference_jsd(lc, l1, l2):
@@ -218,8 +223,8 @@ def _reference_jsd(lc, l1, l2):
             F.kl_div(pm, p2, reduction='batchmean')) / 3.
 
 
-@pytest.mark.parametrize("autocast", [False, True])
-def test_resnet50_jsd_step_matches_reference(autocast):
+@pytest.mark.parametrize("autocast,channels_last", [(False, False), (True, False), (False, True), (True, True)])
+def test_resnet50_jsd_step_matches_reference(autocast, channels_last):
     """BASELINE config 5: the 3-view consistency step (imagenet.py:337-406): views concatenated, image-space CrossNorm on
     the whole 3B batch, one forward, CE on the clean third + 12 x JSD.  fp32: the whole-step tolerances above.  bf16
     autocast (what the benchmark runs): the reference's SelfNorm computes its statistics in bf16 there (SURVEY.md C.4:
@@ -234,6 +239,8 @@ def test_resnet50_jsd_step_matches_reference(autocast):
     a = RefResNet([3, 4, 6, 3], **kw).to(DEV).train()
     b = ResNet([3, 4, 6, 3], fuse_post=True, **kw).to(DEV).train()
     b.load_state_dict(a.state_dict())
+    if channels_last:
+        b = b.to(memory_format=torch.channels_last)
     nets = [(a, ref_ops, _reference_jsd), (b, M, jsd_consistency)]
     if not autocast:
         t = RefResNet([3, 4, 6, 3], **kw).to(DEV).double().train()
@@ -248,7 +255,10 @@ def test_resnet50_jsd_step_matches_reference(autocast):
         def fwd(net):
             torch.manual_seed(5)
             np.random.seed(6)
-            images = ops.cn_op_2ins_space_chan(x.to(next(net.parameters()).dtype), beta=1, crop="neither")   # imagenet.py:355
+            xx = x.to(next(net.parameters()).dtype)
+            if channels_last and net is b:
+                xx = xx.contiguous(memory_format=torch.channels_last)
+            images = ops.cn_op_2ins_space_chan(xx, beta=1, crop="neither")   # imagenet.py:355
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
                 logits_all = net(images, aug=False)
             lc, l1, l2 = torch.split(logits_all, B)
@@ -261,7 +271,7 @@ def test_resnet50_jsd_step_matches_reference(autocast):
         opt = torch.optim.SGD(net.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
         outs.append(_train_step(net, opt, make_fwd(ops, jsd)))
     if not autocast:
-        _compare("resnet50 jsd fp32 vs %s" % label, (nets[0][0], outs[0]), (a, outs[1]), (b, outs[2]))
+        _compare("resnet50 jsd fp32 channels_last=%s vs %s" % (channels_last, label), (nets[0][0], outs[0]), (a, outs[1]), (b, outs[2]))
         return
     assert torch.isfinite(outs[1]["logits"]).all() and torch.isfinite(outs[1]["loss"])
     assert abs(float(outs[1]["loss"]) - float(outs[0]["loss"])) <= 0.05 * abs(float(outs[0]["loss"]))
