@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold(const float2* __restric
 
 // per chunk and channel: (sum d, sum d * xhat)
 template <typename T>
-__global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, const T* __restrict__ dy, const Geom g, int relu,
+__global__ void __launch_bounds__(kT, 4) k_bn_nhwc_reduce(const T* __restrict__ x, const T* __restrict__ dy, const Geom g, int relu,
                                                        const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                                        const float2* __restrict__ coef, float2* __restrict__ part) {
     constexpr int V = VecOf<T>::n;
@@ -177,10 +177,10 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, 
     const uint4* vx = reinterpret_cast<const uint4*>(x) + vb;
     const uint4* vd = reinterpret_cast<const uint4*>(dy) + vb;
     const int c0 = blockIdx.y * W + cg * V;
-    float mean[V], rstd[V], fs[V], fb[V], a[V], b[V];
+    float mean[V], fs[V], fb[V], a[V], b[V];                // b accumulates d * (x - mean); rstd multiplies the column total
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        mean[e] = save_mean[c0 + e]; rstd[e] = save_rstd[c0 + e];
+        mean[e] = save_mean[c0 + e];
         const float2 f = coef[c0 + e];
         fs[e] = f.x; fb[e] = f.y; a[e] = 0.f; b[e] = 0.f;
     }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, 
         for (int e = 0; e < V; ++e) {
             const float d = (relu && !(fmaf(fs[e], xv[e], fb[e]) > 0.f)) ? 0.f : dv[e];
             a[e] += d;
-            b[e] = fmaf(d, (xv[e] - mean[e]) * rstd[e], b[e]);
+            b[e] = fmaf(d, xv[e] - mean[e], b[e]);
         }
     }
 #pragma unroll
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_reduce(const T* __restrict__ x, 
     for (int c = threadIdx.x; c < W; c += kT) {
         double ta = 0.0, tb = 0.0;
         for (int l = 0; l < g.RL; ++l) { ta += (double)s_a[l * W + c]; tb += (double)s_b[l * W + c]; }
+        tb *= (double)save_rstd[blockIdx.y * W + c];
         part[(size_t)blockIdx.x * g.C + (size_t)blockIdx.y * W + c] = make_float2((float)ta, (float)tb);
     }
 }
@@ -230,7 +231,7 @@ __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2* __res
 }
 
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(kT) k_bn_nhwc_apply(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
+__global__ void __launch_bounds__(kT, 4) k_bn_nhwc_apply(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
                                                       int relu, const float2* __restrict__ coef, const float* __restrict__ cdx) {
     constexpr int V = VecOf<T>::n;
     const int W = g.CGB * V;
@@ -281,7 +282,9 @@ static int make_geom(Geom& g, int dtype, int N, int C, int H, int W) {
     if (g.R < 2) return CNSN_E_UNSUPPORTED;
     g.RL = kT / g.CGB;
     const int cblocks = g.CG / g.CGB;
-    // about 4 CTAs per SM over all channel blocks, at least 4 rows per row lane, at most kMaxChunks chunks
+    // 4 CTAs per SM over all channel blocks whatever the tensor size (measured on the WideResNet / ResNet-50 steps: 8 per SM
+    // costs more in the fold than it gains, fewer-but-larger chunks for small tensors lose bandwidth), at least 4 rows per
+    // row lane, at most kMaxChunks chunks
     long long G = std::max<long long>(1, (148 * 4) / cblocks);
     G = std::min<long long>(G, std::max<long long>(1, g.R / (4 * g.RL)));
     G = std::min<long long>(G, kMaxChunks);

@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kT) k_nhwc_reduce_bwd(const T* __restrict__ z,
 
 // forward: y = relu?(z * gate[n][c]);  backward: dx = gate * d + cb * z + cc, d = dy masked where z <= 0
 template <typename T, bool BWD>
-__global__ void __launch_bounds__(kT) k_nhwc_apply(const T* __restrict__ z, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
+__global__ void __launch_bounds__(kT, 4) k_nhwc_apply(const T* __restrict__ z, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
                                                    int relu, const float* __restrict__ gate, const float* __restrict__ cb,
                                                    const float* __restrict__ cc) {
     constexpr int V = VecOf<T>::n;

@@ -16,9 +16,14 @@ torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 np.random.seed(0)
 net = resnet50(fuse_post=True).to(dev).train()
+cl = len(sys.argv) > 1 and sys.argv[1] == "cl"
+if cl:
+    net = net.to(memory_format=torch.channels_last)
 opt = torch.optim.SGD(net.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
 B = 256
 x = torch.randn(3 * B, 3, 224, 224, device=dev)
+if cl:
+    x = x.contiguous(memory_format=torch.channels_last)
 y = torch.randint(0, 1000, (B,), device=dev)
 
 

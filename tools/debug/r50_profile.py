@@ -15,8 +15,13 @@ torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 np.random.seed(0)
 net = resnet50(fuse_post=True).to(dev).train()
+cl = len(sys.argv) > 1 and sys.argv[1] == "cl"
+if cl:
+    net = net.to(memory_format=torch.channels_last)
 opt = torch.optim.SGD(net.parameters(), 0.1, momentum=0.9, weight_decay=1e-4)
 x = torch.randn(256, 3, 224, 224, device=dev)
+if cl:
+    x = x.contiguous(memory_format=torch.channels_last)
 y = torch.randint(0, 1000, (256,), device=dev)
 
 
@@ -42,4 +47,4 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
     for _ in range(2):
         step()
     torch.cuda.synchronize()
-print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=30, max_name_column_width=100))
+print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=36, max_name_column_width=100))
