@@ -80,6 +80,9 @@ SIGNATURES = {
                                  c_int, c_int, c_float, c_float, c_void_p, c_void_p]),
     "cnsn_bn_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_void_p, c_int, c_int, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p]),
+    "cnsn_maxpool_nhwc_out": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
+    "cnsn_maxpool_nhwc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_void_p]),
+    "cnsn_maxpool_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_void_p]),
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),
@@ -411,6 +414,32 @@ class CudaBackend:
             _check(fn(_p(z), _p(dy), _p(dz), int(relu), _dtype_code(z), N, C, H, W,
                       ctypes.byref(gs), int(training), _p(save), ctypes.byref(gg), _p(ws), _stream(z)))
         return dz, out_g
+
+    # -- channels-last MaxPool2d ------------------------------------------------------------------
+    @staticmethod
+    def maxpool_nhwc_ok(x, k, stride, pad):
+        if x.dim() != 4 or x.is_contiguous() or not x.is_contiguous(memory_format=torch.channels_last):
+            return False
+        return (x.data_ptr() % 16 == 0 and (x.size(1) * x.element_size()) % 16 == 0 and 1 <= k <= 15 and stride >= 1
+                and 0 <= 2 * pad <= k and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+    def maxpool_nhwc_fwd(self, x, k, stride, pad):
+        _require_cuda(x)
+        N, C, H, W = x.shape
+        OH, OW = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        y = torch.empty((N, C, OH, OW), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
+        code = torch.empty((N, OH, OW, C), dtype=torch.uint8, device=x.device)
+        with _on(x.device):
+            _check(lib().cnsn_maxpool_nhwc_fwd(_p(x), _p(y), _p(code), _dtype_code(x), N, C, H, W, k, stride, pad, _stream(x)))
+        return y, code
+
+    def maxpool_nhwc_bwd(self, dy, code, shape, k, stride, pad):
+        _require_cuda(dy)
+        N, C, H, W = shape
+        dx = torch.empty(shape, dtype=dy.dtype, device=dy.device, memory_format=torch.channels_last)
+        with _on(dy.device):
+            _check(lib().cnsn_maxpool_nhwc_bwd(_p(dy), _p(code), _p(dx), _dtype_code(dy), N, C, H, W, k, stride, pad, _stream(dy)))
+        return dx
 
     # -- channels-last BatchNorm2d [+ ReLU] -------------------------------------------------------
     @staticmethod

@@ -405,6 +405,40 @@ struct BnNhwcNode : public torch::autograd::Function<BnNhwcNode> {
     }
 };
 
+// ---- channels-last MaxPool2d (cnsn_maxpool_nhwc_fwd/_bwd) ---------------------------------------------------------------
+struct MaxPoolNhwcNode : public torch::autograd::Function<MaxPoolNhwcNode> {
+    static at::Tensor forward(AutogradContext* ctx, const at::Tensor& x, int64_t k, int64_t stride, int64_t pad) {
+        const c10::cuda::CUDAGuard guard(x.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        const int N = (int)x.size(0), C = (int)x.size(1), H = (int)x.size(2), W = (int)x.size(3);
+        int OH = 0, OW = 0;
+        check(cnsn_maxpool_nhwc_out(H, W, (int)k, (int)stride, (int)pad, &OH, &OW));
+        at::Tensor y = at::empty({N, C, OH, OW}, x.options().memory_format(at::MemoryFormat::ChannelsLast));
+        at::Tensor code = at::empty({N, OH, OW, C}, x.options().dtype(at::kByte).memory_format(at::MemoryFormat::Contiguous));
+        check(cnsn_maxpool_nhwc_fwd(x.data_ptr(), y.data_ptr(), code.data_ptr<uint8_t>(), dtype_code(x), N, C, H, W, (int)k, (int)stride,
+                                    (int)pad, stream));
+        ctx->save_for_backward({code});
+        ctx->saved_data["shape"] = std::vector<int64_t>{N, C, H, W};
+        ctx->saved_data["k"] = k; ctx->saved_data["stride"] = stride; ctx->saved_data["pad"] = pad;
+        return y;
+    }
+
+    static variable_list backward(AutogradContext* ctx, variable_list grads) {
+        const at::Tensor code = ctx->get_saved_variables()[0];
+        const auto shape = ctx->saved_data["shape"].toIntVector();
+        const int k = (int)ctx->saved_data["k"].toInt(), stride = (int)ctx->saved_data["stride"].toInt(), pad = (int)ctx->saved_data["pad"].toInt();
+        at::Tensor dy = grads[0];
+        if (!is_channels_last(dy)) dy = dy.contiguous().contiguous(at::MemoryFormat::ChannelsLast);
+        const c10::cuda::CUDAGuard guard(dy.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        at::Tensor dx = at::empty(shape, dy.options().memory_format(at::MemoryFormat::ChannelsLast));
+        check(cnsn_maxpool_nhwc_bwd(dy.data_ptr(), code.data_ptr<uint8_t>(), dx.data_ptr(), dtype_code(dy), (int)shape[0], (int)shape[1],
+                                    (int)shape[2], (int)shape[3], k, stride, pad, stream));
+        at::Tensor none;
+        return {dx, none, none, none};
+    }
+};
+
 void check_gate(const at::Tensor& x, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta, const GateBufs& b) {
     const int64_t C = x.size(1);
     for (const at::Tensor* t : {&w, &gamma, &beta, &b.run_mean, &b.run_var}) {
@@ -453,6 +487,12 @@ at::Tensor bn_nhwc(const at::Tensor& x, bool training, bool relu, double momentu
     return BnNhwcNode::apply(x, training, relu, momentum, eps, b, weight, bias);
 }
 
+at::Tensor maxpool_nhwc(const at::Tensor& x, int64_t k, int64_t stride, int64_t pad) {
+    require_cuda4(x);
+    TORCH_CHECK(is_channels_last(x) && (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15u) == 0, "maxpool_nhwc: x must be a dense, 16-byte aligned channels_last tensor");
+    return MaxPoolNhwcNode::apply(x, k, stride, pad);
+}
+
 bool site_supported(const at::Tensor& x) {
     if (!x.is_cuda() || x.dim() != 4 || (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15u)) return false;
     const c10::cuda::CUDAGuard guard(x.device());
@@ -494,5 +534,6 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("site_supported", &site_supported);
     m.def("ibn", &ibn, "IBN / InstanceNorm2d (half == C) / BatchNorm2d (half == 0), one kernel per direction (resnet_ibn_cnsn.py:24-44)");
     m.def("ibn_resident", &ibn_resident);
+    m.def("maxpool_nhwc", &maxpool_nhwc, "nn.MaxPool2d(k, stride, pad) on a dense channels_last tensor (csrc/pool_nhwc.cu)");
     m.def("bn_nhwc", &bn_nhwc, "nn.BatchNorm2d [+ ReLU] on a dense channels_last tensor, three kernels per direction (csrc/bn_nhwc.cu)");
 }

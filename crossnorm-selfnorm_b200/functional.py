@@ -238,3 +238,21 @@ class BnNhwcFn(torch.autograd.Function):
             dy = dy.contiguous(memory_format=torch.channels_last)
         dx, dw, db = _lib.backend().bn_nhwc_bwd(x, dy, weight, training, relu, save)
         return dx, None, None, None, None, None, dw, db
+
+
+class MaxPoolNhwcFn(torch.autograd.Function):
+    """nn.MaxPool2d(k, stride, pad) on a dense channels_last tensor (cnsn_maxpool_nhwc_fwd / _bwd, csrc/pool_nhwc.cu).  Saved for
+    backward: one byte per output element (torch keeps an int64)."""
+
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        y, code = _lib.backend().maxpool_nhwc_fwd(x, k, stride, pad)
+        ctx.pool = (code, tuple(x.shape), k, stride, pad)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        code, shape, k, stride, pad = ctx.pool
+        if not dy.is_contiguous(memory_format=torch.channels_last) or dy.is_contiguous():
+            dy = dy.contiguous(memory_format=torch.channels_last)
+        return _lib.backend().maxpool_nhwc_bwd(dy, code, shape, k, stride, pad), None, None, None

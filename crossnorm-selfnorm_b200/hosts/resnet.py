@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._norm import batchnorm2d_for, bn_relu
+from ._norm import batchnorm2d_for, bn_relu, maxpool2d_for
 
 _POSITIONS = ("residual", "pre", "post", "identity")
 _EXPANSION = 4
@@ -101,7 +101,7 @@ class ResNet(nn.Module):
         else:
             self.bn1 = BN(64)
         self.relu = nn.ReLU(inplace=True)
-        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        self.maxpool = maxpool2d_for(ops, fast_bn)(3, 2, 1)
         kw = dict(pos=pos, beta=beta, crop=crop, cnsn_type=cnsn_type, ops=ops, fuse_post=fuse_post,
                   ibn_host=any(v is not None for v in ibn_cfg), fast_bn=fast_bn)
         width = 64

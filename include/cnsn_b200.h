@@ -325,6 +325,16 @@ int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dtype, int N, 
                      const float* gamma, int training, int relu, const float* save,
                      float* dgamma, float* dbeta, float* workspace, void* stream);
 
+/* Channels-last nn.MaxPool2d(k, stride, pad) (dilation 1, ceil_mode off; the stem of models/imagenet/resnet_cnsn.py:183,238):
+ * x (N, C, H, W) and y (N, C, OH, OW) in N, H, W, C memory order, `code` one byte per OUTPUT element (the position of the
+ * maximum inside its window, rows first; 8-byte aligned; written by forward, read by backward).  torch's tie rule: the first
+ * of equal maxima wins, NaN propagates.  C * sizeof(T) must be a multiple of 16, 2 * pad <= k <= 15. */
+int cnsn_maxpool_nhwc_out(int H, int W, int k, int stride, int pad, int* OH, int* OW);
+int cnsn_maxpool_nhwc_fwd(const void* x, void* y, unsigned char* code, int dtype, int N, int C, int H, int W,
+                          int k, int stride, int pad, void* stream);
+int cnsn_maxpool_nhwc_bwd(const void* dy, const unsigned char* code, void* dx, int dtype, int N, int C, int H, int W,
+                          int k, int stride, int pad, void* stream);
+
 /* ---------------------------------------------------------------- JSD consistency -----------
  * The Jensen-Shannon consistency term of the 3-view steps, imagenet.py:367-376 / cifar.py:173-182:
  *   p_v = softmax(logits_v); lm = log(clamp(mean_v p_v, 1e-7, 1));

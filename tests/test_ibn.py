@@ -423,3 +423,45 @@ def test_batchnorm2d_channels_last_matches_torch(shape, dtype, training, relu, b
             a, b = a[clear], b[clear]
         err = float((a - b).abs().max() / a.abs().max().clamp_min(1e-12))
         assert err <= tol, (name, err)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype,k,stride,pad", [((8, 64, 112, 112), torch.float32, 3, 2, 1), ((6, 16, 17, 23), torch.float32, 3, 2, 1),
+                                                      ((4, 8, 9, 9), torch.bfloat16, 3, 2, 1), ((3, 32, 12, 12), torch.float16, 2, 2, 0),
+                                                      ((2, 4, 10, 7), torch.float32, 3, 1, 1), ((2, 8, 15, 15), torch.float32, 5, 3, 2),
+                                                      ((16, 64, 56, 56), torch.bfloat16, 3, 2, 1)])
+@pytest.mark.parametrize("binding", ["ext", "ctypes"])
+def test_maxpool_channels_last_matches_torch(shape, dtype, k, stride, pad, binding):
+    """hosts._norm.MaxPool2d on torch.channels_last inputs (csrc/pool_nhwc.cu) against torch's max_pool2d: outputs bit-equal;
+    input gradients bit-equal in fp32 (the same windows win -- the input is ReLU'd, so whole windows tie at 0 and the tie
+    rule decides -- and their contributions are added in the same order), 16-bit: against torch in fp32 within one rounding."""
+    import torch.nn as nn
+    import cnsn_b200._lib as L
+    from cnsn_b200.hosts._norm import MaxPool2d
+    dev = "cuda:0"
+    cl = torch.channels_last
+    g = torch.Generator().manual_seed(sum(shape))
+    x0 = torch.relu(torch.randn(shape, generator=g)).to(dtype)
+    x0[0, :, 0, 0] = float("nan")                           # NaN propagates like torch's
+    ours, ref = MaxPool2d(k, stride, pad), nn.MaxPool2d(k, stride, pad)
+    old = L.set_binding(binding)
+    try:
+        x = x0.to(dev).contiguous(memory_format=cl).requires_grad_(True)
+        n0 = L.launch_count()
+        y = ours(x)
+        dy0 = torch.randn(y.shape, generator=g).to(dtype)
+        y.backward(dy0.to(dev).contiguous(memory_format=cl))
+        torch.cuda.synchronize()
+        assert L.launch_count() - n0 == 2 and y.is_contiguous(memory_format=cl) and x.grad.is_contiguous(memory_format=cl)
+    finally:
+        L.set_binding(old)
+    xr = x0.to(dev).float().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(dy0.to(dev).float())
+    assert torch.equal(torch.nan_to_num(y.float(), nan=-1.0), torch.nan_to_num(yr, nan=-1.0))
+    if dtype == torch.float32:
+        assert torch.equal(x.grad, xr.grad)
+    else:
+        assert torch.allclose(x.grad.float(), xr.grad, rtol=1e-2, atol=1e-2)
+    # NCHW input: torch's own kernel
+    assert torch.equal(torch.nan_to_num(ours(x0.to(dev)), nan=-1.0), torch.nan_to_num(ref(x0.to(dev)), nan=-1.0))
