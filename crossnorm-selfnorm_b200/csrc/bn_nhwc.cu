@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kT) k_bn_nhwc_stats(const T* __restrict__ x, c
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         s_mean[rl * W + cg * V + e] = k[e] + s1[e] * inv;
-        s_m2[rl * W + cg * V + e] = fmaxf(s2[e] - s1[e] * s1[e] * inv, 0.f);
+        const float m2 = s2[e] - s1[e] * s1[e] * inv;
+        s_m2[rl * W + cg * V + e] = m2 < 0.f ? 0.f : m2;      // (not fmaxf: a NaN must stay a NaN)
     }
     __syncthreads();
     // merge the row lanes (lane l holds ceil((nrows - l) / RL) rows): mean = sum n_l m_l / n, M2 = sum (M2_l + n_l (m_l - mean)^2);

@@ -95,9 +95,10 @@ def _eager(shape_c):
     return eager_modules
 
 
-@pytest.mark.parametrize("shape", [(8, 6, 16, 16), (16, 4, 56, 56), (8, 8, 7, 7)])
+@pytest.mark.parametrize("shape,channels_last", [((8, 6, 16, 16), False), ((16, 4, 56, 56), False), ((8, 8, 7, 7), False),
+                                                 ((8, 8, 16, 16), True), ((6, 16, 40, 40), True)])
 @pytest.mark.parametrize("bad", [float("nan"), float("inf")])
-def test_selfnorm_propagates_non_finite_like_the_reference(mod, shape, bad):
+def test_selfnorm_propagates_non_finite_like_the_reference(mod, shape, bad, channels_last):
     """A NaN / Inf element makes its instance's statistics non-finite, BatchNorm1d's batch statistics carry that to the
     whole channel (models/cnsn.py:133-150): the kernels must produce the SAME non-finite pattern as the eager chain on
     the same GPU, finite values elsewhere, and must not stall on the polled words (NaN payloads are canonicalised,
@@ -114,7 +115,10 @@ def test_selfnorm_propagates_non_finite_like_the_reference(mod, shape, bad):
     ref.load_state_dict(ours.state_dict())
     res = []
     for m in (ref, ours):
-        xt = x.to(DEV).requires_grad_(True)
+        xt = x.to(DEV)
+        if channels_last and m is ours:              # the NHWC kernels (csrc/selfnorm_nhwc.cu): same pattern, same values
+            xt = xt.contiguous(memory_format=torch.channels_last)
+        xt = xt.requires_grad_(True)
         y = m(xt)
         y.backward(dy.to(DEV))
         res.append((y.detach(), xt.grad, m.g_bn.running_mean.clone(), m.g_fc.weight.grad.clone()))

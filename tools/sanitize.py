@@ -3,7 +3,8 @@
     compute-sanitizer --tool racecheck|synccheck|memcheck python tools/sanitize.py
 
 SelfNorm (shared-memory-resident k_sn_res, L2 items k_sn_flow, channel groups k_sn_grp, the shared + tensor memory
-pipeline k_sn_tm), CrossNorm (k_cn_res), the fused site (k_site_res), IBN / BatchNorm2d (k_ibn_res); each result is
+pipeline k_sn_tm), CrossNorm (k_cn_res), the fused site (k_site_res), IBN / BatchNorm2d (k_ibn_res, k_bn_grp), the channels-last
+SelfNorm block, BatchNorm2d and MaxPool2d kernels (k_nhwc_*, k_bn_nhwc_*, k_maxpool_nhwc_*); each result is
 checked against the three-kernel general path of the same library, and the asynchronous error state must stay clear."""
 import os
 import sys
@@ -86,6 +87,45 @@ for name, mod, ref in (("IBN k_ibn_res", IBN(4).to(dev).train(), None), ("BatchN
         print("%-34s %-18s max |ours - torch| = %.2e" % (name, tuple(x.shape), err), flush=True)
     else:
         print("%-34s %-18s ran" % (name, tuple(x.shape)), flush=True)
+# ---- the kernels added late in round 2: channel-group batch norm, channels-last SelfNorm block / BatchNorm2d / MaxPool2d
+cl = torch.channels_last
+xb = torch.randn(12, 8, 7, 7, device=dev, requires_grad=True)              # 7x7 planes: k_bn_grp
+db = torch.randn(12, 8, 7, 7, device=dev)
+bn, tbn = BatchNorm2d(8).to(dev).train(), torch.nn.BatchNorm2d(8).to(dev).train()
+y = bn(xb, True); (dx,) = torch.autograd.grad(y, xb, db)
+yr = torch.relu(tbn(xb)); (dxr,) = torch.autograd.grad(yr, xb, db)
+err = max(float((y - yr).abs().max()), float((dx - dxr).abs().max()))
+print("%-34s %-18s max |ours - torch| = %.2e" % ("BatchNorm2d + ReLU k_bn_grp", tuple(xb.shape), err), flush=True)
+assert err < 1e-4
+for shape in ((6, 16, 20, 20), (5, 8, 50, 50)):                           # one slab / several slabs per sample
+    xc = torch.randn(shape, device=dev).contiguous(memory_format=cl).requires_grad_(True)
+    rc = torch.randn(shape, device=dev).contiguous(memory_format=cl).requires_grad_(True)
+    dc = torch.randn(shape, device=dev).contiguous(memory_format=cl)
+    sn = M.SelfNorm(shape[1]).to(dev).train()
+    outs = []
+    for xx, rr, dd in ((xc, rc, dc), (xc.detach().contiguous().requires_grad_(True), rc.detach().contiguous().requires_grad_(True), dc.contiguous())):
+        sn.g_bn.running_mean.zero_(); sn.g_bn.running_var.fill_(1)
+        y = sn(xx, rr, True)
+        dx, dr = torch.autograd.grad(y, (xx, rr), dd)
+        outs.append((y.detach(), dx, dr))
+    err = max(float((a - b).abs().max()) for a, b in zip(*outs))
+    print("%-34s %-18s max |NHWC - NCHW kernels| = %.2e" % ("SelfNorm block k_nhwc_*", shape, err), flush=True)
+    assert err < 1e-4
+    bn, tbn = BatchNorm2d(shape[1]).to(dev).train(), torch.nn.BatchNorm2d(shape[1]).to(dev).train()
+    y = bn(xc, True); (dx,) = torch.autograd.grad(y, xc, dc)
+    yr = torch.relu(tbn(xc)); (dxr,) = torch.autograd.grad(yr, xc, dc)
+    err = max(float((y - yr).abs().max()), float((dx - dxr).abs().max()))
+    print("%-34s %-18s max |ours - torch| = %.2e" % ("BatchNorm2d + ReLU k_bn_nhwc_*", shape, err), flush=True)
+    assert err < 1e-4
+from cnsn_b200.hosts._norm import MaxPool2d  # noqa: E402
+xp = torch.relu(torch.randn(4, 8, 13, 11, device=dev)).contiguous(memory_format=cl).requires_grad_(True)
+y = MaxPool2d(3, 2, 1)(xp)
+dp = torch.randn_like(y)
+(dx,) = torch.autograd.grad(y, xp, dp)
+yr = torch.nn.functional.max_pool2d(xp, 3, 2, 1)
+(dxr,) = torch.autograd.grad(yr, xp, dp)
+assert torch.equal(y, yr) and torch.equal(dx, dxr)
+print("%-34s %-18s equal to torch" % ("MaxPool2d k_maxpool_nhwc_*", tuple(xp.shape)), flush=True)
 torch.cuda.synchronize()
 L.async_error()
 print("sanitize.py: %d library kernels launched, asynchronous error state clear" % (L.launch_count() - n0))
