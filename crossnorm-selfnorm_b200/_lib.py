@@ -83,6 +83,13 @@ SIGNATURES = {
     "cnsn_maxpool_nhwc_out": (c_int, [c_int, c_int, c_int, c_int, c_int, POINTER(c_int), POINTER(c_int)]),
     "cnsn_maxpool_nhwc_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_void_p]),
     "cnsn_maxpool_nhwc_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, *_DIMS, c_int, c_int, c_int, c_void_p]),
+    "cnsn_bn_selfnorm_tail_supported": (c_int, [c_int, *_DIMS]),
+    "cnsn_bn_selfnorm_tail_fwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS,
+                                               c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p,
+                                               POINTER(GateParams), c_int, c_float, c_float, c_float, c_void_p, c_void_p]),
+    "cnsn_bn_selfnorm_tail_bwd_nhwc": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, *_DIMS,
+                                               c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                               POINTER(GateParams), c_int, c_void_p, POINTER(GateGrads), c_void_p, c_void_p]),
     "cnsn_ibn_save_floats": (c_size_t, [c_int, c_int, c_int]),
     "cnsn_ibn_workspace_floats": (c_size_t, [c_int, c_int]),
     "cnsn_ibn_resident": (c_int, [c_int, *_DIMS, c_int, c_int]),

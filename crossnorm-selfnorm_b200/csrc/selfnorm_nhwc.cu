@@ -24,6 +24,7 @@
 
 #include <algorithm>
 
+#include "bn_nhwc.cuh"
 #include "flow_common.cuh"
 #include "selfnorm_gate.cuh"
 
@@ -58,12 +59,16 @@ __device__ __forceinline__ void column_sums(const float (&v)[V], float* red, flo
 
 // forward statistics of slab (n, s): exact two-pass per slab, Chan merge across the slabs of the sample.
 // ADD: z = x + res is formed on the way (rounded to T like torch.add's output), written out, and the statistics are z's.
-template <typename T, bool ADD>
+// AFF (with ADD; the fused bottleneck tail): x is the raw output of conv3 and is first sent through bn3's batch-norm map
+// y3 = scale * x + shift (coef[c], rounded to T as the unfused batch norm would have stored it), z = y3 + res.
+template <typename T, bool ADD, bool AFF = false>
 __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, const T* __restrict__ res, T* __restrict__ z,
                                                    const Geom g, float eps, float2* __restrict__ part,
-                                                   unsigned* __restrict__ cnt, float* __restrict__ mu, float* __restrict__ sd) {
+                                                   unsigned* __restrict__ cnt, float* __restrict__ mu, float* __restrict__ sd,
+                                                   const float2* __restrict__ coef = nullptr) {
+    static_assert(ADD || !AFF, "the batch-norm map comes with the residual add");
     constexpr int V = VecOf<T>::n;
-    extern __shared__ float sm[];                            // red [RL][C] | col [C] | mean [C]
+    extern __shared__ float sm[];                            // red [RL][W] | col [W] | mean [W]
     const int W = g.CGB * V, c0 = blockIdx.y * W;            // this CTA's channels: c0 .. c0 + W - 1
     float* red = sm;
     float* s_col = sm + g.RL * W;
@@ -76,16 +81,25 @@ __global__ void __launch_bounds__(kT) k_nhwc_stats(const T* __restrict__ x, cons
     const uint4* vx = reinterpret_cast<const uint4*>(x) + vbase;
     const uint4* vr = reinterpret_cast<const uint4*>(res) + vbase;
     uint4* vz = reinterpret_cast<uint4*>(z) + vbase;
-    float acc[V];
+    float acc[V], fs[V], fb[V];
 #pragma unroll
-    for (int e = 0; e < V; ++e) acc[e] = 0.f;
+    for (int e = 0; e < V; ++e) {
+        acc[e] = 0.f;
+        const float2 f = AFF ? coef[c0 + cg * V + e] : make_float2(1.f, 0.f);
+        fs[e] = f.x; fb[e] = f.y;
+    }
 #pragma unroll 4
     for (int r = rl; r < nrows; r += g.RL) {
         float a[V];
         if (ADD) {
             float b[V];
-            unpack<T>(ldg_stream(vx + (size_t)r * g.CG), a);
+            unpack<T>(AFF ? __ldg(vx + (size_t)r * g.CG) : ldg_stream(vx + (size_t)r * g.CG), a);   // AFF: the backward reads x again
             unpack<T>(ldg_stream(vr + (size_t)r * g.CG), b);
+            if (AFF) {
+#pragma unroll
+                for (int e = 0; e < V; ++e) a[e] = fmaf(fs[e], a[e], fb[e]);
+                unpack<T>(pack<T>(a), a);                    // y3 as the element type holds it
+            }
 #pragma unroll
             for (int e = 0; e < V; ++e) a[e] += b[e];
             const uint4 q = pack<T>(a);
@@ -233,6 +247,71 @@ __global__ void __launch_bounds__(kT, 4) k_nhwc_apply(const T* __restrict__ z, c
     }
 }
 
+// The fused bottleneck tail, backward middle step, in the BATCH NORM's geometry (row chunks over the whole tensor): forms
+// dz = gate * d + cb * z + cc (SelfNorm block backward, d = dy masked where z <= 0), writes it -- it is also the gradient of
+// the residual branch --, and on the way accumulates bn3's reduction (sum dz, sum dz * (c - mean)) * (1, rstd) per chunk and
+// column: the unfused sequence would write dz, then read it and c again for that.
+template <typename T>
+__global__ void __launch_bounds__(bnl::kT, 3) k_tail_mid_bwd(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ c,
+                                                             T* __restrict__ dz, const bnl::Geom g, int HW, int relu,
+                                                             const float* __restrict__ gate, const float* __restrict__ cb,
+                                                             const float* __restrict__ cc, const float* __restrict__ bn_mean,
+                                                             const float* __restrict__ bn_rstd, float2* __restrict__ part) {
+    constexpr int V = VecOf<T>::n;
+    extern __shared__ float sm[];                            // a [RL][W] | b [RL][W]
+    const int W = g.CGB * V;
+    float* s_a = sm;
+    float* s_b = sm + g.RL * W;
+    const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
+    const long long row0 = (long long)blockIdx.x * g.rows;
+    const long long nrows = min(g.rows, g.R - row0);
+    const size_t vb = (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
+    const uint4* vz = reinterpret_cast<const uint4*>(z) + vb;
+    const uint4* vd = reinterpret_cast<const uint4*>(dy) + vb;
+    const uint4* vc = reinterpret_cast<const uint4*>(c) + vb;
+    uint4* vo = reinterpret_cast<uint4*>(dz) + vb;
+    const int c0 = blockIdx.y * W + cg * V;
+    float mean[V], a[V], b[V], kg[V], kb[V], kc[V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) { mean[e] = bn_mean[c0 + e]; a[e] = 0.f; b[e] = 0.f; kg[e] = kb[e] = kc[e] = 0.f; }
+    long long n = (row0 + rl) / HW;                          // sample of this thread's current row
+    int rem = (int)((row0 + rl) - n * HW);
+    long long loaded = -1;
+    for (long long r = rl; r < nrows; r += g.RL) {
+        if (n != loaded) {                                   // a new sample: its SelfNorm coefficients (rarely: a chunk spans few samples)
+            const size_t i = (size_t)n * g.C + c0;
+#pragma unroll
+            for (int e = 0; e < V; ++e) { kg[e] = gate[i + e]; kb[e] = cb[i + e]; kc[e] = cc[i + e]; }
+            loaded = n;
+        }
+        float zv[V], dv[V], cv[V], o[V];
+        unpack<T>(ldg_stream(vz + (size_t)r * g.CG), zv);
+        unpack<T>(ldg_stream(vd + (size_t)r * g.CG), dv);
+        unpack<T>(__ldg(vc + (size_t)r * g.CG), cv);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+            const float d = (relu && !(zv[e] > 0.f)) ? 0.f : dv[e];
+            o[e] = fmaf(kg[e], d, fmaf(kb[e], zv[e], kc[e]));
+        }
+        const uint4 q = pack<T>(o);
+        vo[(size_t)r * g.CG] = q;                            // default policy: bn3's apply reads it next
+        unpack<T>(q, o);                                     // the reduction sees dz as the element type holds it
+#pragma unroll
+        for (int e = 0; e < V; ++e) { a[e] += o[e]; b[e] = fmaf(o[e], cv[e] - mean[e], b[e]); }
+        rem += g.RL;
+        while (rem >= HW) { rem -= HW; ++n; }
+    }
+#pragma unroll
+    for (int e = 0; e < V; ++e) { s_a[rl * W + cg * V + e] = a[e]; s_b[rl * W + cg * V + e] = b[e]; }
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < W; ch += bnl::kT) {
+        double ta = 0.0, tb = 0.0;
+        for (int l = 0; l < g.RL; ++l) { ta += (double)s_a[l * W + ch]; tb += (double)s_b[l * W + ch]; }
+        tb *= (double)bn_rstd[blockIdx.y * W + ch];
+        part[(size_t)blockIdx.x * g.C + (size_t)blockIdx.y * W + ch] = make_float2((float)ta, (float)tb);
+    }
+}
+
 // 0 = this geometry is supported
 static int make_geom(Geom& g, int dtype, int N, int C, int H, int W) {
     const int esz = (int)esize(dtype);
@@ -354,5 +433,117 @@ extern "C" int cnsn_selfnorm_block_bwd_nhwc(const void* z, const void* dy, void*
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T,
         (nhwc::k_nhwc_apply<T, true><<<grid, nhwc::kT, 0, s>>>((const T*)z, (const T*)dy, (T*)dz, gm, relu ? 1 : 0, save + L.g, cb, cc)));
+    return launch_status();
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// The tail of a pos='post' ResNet bottleneck as ONE operator (models/imagenet/resnet_cnsn.py:113-122):
+//     out = self.bn3(out); out += identity; out = self.cnsn(out); out = self.relu(out)
+// forward : bn3 statistics of c (the raw conv3 output) -> fold -> [z = bn3(c) + res, statistics of z] -> gate -> y
+// backward: [sum d z] -> gate backward -> [dz, bn3's reduction] -> fold -> dc
+// Against the two operators called one after the other this never writes bn3's output (forward: -2 S) and reads dz for the
+// batch-norm reduction while it is being formed (backward: -1 S); every value is rounded exactly where the sequence rounds
+// it, so the results are bit-identical to the sequence's.
+extern "C" int cnsn_bn_selfnorm_tail_supported(int dtype, int N, int C, int H, int W) {
+    nhwc::Geom g{};
+    bnl::Geom b{};
+    if (check_dims(N, C, H, W) || dtype < CNSN_F32 || dtype > CNSN_F16) return 0;
+    return nhwc::make_geom(g, dtype, N, C, H, W) == 0 && bnl::make_geom(b, dtype, N, C, H, W) == 0;
+}
+
+extern "C" int cnsn_bn_selfnorm_tail_fwd_nhwc(const void* c, const void* res, void* z, void* y, int relu, int dtype,
+                                              int N, int C, int H, int W,
+                                              const float* bn_gamma, const float* bn_beta, float* bn_run_mean, float* bn_run_var,
+                                              long long* bn_nbt, int bn_training, float bn_momentum, float bn_eps, float* bn_save,
+                                              const cnsn_gate_params* g, int training, float momentum, float sn_bn_eps, float eps,
+                                              float* sn_save, void* stream) {
+    if (!c || !res || !z || !y || !bn_gamma || !bn_beta || !bn_run_mean || !bn_run_var || !bn_save || !sn_save ||
+        check_dims(N, C, H, W) || !gate_ok_nhwc(g)) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    if (!aligned16(c) || !aligned16(res) || !aligned16(z) || !aligned16(y)) return CNSN_E_ALIGN;
+    if ((training && N < 2) || (bn_training && (long long)N * H * W < 2)) return CNSN_E_BATCH1;
+    nhwc::Geom gm{};
+    bnl::Geom bg{};
+    int rc = nhwc::make_geom(gm, dtype, N, C, H, W);
+    if (!rc) rc = bnl::make_geom(bg, dtype, N, C, H, W);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    // bn3: statistics of c -> mean / rstd / (scale, shift)
+    float* bmean = bn_save; float* brstd = bn_save + C;
+    float2* coef = reinterpret_cast<float2*>(bn_save + 2 * (size_t)C);
+    float2* bpart = reinterpret_cast<float2*>(bn_save + 4 * (size_t)C);
+    const dim3 bgrid((unsigned)bg.G, (unsigned)(bg.CG / bg.CGB));
+    if (bn_training) {
+        CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_stats<T><<<bgrid, bnl::kT, bnl::smem_bytes(bg, dtype), s>>>((const T*)c, bg, bpart)));
+        if ((rc = launch_status())) return rc;
+    }
+    bnl::k_bn_nhwc_fold<<<C, bnl::kFoldT, 0, s>>>(bpart, bg, bn_gamma, bn_beta, bn_run_mean, bn_run_var, bn_nbt, bn_training, bn_momentum,
+                                                  bn_eps, bmean, brstd, coef);
+    if ((rc = launch_status())) return rc;
+    // z = bn3(c) + res and its per-instance statistics, gate, y
+    const SaveLayout L(N, C, false);
+    float2* part = reinterpret_cast<float2*>(sn_save + L.total);
+    unsigned* cnt = reinterpret_cast<unsigned*>(sn_save + L.total + 2 * (size_t)N * gm.S * C);
+    if (gm.S > 1) {
+        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * (gm.CG / gm.CGB) * sizeof(unsigned), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((unsigned)((long long)N * gm.S), (unsigned)(gm.CG / gm.CGB));
+    CNSN_DISPATCH_DTYPE(dtype, T, (nhwc::k_nhwc_stats<T, true, true><<<grid, nhwc::kT, nhwc::smem_bytes(gm, dtype), s>>>(
+        (const T*)c, (const T*)res, (T*)z, gm, eps, part, cnt, sn_save + L.mu, sn_save + L.sd, coef)));
+    if ((rc = launch_status())) return rc;
+    GateFwd a{g->w, g->gamma, g->beta, g->run_mean, g->run_var, g->nbt, sn_save + L.g, sn_save + L.shat_g, sn_save + L.r_g};
+    k_sn_gate_fwd<<<dim3(C, 1), kGateThreads, 0, s>>>(sn_save + L.mu, sn_save + L.sd, a, a, N, C, training, momentum, sn_bn_eps);
+    if ((rc = launch_status())) return rc;
+    CNSN_DISPATCH_DTYPE(dtype, T,
+        (nhwc::k_nhwc_apply<T, false><<<grid, nhwc::kT, 0, s>>>((const T*)z, nullptr, (T*)y, gm, relu ? 1 : 0, sn_save + L.g, nullptr, nullptr)));
+    return launch_status();
+}
+
+extern "C" int cnsn_bn_selfnorm_tail_bwd_nhwc(const void* c, const void* z, const void* dy, void* dz, void* dc, int relu, int dtype,
+                                              int N, int C, int H, int W,
+                                              const float* bn_gamma, int bn_training, const float* bn_save,
+                                              float* d_bn_gamma, float* d_bn_beta, float* bn_workspace,
+                                              const cnsn_gate_params* g, int training, const float* sn_save,
+                                              const cnsn_gate_grads* dg, float* sn_workspace, void* stream) {
+    if (!c || !z || !dy || !dz || !dc || !bn_gamma || !bn_save || !d_bn_gamma || !d_bn_beta || !bn_workspace || !sn_save ||
+        !sn_workspace || check_dims(N, C, H, W)) return CNSN_E_BADARG;
+    if (!g || !g->w || !g->gamma || !dg || !dg->dw || !dg->dgamma || !dg->dbeta) return CNSN_E_BADARG;
+    if (dtype < CNSN_F32 || dtype > CNSN_F16) return CNSN_E_BADARG;
+    if (!aligned16(c) || !aligned16(z) || !aligned16(dy) || !aligned16(dz) || !aligned16(dc)) return CNSN_E_ALIGN;
+    nhwc::Geom gm{};
+    bnl::Geom bg{};
+    int rc = nhwc::make_geom(gm, dtype, N, C, H, W);
+    if (!rc) rc = bnl::make_geom(bg, dtype, N, C, H, W);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const SaveLayout L(N, C, false);
+    const size_t nc = (size_t)N * C;
+    float* sxy = sn_workspace; float* st = sn_workspace + nc; float* cb = sn_workspace + 2 * nc; float* cc = sn_workspace + 3 * nc;
+    float* part = sn_workspace + 4 * nc;
+    unsigned* cnt = reinterpret_cast<unsigned*>(part + (size_t)N * gm.S * C);
+    if (gm.S > 1) {
+        const cudaError_t e = cudaMemsetAsync(cnt, 0, (size_t)N * (gm.CG / gm.CGB) * sizeof(unsigned), s);
+        if (e != cudaSuccess) return (int)e;
+    }
+    const dim3 grid((unsigned)((long long)N * gm.S), (unsigned)(gm.CG / gm.CGB));
+    CNSN_DISPATCH_DTYPE(dtype, T, (nhwc::k_nhwc_reduce_bwd<T><<<grid, nhwc::kT, nhwc::smem_bytes(gm, dtype), s>>>(
+        (const T*)z, (const T*)dy, gm, relu ? 1 : 0, part, cnt, sxy)));
+    if ((rc = launch_status())) return rc;
+    GateBwd a{g->w, g->gamma, sn_save + L.g, sn_save + L.shat_g, sn_save + L.r_g, dg->dw, dg->dgamma, dg->dbeta};
+    k_sn_gate_bwd<<<C, kGateThreads, 0, s>>>(sn_save + L.mu, sn_save + L.sd, sxy, st, a, a, 0, N, C, H * W, training, cb, cc);
+    if ((rc = launch_status())) return rc;
+    const float* bmean = bn_save; const float* brstd = bn_save + C;
+    const float2* coef = reinterpret_cast<const float2*>(bn_save + 2 * (size_t)C);
+    float2* bpart = reinterpret_cast<float2*>(bn_workspace);
+    float* cdx = bn_workspace + 2 * (size_t)bg.G * C;
+    const dim3 bgrid((unsigned)bg.G, (unsigned)(bg.CG / bg.CGB));
+    CNSN_DISPATCH_DTYPE(dtype, T, (nhwc::k_tail_mid_bwd<T><<<bgrid, bnl::kT, bnl::smem_bytes(bg, dtype), s>>>(
+        (const T*)z, (const T*)dy, (const T*)c, (T*)dz, bg, H * W, relu ? 1 : 0, sn_save + L.g, cb, cc, bmean, brstd, bpart)));
+    if ((rc = launch_status())) return rc;
+    bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(bpart, bg, bn_gamma, bn_training, bmean, brstd, d_bn_gamma, d_bn_beta, cdx);
+    if ((rc = launch_status())) return rc;
+    CNSN_DISPATCH_DTYPE(dtype, T,
+        (bnl::k_bn_nhwc_apply<T, true><<<bgrid, bnl::kT, 0, s>>>((const T*)c, (const T*)dz, (T*)dc, bg, 0, coef, cdx)));
     return launch_status();
 }

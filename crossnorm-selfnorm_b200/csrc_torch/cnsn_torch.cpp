@@ -439,6 +439,60 @@ struct MaxPoolNhwcNode : public torch::autograd::Function<MaxPoolNhwcNode> {
     }
 };
 
+// ---- fused bottleneck tail: bn3 -> + identity -> SelfNorm -> ReLU, channels-last (cnsn_bn_selfnorm_tail_*_nhwc) -----------
+struct TailNode : public torch::autograd::Function<TailNode> {
+    static at::Tensor forward(AutogradContext* ctx, const at::Tensor& c, const at::Tensor& res_in, bool relu,
+                              const at::Tensor& bn_w, const at::Tensor& bn_b, GateBufs bn_bufs, bool bn_training, double bn_momentum,
+                              double bn_eps, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta, GateBufs bufs,
+                              bool training, double momentum, double sn_bn_eps, double eps) {
+        const at::Tensor res = res_in.contiguous(at::MemoryFormat::ChannelsLast);
+        const c10::cuda::CUDAGuard guard(c.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        const int N = (int)c.size(0), C = (int)c.size(1), H = (int)c.size(2), W = (int)c.size(3);
+        at::Tensor bn_save = f32_buffer(c, (int64_t)cnsn_bn_nhwc_save_floats(dtype_code(c), N, C, H, W));
+        at::Tensor sn_save = f32_buffer(c, (int64_t)cnsn_selfnorm_nhwc_save_floats(dtype_code(c), N, C, H, W));
+        at::Tensor z = at::empty_like(c), y = at::empty_like(c);
+        const cnsn_gate_params g = gate_params(w, gamma, beta, &bufs);
+        check(cnsn_bn_selfnorm_tail_fwd_nhwc(c.data_ptr(), res.data_ptr(), z.data_ptr(), y.data_ptr(), relu ? 1 : 0, dtype_code(c), N, C, H, W,
+                                             bn_w.data_ptr<float>(), bn_b.data_ptr<float>(), bn_bufs.run_mean.data_ptr<float>(),
+                                             bn_bufs.run_var.data_ptr<float>(),
+                                             bn_bufs.nbt.defined() ? reinterpret_cast<long long*>(bn_bufs.nbt.data_ptr<int64_t>()) : nullptr,
+                                             bn_training ? 1 : 0, (float)bn_momentum, (float)bn_eps, bn_save.data_ptr<float>(), &g,
+                                             training ? 1 : 0, (float)momentum, (float)sn_bn_eps, (float)eps, sn_save.data_ptr<float>(), stream));
+        ctx->save_for_backward({c, z, bn_w, w, gamma, beta, bn_save, sn_save});
+        ctx->saved_data["relu"] = relu;
+        ctx->saved_data["bn_training"] = bn_training;
+        ctx->saved_data["training"] = training;
+        return y;
+    }
+
+    static variable_list backward(AutogradContext* ctx, variable_list grads) {
+        const auto saved = ctx->get_saved_variables();
+        const at::Tensor &c = saved[0], &z = saved[1], &bn_w = saved[2], &w = saved[3], &gamma = saved[4], &beta = saved[5];
+        const at::Tensor &bn_save = saved[6], &sn_save = saved[7];
+        const bool relu = ctx->saved_data["relu"].toBool(), bn_training = ctx->saved_data["bn_training"].toBool();
+        const bool training = ctx->saved_data["training"].toBool();
+        const at::Tensor dy = grads[0].contiguous(at::MemoryFormat::ChannelsLast);
+        const c10::cuda::CUDAGuard guard(c.device());
+        cudaStream_t stream = at::cuda::getCurrentCUDAStream();
+        const int N = (int)c.size(0), C = (int)c.size(1), H = (int)c.size(2), W = (int)c.size(3);
+        at::Tensor pg = f32_buffer(c, 6 * (int64_t)C);                // dw (C,2) | dgamma | dbeta | d_bn_w | d_bn_b
+        at::Tensor bn_ws = f32_buffer(c, (int64_t)cnsn_bn_nhwc_workspace_floats(dtype_code(c), N, C, H, W));
+        at::Tensor sn_ws = f32_buffer(c, (int64_t)cnsn_selfnorm_nhwc_workspace_floats(dtype_code(c), N, C, H, W));
+        at::Tensor dz = at::empty_like(c), dc = at::empty_like(c);
+        const cnsn_gate_params g = gate_params(w, gamma, beta, nullptr);
+        float* p = pg.data_ptr<float>();
+        const cnsn_gate_grads gg{p, p + 2 * C, p + 3 * C};
+        check(cnsn_bn_selfnorm_tail_bwd_nhwc(c.data_ptr(), z.data_ptr(), dy.data_ptr(), dz.data_ptr(), dc.data_ptr(), relu ? 1 : 0,
+                                             dtype_code(c), N, C, H, W, bn_w.data_ptr<float>(), bn_training ? 1 : 0,
+                                             bn_save.data_ptr<float>(), p + 4 * C, p + 5 * C, bn_ws.data_ptr<float>(), &g,
+                                             training ? 1 : 0, sn_save.data_ptr<float>(), &gg, sn_ws.data_ptr<float>(), stream));
+        at::Tensor none;
+        return {dc, dz, none, pg.narrow(0, 4 * C, C), pg.narrow(0, 5 * C, C), none, none, none, none,
+                pg.narrow(0, 0, 2 * C).view_as(w), pg.narrow(0, 2 * C, C), pg.narrow(0, 3 * C, C), none, none, none, none, none};
+    }
+};
+
 void check_gate(const at::Tensor& x, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta, const GateBufs& b) {
     const int64_t C = x.size(1);
     for (const at::Tensor* t : {&w, &gamma, &beta, &b.run_mean, &b.run_var}) {
@@ -493,6 +547,31 @@ at::Tensor maxpool_nhwc(const at::Tensor& x, int64_t k, int64_t stride, int64_t 
     return MaxPoolNhwcNode::apply(x, k, stride, pad);
 }
 
+bool bn_sn_tail_supported(const at::Tensor& c) {
+    if (!c.is_cuda() || !is_channels_last(c) || (reinterpret_cast<uintptr_t>(c.data_ptr()) & 15u)) return false;
+    const c10::cuda::CUDAGuard guard(c.device());
+    return cnsn_bn_selfnorm_tail_supported(dtype_code(c), (int)c.size(0), (int)c.size(1), (int)c.size(2), (int)c.size(3)) != 0;
+}
+
+at::Tensor bn_sn_tail(const at::Tensor& c, const at::Tensor& res, bool relu, const at::Tensor& bn_w, const at::Tensor& bn_b,
+                      const at::Tensor& bn_rm, const at::Tensor& bn_rv, const c10::optional<at::Tensor>& bn_nbt, bool bn_training,
+                      double bn_momentum, double bn_eps, const at::Tensor& w, const at::Tensor& gamma, const at::Tensor& beta,
+                      const at::Tensor& run_mean, const at::Tensor& run_var, const c10::optional<at::Tensor>& nbt, bool training,
+                      double momentum, double sn_bn_eps, double eps) {
+    require_cuda4(c);
+    TORCH_CHECK(bn_sn_tail_supported(c), "bn_sn_tail: c must be a dense, 16-byte aligned channels_last tensor of a supported shape");
+    TORCH_CHECK(res.sizes() == c.sizes() && res.scalar_type() == c.scalar_type() && res.is_cuda(), "bn_sn_tail: the residual must match c");
+    const int64_t C = c.size(1);
+    for (const at::Tensor* t : {&bn_w, &bn_b, &bn_rm, &bn_rv}) {
+        TORCH_CHECK(t->defined() && t->is_cuda() && t->scalar_type() == at::kFloat && t->is_contiguous() && t->numel() == C &&
+                    t->device() == c.device(), "bn_sn_tail: batch-norm weight, bias and running statistics must be fp32 [C] on c's device");
+    }
+    GateBufs bnb{bn_rm, bn_rv, bn_nbt.has_value() ? *bn_nbt : at::Tensor()};
+    GateBufs b{run_mean, run_var, nbt.has_value() ? *nbt : at::Tensor()};
+    check_gate(c, w, gamma, beta, b);
+    return TailNode::apply(c, res, relu, bn_w, bn_b, bnb, bn_training, bn_momentum, bn_eps, w, gamma, beta, b, training, momentum, sn_bn_eps, eps);
+}
+
 bool site_supported(const at::Tensor& x) {
     if (!x.is_cuda() || x.dim() != 4 || (reinterpret_cast<uintptr_t>(x.data_ptr()) & 15u)) return false;
     const c10::cuda::CUDAGuard guard(x.device());
@@ -534,6 +613,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
     m.def("site_supported", &site_supported);
     m.def("ibn", &ibn, "IBN / InstanceNorm2d (half == C) / BatchNorm2d (half == 0), one kernel per direction (resnet_ibn_cnsn.py:24-44)");
     m.def("ibn_resident", &ibn_resident);
+    m.def("bn_sn_tail", &bn_sn_tail, "relu?(SelfNorm(bn(c) + residual)) on channels_last tensors: the tail of a pos='post' ResNet bottleneck");
+    m.def("bn_sn_tail_supported", &bn_sn_tail_supported);
     m.def("maxpool_nhwc", &maxpool_nhwc, "nn.MaxPool2d(k, stride, pad) on a dense channels_last tensor (csrc/pool_nhwc.cu)");
     m.def("bn_nhwc", &bn_nhwc, "nn.BatchNorm2d [+ ReLU] on a dense channels_last tensor, three kernels per direction (csrc/bn_nhwc.cu)");
 }

@@ -1,4 +1,5 @@
 """Which BatchNorm2d class a host model builds its blocks with."""
+import torch
 import torch.nn as nn
 
 
@@ -19,6 +20,34 @@ def bn_relu(bn, relu, x):
     if isinstance(bn, BatchNorm2d):
         return bn(x, True)
     return relu(bn(x))
+
+
+def bn_site_relu(bn, cnsn, c, skip):
+    """``relu(cnsn(bn(c) + skip))`` -- the tail of a pos='post' ResNet bottleneck (models/imagenet/resnet_cnsn.py:113-122).
+    ONE fused operator (csrc/selfnorm_nhwc.cu, cnsn_bn_selfnorm_tail_*: bn's output is never written, its backward
+    reduction rides on the SelfNorm backward) when everything lines up -- this package's BatchNorm2d and CNSN with a
+    single-gate SelfNorm whose CrossNorm does not fire at this call, a dense channels_last CUDA tensor of a supported shape,
+    fp32 parameters, the C++ binding --, else exactly the two calls it replaces.  Same results bit for bit either way."""
+    from .. import _lib
+    from ..cnsn import CNSN, SelfNorm, _bn_momentum
+    from ..ibn import BatchNorm2d, bn_momentum
+    sn = getattr(cnsn, "selfnorm", None)
+    cn = getattr(cnsn, "crossnorm", None)
+    if (FUSE_TAIL and isinstance(bn, BatchNorm2d) and isinstance(cnsn, CNSN) and isinstance(sn, SelfNorm) and sn.f_fc is None
+            and not (cn is not None and cn.active) and c.is_cuda and c.dim() == 4 and not c.is_contiguous()
+            and bn.affine and bn.track_running_stats and bn.weight.dtype is torch.float32
+            and sn.g_fc.weight.dtype is torch.float32 and sn.g_bn.weight is not None and skip.shape == c.shape
+            and skip.dtype == c.dtype and c.dtype in (torch.float32, torch.bfloat16, torch.float16)):
+        ext = _lib.fast_binding()
+        if ext is not None and ext.bn_sn_tail_supported(c):
+            g = sn.g_bn
+            return ext.bn_sn_tail(c, skip, True, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.num_batches_tracked,
+                                  bn.training, bn_momentum(bn), float(bn.eps), sn.g_fc.weight, g.weight, g.bias, g.running_mean,
+                                  g.running_var, g.num_batches_tracked, g.training, _bn_momentum(g), float(g.eps), 1e-12)
+    return cnsn(bn(c), skip, True)
+
+
+FUSE_TAIL = True        # module-wide switch (A/B measurements, tests): False -> always the two calls
 
 
 class MaxPool2d(nn.MaxPool2d):

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from ._norm import batchnorm2d_for, bn_relu, maxpool2d_for
+from ._norm import batchnorm2d_for, bn_relu, bn_site_relu, maxpool2d_for
 
 _POSITIONS = ("residual", "pre", "post", "identity")
 _EXPANSION = 4
@@ -72,14 +72,14 @@ class Bottleneck(nn.Module):
             x = h                                        # the IBN host feeds the projection from the site's output (:98-99,:112-113)
         h = bn_relu(self.bn1, self.relu, self.conv1(h))
         h = bn_relu(self.bn2, self.relu, self.conv2(h))
-        h = self.bn3(self.conv3(h))
         skip = x if self.downsample is None else self.downsample(x)
+        if self.fuse_post:                                # relu(cnsn(bn3(conv3(h)) + skip)): one fused operator where possible
+            return bn_site_relu(self.bn3, self.cnsn, self.conv3(h), skip)
+        h = self.bn3(self.conv3(h))
         if self.pos == "residual":
             h = self.cnsn(h)
         elif self.pos == "identity":
             skip = self.cnsn(skip)
-        if self.fuse_post:
-            return self.cnsn(h, skip, True)               # relu(cnsn(h + skip)) in one kernel pair
         h = h + skip
         if self.IN is not None:
             h = self.IN(h)

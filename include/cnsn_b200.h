@@ -335,6 +335,27 @@ int cnsn_maxpool_nhwc_fwd(const void* x, void* y, unsigned char* code, int dtype
 int cnsn_maxpool_nhwc_bwd(const void* dy, const unsigned char* code, void* dx, int dtype, int N, int C, int H, int W,
                           int k, int stride, int pad, void* stream);
 
+/* The tail of a pos='post' ResNet bottleneck as one operator, channels-last (models/imagenet/resnet_cnsn.py:113-122):
+ *     out = self.bn3(out); out += identity; out = self.cnsn(out); out = self.relu(out)          (SelfNorm-only site)
+ * c: the raw conv3 output, res: the identity branch, z (written): bn3(c) + res -- what backward needs --, y: the result.
+ * Backward: dz (written) is the gradient of the residual branch, dc the gradient of c; d_bn_gamma / d_bn_beta / dg are
+ * WRITTEN.  bn_save / bn_workspace as cnsn_bn_nhwc_*, sn_save / sn_workspace as cnsn_selfnorm_block_*_nhwc.  Bit-identical
+ * to cnsn_bn_nhwc_fwd followed by cnsn_selfnorm_block_fwd_nhwc (and the two backward calls in reverse order); it moves
+ * 2 S less forward (bn3's output is never written) and 1 S less backward. */
+int cnsn_bn_selfnorm_tail_supported(int dtype, int N, int C, int H, int W);
+int cnsn_bn_selfnorm_tail_fwd_nhwc(const void* c, const void* res, void* z, void* y, int relu, int dtype,
+                                   int N, int C, int H, int W,
+                                   const float* bn_gamma, const float* bn_beta, float* bn_run_mean, float* bn_run_var,
+                                   long long* bn_nbt, int bn_training, float bn_momentum, float bn_eps, float* bn_save,
+                                   const cnsn_gate_params* g, int training, float momentum, float sn_bn_eps, float eps,
+                                   float* sn_save, void* stream);
+int cnsn_bn_selfnorm_tail_bwd_nhwc(const void* c, const void* z, const void* dy, void* dz, void* dc, int relu, int dtype,
+                                   int N, int C, int H, int W,
+                                   const float* bn_gamma, int bn_training, const float* bn_save,
+                                   float* d_bn_gamma, float* d_bn_beta, float* bn_workspace,
+                                   const cnsn_gate_params* g, int training, const float* sn_save,
+                                   const cnsn_gate_grads* dg, float* sn_workspace, void* stream);
+
 /* ---------------------------------------------------------------- JSD consistency -----------
  * The Jensen-Shannon consistency term of the 3-view steps, imagenet.py:367-376 / cifar.py:173-182:
  *   p_v = softmax(logits_v); lm = log(clamp(mean_v p_v, 1e-7, 1));

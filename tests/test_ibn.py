@@ -465,3 +465,66 @@ def test_maxpool_channels_last_matches_torch(shape, dtype, k, stride, pad, bindi
         assert torch.allclose(x.grad.float(), xr.grad, rtol=1e-2, atol=1e-2)
     # NCHW input: torch's own kernel
     assert torch.equal(torch.nan_to_num(ours(x0.to(dev)), nan=-1.0), torch.nan_to_num(ref(x0.to(dev)), nan=-1.0))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape,dtype", [((8, 64, 14, 14), torch.float32), ((6, 256, 8, 8), torch.float32), ((4, 2048, 7, 7), torch.float32),
+                                         ((5, 16, 50, 50), torch.float32), ((16, 32, 20, 20), torch.bfloat16), ((3, 64, 13, 11), torch.float16),
+                                         ((32, 256, 56, 56), torch.bfloat16)])
+@pytest.mark.parametrize("training", [True, False])
+def test_bottleneck_tail_fused_equals_the_two_operators(shape, dtype, training):
+    """relu(cnsn(bn3(c) + skip)) as ONE operator (hosts._norm.bn_site_relu -> cnsn_bn_selfnorm_tail_*_nhwc) against the two
+    operators it replaces (BatchNorm2d, then the SelfNorm block), both on channels_last tensors: every output, gradient,
+    parameter gradient and buffer BIT-EQUAL -- the fused kernels round where the sequence rounds and sum in the same order --
+    with 10 launches instead of 12 (11 / 9 in eval mode: no statistics kernel)."""
+    import copy
+    import cnsn_b200._lib as L
+    import cnsn_b200.cnsn as M
+    import cnsn_b200.hosts._norm as HN
+    from cnsn_b200.ibn import BatchNorm2d
+    dev = "cuda:0"
+    cl = torch.channels_last
+    g = torch.Generator().manual_seed(sum(shape))
+    C = shape[1]
+    c0 = (torch.randn(shape, generator=g) * (0.5 + torch.rand(1, C, 1, 1, generator=g)) + 0.3 * torch.randn(1, C, 1, 1, generator=g)).to(dtype)
+    s0 = torch.randn(shape, generator=g).to(dtype)
+    dy0 = torch.randn(shape, generator=g).to(dtype)
+    torch.manual_seed(3)
+    bn = BatchNorm2d(C).to(dev).train(training)
+    site = M.CNSN(None, M.SelfNorm(C)).to(dev).train(training)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(C, generator=g) + 0.5); bn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+        bn.running_mean.copy_(torch.randn(C, generator=g) * 0.1); bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+        site.selfnorm.g_bn.weight.copy_(torch.rand(C, generator=g) + 0.5); site.selfnorm.g_bn.bias.copy_(torch.randn(C, generator=g) * 0.3)
+    res = []
+    for fused in (True, False):
+        b, st = copy.deepcopy(bn), copy.deepcopy(site)
+        c = c0.to(dev).contiguous(memory_format=cl).requires_grad_(True)
+        sk = s0.to(dev).contiguous(memory_format=cl).requires_grad_(True)
+        HN.FUSE_TAIL = fused
+        try:
+            n0 = L.launch_count()
+            y = HN.bn_site_relu(b, st, c, sk)
+            y.backward(dy0.to(dev).contiguous(memory_format=cl))
+            torch.cuda.synchronize()
+            launched = L.launch_count() - n0
+        finally:
+            HN.FUSE_TAIL = True
+        assert launched == ((10 if fused else 12) if training else (9 if fused else 11)), (fused, launched)
+        assert y.is_contiguous(memory_format=cl) and c.grad.is_contiguous(memory_format=cl)
+        res.append([y.detach(), c.grad, sk.grad, b.weight.grad, b.bias.grad, b.running_mean, b.running_var, b.num_batches_tracked,
+                    st.selfnorm.g_fc.weight.grad, st.selfnorm.g_bn.weight.grad, st.selfnorm.g_bn.bias.grad,
+                    st.selfnorm.g_bn.running_mean, st.selfnorm.g_bn.running_var])
+    names = ("y", "dc", "dskip", "d bn.weight", "d bn.bias", "bn.running_mean", "bn.running_var", "bn.num_batches_tracked",
+             "d g_fc.weight", "d g_bn.weight", "d g_bn.bias", "g_bn.running_mean", "g_bn.running_var")
+    for name, a, b in zip(names, res[0], res[1]):
+        assert torch.equal(a, b), (name, float((a.double() - b.double()).abs().max()))
+    # and against torch in fp64 (the sequence itself is covered operator by operator elsewhere)
+    ref_bn = torch.nn.BatchNorm2d(C).to(dev).double().train(training)
+    ref_bn.load_state_dict({k: (v.double() if v.dtype.is_floating_point else v) for k, v in bn.state_dict().items()})
+    from oracle import eager_modules as E
+    ref_sn = E.SelfNorm(C).to(dev).double().train(training)
+    ref_sn.load_state_dict({k: (v.double() if v.dtype.is_floating_point else v) for k, v in site.selfnorm.state_dict().items()})
+    yr = torch.relu(ref_sn(ref_bn(c0.to(dev).double()) + s0.to(dev).double()))
+    tol = 2e-5 if dtype == torch.float32 else 3e-2
+    assert float((res[0][0].double() - yr).abs().max()) <= tol * max(1.0, float(yr.abs().max()))
