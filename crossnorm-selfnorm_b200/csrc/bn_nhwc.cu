@@ -61,8 +61,8 @@ extern "C" int cnsn_bn_nhwc_fwd(const void* x, void* y, int dtype, int N, int C,
     }
     bnl::k_bn_nhwc_fold<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, beta, run_mean, run_var, nbt, training, momentum, eps, mean, rstd, coef);
     if ((rc = launch_status())) return rc;
-    CNSN_DISPATCH_DTYPE(dtype, T,
-        (bnl::k_bn_nhwc_apply<T, false><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, relu ? 1 : 0, coef, nullptr)));
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_BOOL(relu != 0, RELU,
+        (bnl::k_bn_nhwc_apply<T, false, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, coef, nullptr))));
     return launch_status();
 }
 
@@ -81,12 +81,12 @@ extern "C" int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dty
     float* cdx = workspace + 2 * (size_t)g.G * C;
     cudaStream_t s = (cudaStream_t)stream;
     const dim3 grid((unsigned)g.G, (unsigned)(g.CG / g.CGB));
-    CNSN_DISPATCH_DTYPE(dtype, T, (bnl::k_bn_nhwc_reduce<T><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>(
-        (const T*)x, (const T*)dy, g, relu ? 1 : 0, mean, rstd, coef, part)));
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_BOOL(relu != 0, RELU, (bnl::k_bn_nhwc_reduce<T, RELU><<<grid, bnl::kT, bnl::smem_bytes(g, dtype), s>>>(
+        (const T*)x, (const T*)dy, g, mean, rstd, coef, part))));
     if ((rc = launch_status())) return rc;
     bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, training, mean, rstd, dgamma, dbeta, cdx);
     if ((rc = launch_status())) return rc;
-    CNSN_DISPATCH_DTYPE(dtype, T,
-        (bnl::k_bn_nhwc_apply<T, true><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, relu ? 1 : 0, coef, cdx)));
+    CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_BOOL(relu != 0, RELU,
+        (bnl::k_bn_nhwc_apply<T, true, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, coef, cdx))));
     return launch_status();
 }

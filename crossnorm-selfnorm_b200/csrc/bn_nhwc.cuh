@@ -146,8 +146,8 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold(const float2* __
 }
 
 // per chunk and channel: (sum d, sum d * xhat)
-template <typename T>
-__global__ void __launch_bounds__(kT, 4) k_bn_nhwc_reduce(const T* __restrict__ x, const T* __restrict__ dy, const Geom g, int relu,
+template <typename T, bool RELU>
+__global__ void __launch_bounds__(kT, 4) k_bn_nhwc_reduce(const T* __restrict__ x, const T* __restrict__ dy, const Geom g,
                                                        const float* __restrict__ save_mean, const float* __restrict__ save_rstd,
                                                        const float2* __restrict__ coef, float2* __restrict__ part) {
     constexpr int V = VecOf<T>::n;
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_reduce(const T* __restrict__ 
 #pragma unroll
     for (int e = 0; e < V; ++e) {
         mean[e] = save_mean[c0 + e];
-        const float2 f = coef[c0 + e];
+        const float2 f = RELU ? coef[c0 + e] : make_float2(0.f, 0.f);
         fs[e] = f.x; fb[e] = f.y; a[e] = 0.f; b[e] = 0.f;
     }
 #pragma unroll 4
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_reduce(const T* __restrict__ 
         unpack<T>(__ldg(vd + (size_t)r * g.CG), dv);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const float d = (relu && !(fmaf(fs[e], xv[e], fb[e]) > 0.f)) ? 0.f : dv[e];
+            const float d = (RELU && !(fmaf(fs[e], xv[e], fb[e]) > 0.f)) ? 0.f : dv[e];
             a[e] += d;
             b[e] = fmaf(d, xv[e] - mean[e], b[e]);
         }
@@ -215,9 +215,12 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2
     }
 }
 
-template <typename T, bool BWD>
+// RELU: compile-time, so that the backward without a ReLU (bn3 of a bottleneck, the projection's batch norm: the widest
+// tensors) does not carry the forward map's coefficients in registers
+template <typename T, bool BWD, bool RELU>
 __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_apply(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
-                                                      int relu, const float2* __restrict__ coef, const float* __restrict__ cdx) {
+                                                      const float2* __restrict__ coef, const float* __restrict__ cdx) {
+    constexpr bool relu = RELU;
     constexpr int V = VecOf<T>::n;
     const int W = g.CGB * V;
     const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
@@ -231,7 +234,7 @@ __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_apply(const T* __restrict__ x
     float fs[V], fb[V], ca[V], cb[V], cc[V];
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-        const float2 f = coef[c0 + e];
+        const float2 f = (!BWD || RELU) ? coef[c0 + e] : make_float2(0.f, 0.f);
         fs[e] = f.x; fb[e] = f.y;
         ca[e] = BWD ? cdx[c0 + e] : 0.f; cb[e] = BWD ? cdx[g.C + c0 + e] : 0.f; cc[e] = BWD ? cdx[2 * g.C + c0 + e] : 0.f;
     }
@@ -242,11 +245,11 @@ __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_apply(const T* __restrict__ x
         if (BWD) unpack<T>(ldg_stream(vd + (size_t)r * g.CG), dv);
 #pragma unroll
         for (int e = 0; e < V; ++e) {
-            const float y = fmaf(fs[e], xv[e], fb[e]);
             if (BWD) {
-                const float d = (relu && !(y > 0.f)) ? 0.f : dv[e];
+                const float d = (relu && !(fmaf(fs[e], xv[e], fb[e]) > 0.f)) ? 0.f : dv[e];
                 o[e] = fmaf(ca[e], d, fmaf(cb[e], xv[e], cc[e]));
             } else {
+                const float y = fmaf(fs[e], xv[e], fb[e]);
                 o[e] = relu ? fmaxf(y, 0.f) : y;
             }
         }

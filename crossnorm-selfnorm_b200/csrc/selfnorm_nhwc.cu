@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(kT, 4) k_nhwc_apply(const T* __restrict__ z, c
 // the residual branch --, and on the way accumulates bn3's reduction (sum dz, sum dz * (c - mean)) * (1, rstd) per chunk and
 // column: the unfused sequence would write dz, then read it and c again for that.
 template <typename T>
-__global__ void __launch_bounds__(bnl::kT, 3) k_tail_mid_bwd(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ c,
+__global__ void __launch_bounds__(bnl::kT, 4) k_tail_mid_bwd(const T* __restrict__ z, const T* __restrict__ dy, const T* __restrict__ c,
                                                              T* __restrict__ dz, const bnl::Geom g, int HW, int relu,
                                                              const float* __restrict__ gate, const float* __restrict__ cb,
                                                              const float* __restrict__ cc, const float* __restrict__ bn_mean,
@@ -544,6 +544,6 @@ extern "C" int cnsn_bn_selfnorm_tail_bwd_nhwc(const void* c, const void* z, cons
     bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(bpart, bg, bn_gamma, bn_training, bmean, brstd, d_bn_gamma, d_bn_beta, cdx);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T,
-        (bnl::k_bn_nhwc_apply<T, true><<<bgrid, bnl::kT, 0, s>>>((const T*)c, (const T*)dz, (T*)dc, bg, 0, coef, cdx)));
+        (bnl::k_bn_nhwc_apply<T, true, false><<<bgrid, bnl::kT, 0, s>>>((const T*)c, (const T*)dz, (T*)dc, bg, coef, cdx)));
     return launch_status();
 }
