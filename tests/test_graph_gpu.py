@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 DEV = torch.device("cuda", 0)
 
 
-def _run(capture, steps=8, cn_prob=0.4):
+def _run(capture, steps=8, cn_prob=0.4, channels_last=False):
     from cnsn_b200.train import GraphedStep, make_optimizer, wrn40_2
     torch.manual_seed(0)
     np.random.seed(0)
@@ -18,6 +18,9 @@ def _run(capture, steps=8, cn_prob=0.4):
     g = torch.Generator().manual_seed(1)
     x = torch.randn(64, 3, 32, 32, generator=g).to(DEV)
     y = torch.randint(0, 10, (64,), generator=g).to(DEV)
+    if channels_last:                                     # the layout train.bench_wrn runs in
+        net = net.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
     before = {k: v.clone() for k, v in net.state_dict().items()}
     gs = GraphedStep(net, x, y, 1, capture=capture)
     assert (gs.graph is not None) == capture
@@ -29,12 +32,13 @@ def _run(capture, steps=8, cn_prob=0.4):
     return losses, {k: v.clone() for k, v in net.state_dict().items()}
 
 
-def test_graph_replay_is_the_eager_step():
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_graph_replay_is_the_eager_step(channels_last):
     saved = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark)
     torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = True, False
     try:
-        le, se = _run(False)
-        lg, sg = _run(True)
+        le, se = _run(False, channels_last=channels_last)
+        lg, sg = _run(True, channels_last=channels_last)
     finally:
         torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = saved
     np.random.seed(3)

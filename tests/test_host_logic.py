@@ -395,3 +395,44 @@ def test_cnsn_site_fusion_declines_what_the_kernels_do_not_cover(mod):
     assert calls_of(plain) == ["site_fwd"]
     only_cn = mod.CNSN(mod.CrossNorm("neither", 1), None).train()
     assert calls_of(only_cn) == ["crossnorm_fwd"]
+
+
+def test_graphed_step_flat_gradients_follow_channels_last_parameters():
+    """train.GraphedStep keeps every gradient as a view of ONE flat buffer (the single all-reduce of the data-parallel step).
+    For channels_last parameters the views carry the parameters' strides (autograd's gradient layout contract), and the
+    step trains exactly like the plain eager step (CPU: no graph capture, same arithmetic)."""
+    import copy
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from cnsn_b200.train import GraphedStep
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.c1, self.c2, self.fc = nn.Conv2d(3, 8, 3, padding=1), nn.Conv2d(8, 4, 1), nn.Linear(4, 5)
+
+        def forward(self, x, aug=False):
+            return self.fc(F.relu(self.c2(F.relu(self.c1(x)))).mean((2, 3)))
+
+    torch.manual_seed(0)
+    a = Net().to(memory_format=torch.channels_last)
+    b = copy.deepcopy(a)
+    x = torch.randn(6, 3, 8, 8).contiguous(memory_format=torch.channels_last)
+    y = torch.randint(0, 5, (6,))
+    gs = GraphedStep(a, x, y, 1, capture=False)
+    for p in a.parameters():
+        live = [d for d in range(p.dim()) if p.size(d) > 1]          # the stride of a size-1 dimension is arbitrary
+        assert [p.grad.stride(d) for d in live] == [p.stride(d) for d in live]
+        assert p.grad.untyped_storage().data_ptr() == gs.flat.untyped_storage().data_ptr()
+    assert not a.c1.weight.is_contiguous() and a.c1.weight.grad.is_contiguous(memory_format=torch.channels_last)
+    oa, ob = torch.optim.SGD(a.parameters(), 0.1, momentum=0.9), torch.optim.SGD(b.parameters(), 0.1, momentum=0.9)
+    for _ in range(3):
+        la = gs.step(x, y, oa, None, 0.0)
+        ob.zero_grad()
+        lb = F.cross_entropy(b(x), y)
+        lb.backward()
+        ob.step()
+        assert abs(la - float(lb)) < 1e-6
+    for p, q in zip(a.parameters(), b.parameters()):
+        assert torch.allclose(p, q, atol=1e-6)
+        assert p.grad.untyped_storage().data_ptr() == gs.flat.untyped_storage().data_ptr()      # still views after the steps
