@@ -248,6 +248,8 @@ def train_summary(train):
             out[short + "_ms"] = round(t["ms_per_step"], 2)
     if "graph" in train:
         out["wrn_graph"] = train["graph"]
+    if "memory_format" in train:
+        out["memory_format"] = train["memory_format"]
     return out
 
 

@@ -258,3 +258,26 @@ def test_reference_checkpoint_round_trip(fake, tmp_path, capsys):
     bare = dict(ref.state_dict(), **{"aux.weight": torch.zeros(1)})
     missing, unexpected, _ = load_reference_checkpoint(net, bare)
     assert missing == [] and unexpected == ["aux.weight"]
+
+
+def test_bottleneck_tail_helper_falls_back_to_the_two_calls_on_cpu(fake):
+    """hosts._norm.bn_site_relu is relu(cnsn(bn(c) + skip)); without a CUDA channels_last tensor it IS the two calls it
+    replaces (the fused operator is a GPU path; here the operators run on the oracle-backed stand-in), and
+    hosts._norm.MaxPool2d is nn.MaxPool2d."""
+    import torch
+    import torch.nn as nn
+    import cnsn_b200.cnsn as M
+    from cnsn_b200.hosts._norm import MaxPool2d, bn_site_relu
+    from cnsn_b200.ibn import BatchNorm2d
+    torch.manual_seed(0)
+    bn = BatchNorm2d(8).train()
+    site = M.CNSN(None, M.SelfNorm(8)).train()
+    c, skip = torch.randn(4, 8, 6, 6), torch.randn(4, 8, 6, 6)
+    import copy
+    bn2, site2 = copy.deepcopy(bn), copy.deepcopy(site)
+    a = bn_site_relu(bn, site, c, skip)
+    b = torch.relu(site2(bn2(c) + skip))
+    assert torch.allclose(a, b, atol=1e-6) and torch.equal(bn.running_mean, bn2.running_mean)
+    x = torch.randn(2, 4, 9, 9)
+    assert torch.equal(MaxPool2d(3, 2, 1)(x), nn.MaxPool2d(3, 2, 1)(x))
+    assert torch.equal(MaxPool2d(3, 2, 1)(x.contiguous(memory_format=torch.channels_last)), nn.MaxPool2d(3, 2, 1)(x))
