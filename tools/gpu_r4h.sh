@@ -1,0 +1,20 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_ibn.py tests/test_gpu_parity.py tests/test_robustness_gpu.py -m gpu -q -k "bottleneck_tail or channels_last or non_finite" 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_models_gpu.py tests/test_graph_gpu.py -m gpu -q 2>&1 | tail -2
+timeout 1200 python - > gpurun_out/r4h_bench.log 2>&1 <<'PY'
+import sys, json; sys.path.insert(0, '.')
+import torch
+from cnsn_b200 import train
+dev = torch.device("cuda", 0)
+keys = ("value", "ms_per_step", "memory_format")
+r = train.bench_resnet50(dev, 1, 0, steps=8, warmup=3)
+print("r50", json.dumps({k: r[k] for k in keys}), flush=True)
+torch.cuda.empty_cache()
+r = train.bench_resnet50_jsd(dev, 1, 0, steps=5, warmup=3)
+print("jsd", json.dumps({k: r[k] for k in keys}), flush=True)
+torch.cuda.empty_cache()
+r = train.bench_wrn(dev, 1, 0, steps=40, warmup=8, cn_prob=0.25, fuse_post=True)
+print("wrn", json.dumps({k: r[k] for k in keys}), flush=True)
+PY
+cat gpurun_out/r4h_bench.log | tail -3
