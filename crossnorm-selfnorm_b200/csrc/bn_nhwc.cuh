@@ -94,6 +94,8 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold(const float2* __
                                                          float* __restrict__ save_rstd, float2* __restrict__ coef) {
     __shared__ double sm[kFoldT / 32];
     const int c = blockIdx.x;
+    // the channel's scalars first: their (cold) loads overlap the loads of the chunk pairs instead of trailing the reductions
+    const float ga = gamma[c], be = beta[c], rm0 = run_mean[c], rv0 = run_var[c];
     float mean, rstd;
     if (training) {
         constexpr int kHold = 8;                             // G <= 592 in practice: every pair stays in registers
@@ -130,18 +132,18 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold(const float2* __
         mean = (float)ma;
         rstd = 1.f / sqrtf((float)(qa / cnt) + eps);
         if (threadIdx.x == 0) {
-            run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * mean;
-            run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)(qa / (cnt - 1.0));
+            run_mean[c] = (1.f - momentum) * rm0 + momentum * mean;
+            run_var[c] = (1.f - momentum) * rv0 + momentum * (float)(qa / (cnt - 1.0));
             if (nbt && c == 0) *nbt += 1;
         }
     } else {
-        mean = run_mean[c];
-        rstd = 1.f / sqrtf(run_var[c] + eps);
+        mean = rm0;
+        rstd = 1.f / sqrtf(rv0 + eps);
     }
     if (threadIdx.x == 0) {
         save_mean[c] = mean; save_rstd[c] = rstd;
-        const float sc = rstd * gamma[c];
-        coef[c] = make_float2(sc, beta[c] - mean * sc);
+        const float sc = rstd * ga;
+        coef[c] = make_float2(sc, be - mean * sc);
     }
 }
 
@@ -199,6 +201,7 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2
                                                              float* __restrict__ dbeta, float* __restrict__ cdx) {
     __shared__ double sm[kFoldT / 32];
     const int c = blockIdx.x;
+    const float ga = gamma[c], mean = save_mean[c], rstd = save_rstd[c];     // early: overlaps the loads of the chunk pairs
     double ta = 0.0, tb = 0.0;
 #pragma unroll 4
     for (int j = threadIdx.x; j < g.G; j += kFoldT) { const float2 p = __ldcg(part + (size_t)j * g.C + c); ta += (double)p.x; tb += (double)p.y; }
@@ -208,8 +211,7 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2
         dbeta[c] = (float)ta; dgamma[c] = (float)tb;
         const float inv = training ? 1.f / (float)g.R : 0.f;     // eval: the statistics are constants, nothing to remove
         const float ma = (float)ta * inv, mb = (float)tb * inv;
-        const float mean = save_mean[c], rstd = save_rstd[c];
-        const float ca = gamma[c] * rstd;
+        const float ca = ga * rstd;
         const float cb = -ca * mb * rstd;
         cdx[c] = ca; cdx[g.C + c] = cb; cdx[2 * g.C + c] = -ca * ma - cb * mean;
     }
