@@ -62,7 +62,7 @@ extern "C" int cnsn_bn_nhwc_fwd(const void* x, void* y, int dtype, int N, int C,
     bnl::k_bn_nhwc_fold<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, beta, run_mean, run_var, nbt, training, momentum, eps, mean, rstd, coef);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_BOOL(relu != 0, RELU,
-        (bnl::k_bn_nhwc_apply<T, false, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, coef, nullptr))));
+        (bnl::k_bn_nhwc_apply<T, false, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, nullptr, (T*)y, g, coef, nullptr, 1))));
     return launch_status();
 }
 
@@ -87,6 +87,6 @@ extern "C" int cnsn_bn_nhwc_bwd(const void* x, const void* dy, void* dx, int dty
     bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(part, g, gamma, training, mean, rstd, dgamma, dbeta, cdx);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T, CNSN_DISPATCH_BOOL(relu != 0, RELU,
-        (bnl::k_bn_nhwc_apply<T, true, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, coef, cdx))));
+        (bnl::k_bn_nhwc_apply<T, true, RELU><<<grid, bnl::kT, 0, s>>>((const T*)x, (const T*)dy, (T*)dx, g, coef, cdx, 1))));
     return launch_status();
 }

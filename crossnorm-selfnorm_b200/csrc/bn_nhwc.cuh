@@ -221,12 +221,14 @@ static __global__ void __launch_bounds__(kFoldT) k_bn_nhwc_fold_bwd(const float2
 // tensors) does not carry the forward map's coefficients in registers
 template <typename T, bool BWD, bool RELU>
 __global__ void __launch_bounds__(kT, 4) k_bn_nhwc_apply(const T* __restrict__ x, const T* __restrict__ dy, T* __restrict__ out, const Geom g,
-                                                      const float2* __restrict__ coef, const float* __restrict__ cdx) {
+                                                      const float2* __restrict__ coef, const float* __restrict__ cdx, int reverse) {
     constexpr bool relu = RELU;
     constexpr int V = VecOf<T>::n;
     const int W = g.CGB * V;
     const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
-    const long long row0 = (long long)blockIdx.x * g.rows;
+    // reverse: chunks in REVERSE launch order -- the kernel in front of this one (statistics / reduction) read the same tensors
+    // front to back, so the last chunks are the ones still in L2
+    const long long row0 = (long long)(reverse ? gridDim.x - 1 - blockIdx.x : blockIdx.x) * g.rows;
     const long long nrows = min(g.rows, g.R - row0);
     const size_t vb = (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
     const uint4* vx = reinterpret_cast<const uint4*>(x) + vb;

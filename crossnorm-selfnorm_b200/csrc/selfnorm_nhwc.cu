@@ -213,7 +213,8 @@ __global__ void __launch_bounds__(kT, 4) k_nhwc_apply(const T* __restrict__ z, c
                                                    int relu, const float* __restrict__ gate, const float* __restrict__ cb,
                                                    const float* __restrict__ cc) {
     constexpr int V = VecOf<T>::n;
-    const int n = blockIdx.x / g.S, s = blockIdx.x - n * g.S;
+    const unsigned bx = gridDim.x - 1 - blockIdx.x;          // reverse launch order: the statistics / reduction kernel in front read
+    const int n = bx / g.S, s = bx - n * g.S;                // front to back, the last slabs are the ones still in L2
     const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
     const int row0 = s * g.rows, nrows = min(g.rows, g.HW - row0);
     const size_t vbase = ((size_t)n * g.HW + row0) * g.CG + (size_t)blockIdx.y * g.CGB + cg;
@@ -263,7 +264,8 @@ __global__ void __launch_bounds__(bnl::kT, 4) k_tail_mid_bwd(const T* __restrict
     float* s_a = sm;
     float* s_b = sm + g.RL * W;
     const int cg = threadIdx.x % g.CGB, rl = threadIdx.x / g.CGB;
-    const long long row0 = (long long)blockIdx.x * g.rows;
+    const unsigned bx = gridDim.x - 1 - blockIdx.x;          // reverse launch order (see k_nhwc_apply)
+    const long long row0 = (long long)bx * g.rows;
     const long long nrows = min(g.rows, g.R - row0);
     const size_t vb = (size_t)row0 * g.CG + (size_t)blockIdx.y * g.CGB + cg;
     const uint4* vz = reinterpret_cast<const uint4*>(z) + vb;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(bnl::kT, 4) k_tail_mid_bwd(const T* __restrict
         double ta = 0.0, tb = 0.0;
         for (int l = 0; l < g.RL; ++l) { ta += (double)s_a[l * W + ch]; tb += (double)s_b[l * W + ch]; }
         tb *= (double)bn_rstd[blockIdx.y * W + ch];
-        part[(size_t)blockIdx.x * g.C + (size_t)blockIdx.y * W + ch] = make_float2((float)ta, (float)tb);
+        part[(size_t)bx * g.C + (size_t)blockIdx.y * W + ch] = make_float2((float)ta, (float)tb);
     }
 }
 
@@ -544,6 +546,6 @@ extern "C" int cnsn_bn_selfnorm_tail_bwd_nhwc(const void* c, const void* z, cons
     bnl::k_bn_nhwc_fold_bwd<<<C, bnl::kFoldT, 0, s>>>(bpart, bg, bn_gamma, bn_training, bmean, brstd, d_bn_gamma, d_bn_beta, cdx);
     if ((rc = launch_status())) return rc;
     CNSN_DISPATCH_DTYPE(dtype, T,
-        (bnl::k_bn_nhwc_apply<T, true, false><<<bgrid, bnl::kT, 0, s>>>((const T*)c, (const T*)dz, (T*)dc, bg, coef, cdx)));
+        (bnl::k_bn_nhwc_apply<T, true, false><<<bgrid, bnl::kT, 0, s>>>((const T*)c, (const T*)dz, (T*)dc, bg, coef, cdx, 0)));      // the kernel in front ran back to front
     return launch_status();
 }
